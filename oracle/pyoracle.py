@@ -1,0 +1,320 @@
+"""ctypes binding of the CPU oracle (oracle/liblvreg_oracle.so).
+
+TEST INFRASTRUCTURE: imported only by tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs.  The product package never imports this.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "liblvreg_oracle.so")
+
+
+def build(force=False):
+    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".cpp", ".h"))]
+    if (not force and os.path.exists(_LIB)
+            and all(os.path.getmtime(_LIB) >= os.path.getmtime(s) for s in srcs)):
+        return _LIB
+    subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return _LIB
+
+
+class Params(C.Structure):
+    _fields_ = [("corner_leaf", C.c_float), ("surf_leaf", C.c_float),
+                ("edge_min_valid", C.c_int), ("surf_min_valid", C.c_int),
+                ("max_iters", C.c_int), ("knn_gate_sq", C.c_float),
+                ("line_eig_ratio", C.c_float), ("plane_tol", C.c_float),
+                ("min_weight", C.c_float), ("min_matches", C.c_int),
+                ("degeneracy_eig", C.c_float), ("conv_deg", C.c_float), ("conv_cm", C.c_float),
+                ("reference_quirks", C.c_int), ("keyframe_search_radius", C.c_float),
+                ("keyframe_density", C.c_float), ("rotation_tolerance", C.c_float),
+                ("z_tolerance", C.c_float), ("num_threads", C.c_int)]
+
+
+class Result(C.Structure):
+    _fields_ = [("status", C.c_int), ("iterations", C.c_int), ("converged", C.c_int),
+                ("degenerate", C.c_int), ("n_sel", C.c_int * 32),
+                ("pose_iter", (C.c_float * 6) * 32)]
+
+
+class LmState(C.Structure):
+    _fields_ = [("is_degenerate", C.c_int), ("matP", C.c_float * 36)]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(_LIB)
+        _lib.orc_voxelgrid.restype = C.c_size_t
+        _lib.orc_kdtree_build.restype = C.c_void_p
+        _lib.orc_kdtree_radius.restype = C.c_size_t
+        _lib.orc_mo_create.restype = C.c_void_p
+        _lib.orc_mo_num_keyframes.restype = C.c_size_t
+        _lib.orc_mo_extract_nearby.restype = C.c_size_t
+        _lib.orc_mo_map_size.restype = C.c_size_t
+    return _lib
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def default_params(**kw):
+    p = Params()
+    lib().orc_default_params(C.byref(p))
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+# ---- dense math -------------------------------------------------------------------------
+def jacobi_eigen(A):
+    A = _f32(A)
+    n = A.shape[0]
+    w = np.zeros(n, np.float32)
+    v = np.zeros((n, n), np.float32)
+    lib().orc_jacobi_eigen(_p(A), n, _p(w), _p(v))
+    return w, v
+
+
+def qr_solve(A, b):
+    A = _f32(A)
+    b = _f32(b).reshape(A.shape[0], -1)
+    x = np.zeros_like(b)
+    ok = lib().orc_qr_solve(_p(A), _p(b), A.shape[0], b.shape[1], _p(x))
+    return ok, x
+
+
+def lu_solve(A, B):
+    A = _f32(A)
+    B = _f32(B).reshape(A.shape[0], -1)
+    X = np.zeros_like(B)
+    ok = lib().orc_lu_solve(_p(A), _p(B), A.shape[0], B.shape[1], _p(X))
+    return ok, X
+
+
+def gemm(A, B):
+    A = _f32(A)
+    B = _f32(B)
+    out = np.zeros((A.shape[0], B.shape[1]), np.float32)
+    lib().orc_gemm(_p(A), _p(B), A.shape[0], A.shape[1], B.shape[1], _p(out))
+    return out
+
+
+def normal_equations(A, b):
+    A = _f32(A)
+    b = _f32(b)
+    AtA = np.zeros((6, 6), np.float32)
+    Atb = np.zeros(6, np.float32)
+    lib().orc_normal_equations(_p(A), _p(b), A.shape[0], _p(AtA), _p(Atb))
+    return AtA, Atb
+
+
+def plane_fit(A5x3, b5=None):
+    A = _f32(A5x3)
+    b = _f32(np.full(5, -1.0) if b5 is None else b5)
+    x = np.zeros(3, np.float32)
+    lib().orc_colpiv_qr_solve_5x3(_p(A), _p(b), _p(x))
+    return x
+
+
+# ---- clouds -----------------------------------------------------------------------------
+def pose_to_affine(pose):
+    pose = _f32(pose)
+    T = np.zeros(12, np.float32)
+    lib().orc_pose_to_affine(_p(pose), _p(T))
+    return T
+
+
+def transform_cloud(pts, pose=None, T=None, num_threads=1):
+    pts = _f32(pts)
+    if T is None:
+        T = pose_to_affine(pose)
+    T = _f32(T)
+    out = np.zeros_like(pts)
+    lib().orc_transform_cloud(_p(pts), C.c_size_t(len(pts)), _p(T), _p(out), num_threads)
+    return out
+
+
+def voxelgrid(pts, leaf):
+    """returns (out points, per-input keys, per-output keys, passthrough)"""
+    pts = _f32(pts)
+    n = len(pts)
+    out = np.zeros((max(n, 1), 4), np.float32)
+    keys = np.zeros(max(n, 1), np.uint32)
+    okeys = np.zeros(max(n, 1), np.uint32)
+    pt = C.c_int(0)
+    m = lib().orc_voxelgrid(_p(pts), C.c_size_t(n), C.c_float(leaf), _p(out), _p(keys), _p(okeys),
+                            C.byref(pt))
+    return out[:m].copy(), keys[:n].copy(), okeys[:m].copy(), bool(pt.value)
+
+
+# ---- kNN ----------------------------------------------------------------------------------
+def knn5_brute(map_pts, queries, num_threads=8):
+    map_pts = _f32(map_pts)
+    queries = _f32(queries)
+    nq = len(queries)
+    idx = np.zeros((nq, 5), np.int32)
+    d2 = np.zeros((nq, 5), np.float32)
+    lib().orc_knn5_brute(_p(map_pts), C.c_size_t(len(map_pts)), _p(queries), C.c_size_t(nq),
+                         _p(idx), _p(d2), num_threads)
+    return idx, d2
+
+
+class KdTree:
+    def __init__(self, map_pts):
+        self.map = _f32(map_pts)
+        self.h = C.c_void_p(lib().orc_kdtree_build(_p(self.map), C.c_size_t(len(self.map))))
+
+    def knn(self, queries, k=5, num_threads=8):
+        queries = _f32(queries)
+        nq = len(queries)
+        idx = np.zeros((nq, k), np.int32)
+        d2 = np.zeros((nq, k), np.float32)
+        lib().orc_kdtree_knn(self.h, _p(queries), C.c_size_t(nq), k, _p(idx), _p(d2), num_threads)
+        return idx, d2
+
+    def radius(self, q, radius):
+        q = _f32(q)
+        cap = len(self.map)
+        idx = np.zeros(cap, np.int32)
+        d2 = np.zeros(cap, np.float32)
+        n = lib().orc_kdtree_radius(self.h, _p(q), C.c_float(radius), _p(idx), _p(d2), C.c_size_t(cap))
+        return idx[:n].copy(), d2[:n].copy()
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_kdtree_free(self.h)
+            self.h = None
+
+
+# ---- registration -----------------------------------------------------------------------
+def _residuals(fn, map_pts, pts, pose, params, tree):
+    map_pts = _f32(map_pts)
+    pts = _f32(pts)
+    pose = _f32(pose)
+    tree = tree or KdTree(map_pts)
+    n = len(pts)
+    coeff = np.zeros((n, 4), np.float32)
+    flag = np.zeros(n, np.uint8)
+    nn = np.zeros((n, 5), np.int32)
+    fn(_p(map_pts), C.c_size_t(len(map_pts)), tree.h, _p(pts), C.c_size_t(n), _p(pose),
+       C.byref(params), _p(coeff), _p(flag), _p(nn))
+    return coeff, flag, nn
+
+
+def corner_residuals(map_pts, pts, pose, params=None, tree=None):
+    return _residuals(lib().orc_corner_residuals, map_pts, pts, pose, params or default_params(), tree)
+
+
+def surf_residuals(map_pts, pts, pose, params=None, tree=None):
+    return _residuals(lib().orc_surf_residuals, map_pts, pts, pose, params or default_params(), tree)
+
+
+def jacobian_rows(ori, coeff, pose):
+    ori = _f32(ori)
+    coeff = _f32(coeff)
+    pose = _f32(pose)
+    n = len(ori)
+    A = np.zeros((n, 6), np.float32)
+    b = np.zeros(n, np.float32)
+    lib().orc_jacobian_rows(_p(ori), _p(coeff), C.c_size_t(n), _p(pose), _p(A), _p(b))
+    return A, b
+
+
+def lm_step(ori, coeff, it, pose, state=None, params=None):
+    ori = _f32(ori)
+    coeff = _f32(coeff)
+    pose = _f32(pose).copy()
+    state = state or LmState()
+    params = params or default_params()
+    AtA = np.zeros((6, 6), np.float32)
+    Atb = np.zeros(6, np.float32)
+    x = np.zeros(6, np.float32)
+    conv = lib().orc_lm_step(_p(ori), _p(coeff), C.c_size_t(len(ori)), it, _p(pose),
+                             C.byref(state), C.byref(params), _p(AtA), _p(Atb), _p(x))
+    return conv, pose, AtA, Atb, x, state
+
+
+def scan2map(corner_map, surf_map, corner, surf, pose, params=None, state=None):
+    corner_map, surf_map, corner, surf = map(_f32, (corner_map, surf_map, corner, surf))
+    pose = _f32(pose).copy()
+    params = params or default_params()
+    state = state or LmState()
+    res = Result()
+    lib().orc_scan2map(_p(corner_map), C.c_size_t(len(corner_map)), _p(surf_map),
+                       C.c_size_t(len(surf_map)), _p(corner), C.c_size_t(len(corner)),
+                       _p(surf), C.c_size_t(len(surf)), _p(pose), C.byref(state),
+                       C.byref(params), C.byref(res))
+    return pose, res, state
+
+
+def transform_update(pose, imu_available=False, imu_roll=0.0, imu_pitch=0.0, imu_weight=0.01,
+                     params=None):
+    pose = _f32(pose).copy()
+    params = params or default_params()
+    lib().orc_transform_update(_p(pose), int(imu_available), C.c_float(imu_roll),
+                               C.c_float(imu_pitch), C.c_float(imu_weight), C.byref(params))
+    return pose
+
+
+class MapOptimization:
+    """mapOptimization-like object: keyframes, local map, per-scan registration."""
+
+    def __init__(self, params=None):
+        self.params = params or default_params()
+        self.h = C.c_void_p(lib().orc_mo_create(C.byref(self.params)))
+
+    def add_keyframe(self, corner, surf, pose, time):
+        corner = _f32(corner)
+        surf = _f32(surf)
+        pose = _f32(pose)
+        return lib().orc_mo_add_keyframe(self.h, _p(corner), C.c_size_t(len(corner)), _p(surf),
+                                         C.c_size_t(len(surf)), _p(pose), C.c_double(time))
+
+    def num_keyframes(self):
+        return lib().orc_mo_num_keyframes(self.h)
+
+    def extract_nearby(self, time_now):
+        cap = 2 * self.num_keyframes() + 8
+        ids = np.zeros(cap, np.int32)
+        n = lib().orc_mo_extract_nearby(self.h, C.c_double(time_now), _p(ids), C.c_size_t(cap))
+        return ids[:n].copy()
+
+    def build_local_map(self, ids):
+        ids = np.ascontiguousarray(ids, np.int32)
+        lib().orc_mo_build_local_map(self.h, _p(ids), C.c_size_t(len(ids)))
+
+    def get_map(self, which):
+        n = lib().orc_mo_map_size(self.h, which)
+        out = np.zeros((n, 4), np.float32)
+        lib().orc_mo_get_map(self.h, which, _p(out))
+        return out
+
+    def register_scan(self, corner_raw, surf_raw, pose):
+        corner_raw = _f32(corner_raw)
+        surf_raw = _f32(surf_raw)
+        pose = _f32(pose).copy()
+        res = Result()
+        nc = C.c_size_t(0)
+        ns = C.c_size_t(0)
+        lib().orc_mo_register_scan(self.h, _p(corner_raw), C.c_size_t(len(corner_raw)),
+                                   _p(surf_raw), C.c_size_t(len(surf_raw)), _p(pose),
+                                   C.byref(res), C.byref(nc), C.byref(ns))
+        return pose, res, nc.value, ns.value
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_mo_destroy(self.h)
+            self.h = None

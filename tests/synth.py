@@ -1,0 +1,56 @@
+"""Small seeded synthetic scenes for the parity tests (numpy; bench-scale data comes from the
+C++ generator in the harness library).  Clouds are float32 [n,4] = x,y,z,intensity."""
+import numpy as np
+
+
+def rot_rpy(roll, pitch, yaw):
+    cr, sr, cp, sp, cy, sy = np.cos(roll), np.sin(roll), np.cos(pitch), np.sin(pitch), np.cos(yaw), np.sin(yaw)
+    Rx = np.array([[1, 0, 0], [0, cr, -sr], [0, sr, cr]])
+    Ry = np.array([[cp, 0, sp], [0, 1, 0], [-sp, 0, cp]])
+    Rz = np.array([[cy, -sy, 0], [sy, cy, 0], [0, 0, 1]])
+    return Rz @ Ry @ Rx
+
+
+def room_world(rng, n_surf=60000, n_corner=12000, half=12.0, height=6.0, noise=0.01):
+    """points on the shell of a box room (surf) and on vertical/horizontal edges + poles (corner)"""
+    surf = []
+    per = n_surf // 6
+    for axis in range(3):
+        for sgn in (-1, 1):
+            p = rng.uniform(-1, 1, (per, 3)) * np.array([half, half, height / 2])
+            p[:, axis] = sgn * (half if axis < 2 else height / 2)
+            surf.append(p)
+    surf = np.concatenate(surf) + rng.normal(0, noise, (per * 6, 3))
+    corner = []
+    n_lines = 40
+    per = n_corner // n_lines
+    for k in range(n_lines):
+        if k % 2 == 0:   # vertical pole
+            base = np.array([rng.uniform(-half, half), rng.uniform(-half, half), 0.0])
+            d = np.array([0, 0, 1.0])
+            ext = height / 2
+        else:            # horizontal edge
+            base = np.array([rng.uniform(-half, half), rng.uniform(-half, half), rng.uniform(-height / 2, height / 2)])
+            ang = rng.uniform(0, np.pi)
+            d = np.array([np.cos(ang), np.sin(ang), 0.0])
+            ext = 4.0
+        t = rng.uniform(-ext, ext, per)
+        corner.append(base + np.outer(t, d))
+    corner = np.concatenate(corner) + rng.normal(0, noise, (per * n_lines, 3))
+
+    def with_i(p):
+        return np.concatenate([p, rng.uniform(0, 255, (len(p), 1))], axis=1).astype(np.float32)
+    return with_i(corner), with_i(surf)
+
+
+def scan_from_world(rng, corner_w, surf_w, pose, n_corner=800, n_surf=4000, noise=0.01):
+    """sample world points and express them in the sensor frame of `pose` = [r,p,y,x,y,z]"""
+    R = rot_rpy(*pose[:3])
+    t = np.asarray(pose[3:6], dtype=np.float64)
+
+    def pick(w, n):
+        sel = w[rng.choice(len(w), size=min(n, len(w)), replace=False)].astype(np.float64)
+        loc = (sel[:, :3] - t) @ R      # R^T (p - t)
+        loc += rng.normal(0, noise, loc.shape)
+        return np.concatenate([loc, sel[:, 3:4]], axis=1).astype(np.float32)
+    return pick(corner_w, n_corner), pick(surf_w, n_surf)

@@ -1,0 +1,252 @@
+"""Pins of the CPU oracle against the third-party code the reference calls (where that code is
+available in this image: the cv2 wheel = OpenCV 4.13 built without Eigen -> Jacobi cv::eigen) and
+against independent numpy / scipy computations.  CPU only."""
+import numpy as np
+import pytest
+
+from oracle import pyoracle as O
+
+cv2 = pytest.importorskip("cv2")
+
+
+def _spd(rng, n, scale):
+    B = rng.standard_normal((n + 2, n)).astype(np.float32) * np.float32(scale)
+    A = (B.T @ B).astype(np.float32)
+    return (np.triu(A) + np.triu(A, 1).T).astype(np.float32)
+
+
+@pytest.mark.parametrize("n", [3, 6])
+def test_jacobi_eigen_bit_exact_vs_cv2(n):
+    # cv::eigen at MO:1050 (3x3) and MO:1268 (6x6)
+    rng = np.random.default_rng(10 + n)
+    for _ in range(800):
+        A = _spd(rng, n, rng.choice([0.01, 1.0, 30.0]))
+        _, w, v = cv2.eigen(A)
+        w2, v2 = O.jacobi_eigen(A)
+        assert np.array_equal(w.ravel(), w2)
+        assert np.array_equal(v, v2)
+
+
+def test_jacobi_eigen_line_covariances_bit_exact_vs_cv2():
+    rng = np.random.default_rng(3)
+    for _ in range(800):
+        d = rng.standard_normal(3)
+        d /= np.linalg.norm(d)
+        pts = (np.outer(rng.uniform(-1, 1, 5), d) + rng.normal(0, 0.02, (5, 3))).astype(np.float32)
+        c = pts - pts.mean(0)
+        A = (c.T @ c / 5).astype(np.float32)
+        A = np.triu(A) + np.triu(A, 1).T
+        _, w, v = cv2.eigen(A)
+        w2, v2 = O.jacobi_eigen(A)
+        assert np.array_equal(w.ravel(), w2) and np.array_equal(v, v2)
+
+
+def test_qr_solve_bit_exact_vs_cv2():
+    # cv::solve(matAtA, matAtB, matX, DECOMP_QR) MO:1260
+    rng = np.random.default_rng(4)
+    for _ in range(800):
+        J = rng.standard_normal((200, 6)).astype(np.float32) * np.array([5, 5, 5, 1, 1, 1], np.float32)
+        A = (J.T @ J).astype(np.float32)
+        b = rng.standard_normal((6, 1)).astype(np.float32)
+        _, x = cv2.solve(A, b, flags=cv2.DECOMP_QR)
+        ok, x2 = O.qr_solve(A, b)
+        assert ok == 1 and np.array_equal(x, x2)
+
+
+def test_qr_solve_singular_behaves_like_cv2():
+    # exactly singular -> NaNs propagate (0/0 in the reflector), tiny pivot -> "false" and x = 0
+    b = np.ones((6, 1), np.float32)
+    A = np.zeros((6, 6), np.float32)
+    A[0, 0] = 1
+    okc, x = cv2.solve(A, b, flags=cv2.DECOMP_QR)
+    ok, x2 = O.qr_solve(A, b)
+    assert bool(okc) == bool(ok) and np.array_equal(x, x2, equal_nan=True)
+    A = np.diag([1, 1, 1, 1, 1, 1e-7]).astype(np.float32)
+    okc, x = cv2.solve(A, b, flags=cv2.DECOMP_QR)
+    ok, x2 = O.qr_solve(A, b)
+    assert (not okc) and ok == 0 and not x.any() and not x2.any()
+
+
+def test_lu_solve_bit_exact_vs_cv2():
+    # matV.inv() * matV2 (MO:1283) lowers to cv::solve(matV, matV2, DECOMP_LU)
+    rng = np.random.default_rng(5)
+    for _ in range(800):
+        A = rng.standard_normal((6, 6)).astype(np.float32)
+        B = rng.standard_normal((6, 6)).astype(np.float32)
+        _, x = cv2.solve(A, B, flags=cv2.DECOMP_LU)
+        ok, x2 = O.lu_solve(A, B)
+        assert ok == 1 and np.array_equal(x, x2)
+
+
+@pytest.mark.parametrize("n", [57, 300, 5000, 12000, 120000])
+def test_normal_equations_bit_exact_vs_cv2_gemm(n):
+    # cv::transpose(matA, matAt); matAtA = matAt*matA; matAtB = matAt*matB  MO:1257-1259
+    rng = np.random.default_rng(n)
+    J = (rng.standard_normal((n, 6)) * np.array([5, 5, 5, 1, 1, 1])).astype(np.float32)
+    b = rng.standard_normal((n, 1)).astype(np.float32)
+    At = np.ascontiguousarray(J.T)
+    AtA, Atb = O.normal_equations(J, b)
+    assert np.array_equal(cv2.gemm(At, J, 1, None, 0), AtA)
+    assert np.array_equal(cv2.gemm(At, b, 1, None, 0).ravel(), Atb)
+
+
+def test_small_gemm_bit_exact_vs_cv2():
+    rng = np.random.default_rng(6)
+    for _ in range(300):
+        P = rng.standard_normal((6, 6)).astype(np.float32)
+        x = rng.standard_normal((6, 1)).astype(np.float32)
+        assert np.array_equal(cv2.gemm(P, x, 1, None, 0), O.gemm(P, x))
+
+
+def test_plane_fit_matches_lstsq():
+    # Eigen colPivHouseholderQr().solve MO:1128: Eigen is absent here -> tolerance check only
+    rng = np.random.default_rng(7)
+    for _ in range(500):
+        n = rng.standard_normal(3)
+        n /= np.linalg.norm(n)
+        c = rng.uniform(-30, 30, 3) + n * rng.uniform(2, 20)
+        basis = np.linalg.svd(n[None])[2][1:]
+        pts = c + rng.uniform(-0.6, 0.6, (5, 2)) @ basis + rng.normal(0, 0.01, (5, 3))
+        A = pts.astype(np.float32)
+        x = O.plane_fit(A)
+        ref = np.linalg.lstsq(A.astype(np.float64), -np.ones(5), rcond=None)[0]
+        assert np.allclose(x, ref, rtol=2e-3, atol=1e-5)
+
+
+def test_plane_fit_rank_deficient_gives_basic_solution():
+    # all five points identical -> rank 1: Eigen returns a basic solution with zeros, no NaN
+    A = np.tile(np.array([[1.0, 2.0, 3.0]], np.float32), (5, 1))
+    x = O.plane_fit(A)
+    assert np.isfinite(x).all()
+    assert np.count_nonzero(x) == 1
+    assert np.allclose(A @ x, -1, atol=1e-5)
+
+
+def test_pose_to_affine_matches_rotation_convention():
+    # pcl::getTransformation: R = Rz(yaw) Ry(pitch) Rx(roll)
+    from tests.synth import rot_rpy
+    rng = np.random.default_rng(8)
+    for _ in range(100):
+        pose = rng.uniform(-1, 1, 6).astype(np.float32)
+        T = O.pose_to_affine(pose).reshape(3, 4)
+        assert np.allclose(T[:, :3], rot_rpy(*pose[:3].astype(np.float64)), atol=3e-7)
+        assert np.array_equal(T[:, 3], pose[3:])
+
+
+def test_transform_is_unfused_fp32():
+    rng = np.random.default_rng(9)
+    pts = rng.uniform(-50, 50, (1000, 4)).astype(np.float32)
+    pose = np.array([0.1, -0.2, 0.7, 3, -4, 5], np.float32)
+    T = O.pose_to_affine(pose)
+    out = O.transform_cloud(pts, T=T)
+    x, y, z = pts[:, 0], pts[:, 1], pts[:, 2]
+    for r in range(3):
+        ref = ((T[4 * r] * x + T[4 * r + 1] * y) + T[4 * r + 2] * z) + T[4 * r + 3]   # fp32 numpy, one rounding per op
+        assert np.array_equal(out[:, r], ref)
+    assert np.array_equal(out[:, 3], pts[:, 3])
+
+
+def _numpy_voxel_keys(pts, leaf):
+    inv = np.float32(1.0) / np.float32(leaf)
+    mn = pts[:, :3].min(0)
+    mx = pts[:, :3].max(0)
+    min_b = np.floor(mn * inv).astype(np.int32)
+    max_b = np.floor(mx * inv).astype(np.int32)
+    div = max_b - min_b + 1
+    ijk = (np.floor(pts[:, :3] * inv) - min_b.astype(np.float32)).astype(np.int32)
+    return (ijk[:, 0] + ijk[:, 1] * div[0] + ijk[:, 2] * div[0] * div[1]).astype(np.uint32)
+
+
+@pytest.mark.parametrize("leaf,n", [(0.2, 5000), (0.4, 20000), (2.0, 300)])
+def test_voxelgrid_keys_and_centroids_vs_numpy(leaf, n):
+    rng = np.random.default_rng(int(leaf * 10) + n)
+    pts = np.concatenate([rng.uniform(-20, 20, (n, 3)) * [1, 1, 0.1], rng.uniform(0, 255, (n, 1))], 1).astype(np.float32)
+    out, keys, okeys, passthrough = O.voxelgrid(pts, leaf)
+    assert not passthrough
+    ref_keys = _numpy_voxel_keys(pts, leaf)
+    assert np.array_equal(keys, ref_keys)
+    uk = np.unique(ref_keys)
+    assert np.array_equal(okeys, uk)            # ascending voxel idx, one output per voxel
+    # centroids: sequential fp32 sums in input order within each voxel
+    order = np.argsort(ref_keys, kind="stable")
+    sk = ref_keys[order]
+    starts = np.flatnonzero(np.r_[True, sk[1:] != sk[:-1]])
+    ends = np.r_[starts[1:], len(sk)]
+    for v in rng.choice(len(starts), size=min(200, len(starts)), replace=False):
+        acc = np.zeros(4, np.float32)
+        for j in order[starts[v]:ends[v]]:
+            acc = acc + pts[j]
+        assert np.array_equal(out[v], acc / np.float32(ends[v] - starts[v]))
+
+
+def test_voxelgrid_overflow_passthrough():
+    # dx*dy*dz > INT32_MAX -> PCL warns and returns the input unchanged
+    pts = np.array([[0, 0, 0, 1], [3000, 3000, 3000, 2], [1, 1, 1, 3]], np.float32)
+    out, _, _, passthrough = O.voxelgrid(pts, 0.2)
+    assert passthrough and np.array_equal(out, pts)
+
+
+def test_voxelgrid_empty_and_single():
+    out, _, _, _ = O.voxelgrid(np.zeros((0, 4), np.float32), 0.2)
+    assert len(out) == 0
+    p = np.array([[1.5, -2.5, 3.0, 9.0]], np.float32)
+    out, keys, _, _ = O.voxelgrid(p, 0.4)
+    assert np.array_equal(out, p) and keys[0] == 0
+
+
+def test_kdtree_matches_brute_and_scipy():
+    from scipy.spatial import cKDTree
+    rng = np.random.default_rng(11)
+    m = 30000
+    mp = np.concatenate([rng.uniform(-20, 20, (m, 3)) * [1, 1, 0.2], np.zeros((m, 1))], 1).astype(np.float32)
+    q = np.concatenate([rng.uniform(-22, 22, (3000, 3)) * [1, 1, 0.2], np.zeros((3000, 1))], 1).astype(np.float32)
+    tree = O.KdTree(mp)
+    idx, d2 = tree.knn(q, 5)
+    bidx, bd2 = O.knn5_brute(mp, q)
+    assert np.array_equal(idx, bidx) and np.array_equal(d2, bd2)
+    # numpy fp32 distances, (d2, index) order
+    for i in rng.choice(len(q), 50, replace=False):
+        d = mp[:, :3] - q[i, :3]
+        dd = (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2]
+        order = np.lexsort((np.arange(m), dd))[:5]
+        assert np.array_equal(order, idx[i]) and np.array_equal(dd[order], d2[i])
+    # scipy (float64 distances): same sets whenever the 5th/6th gap is not a rounding tie
+    _, sidx = cKDTree(mp[:, :3].astype(np.float64)).query(q[:, :3].astype(np.float64), k=6)
+    same = sum(set(sidx[i, :5]) == set(idx[i]) for i in range(len(q)))
+    assert same >= len(q) - 3
+
+
+def test_kdtree_exact_ties_resolved_by_index():
+    # lattice map: many exactly equal distances
+    g = np.arange(-5, 6, dtype=np.float32)
+    mp = np.stack(np.meshgrid(g, g, g, indexing="ij"), -1).reshape(-1, 3)
+    mp = np.concatenate([mp, np.zeros((len(mp), 1), np.float32)], 1)
+    q = np.array([[0, 0, 0, 0], [0.5, 0.5, 0.5, 0], [2, -3, 1, 0]], np.float32)
+    idx, d2 = O.KdTree(mp).knn(q, 5)
+    bidx, bd2 = O.knn5_brute(mp, q)
+    assert np.array_equal(idx, bidx) and np.array_equal(d2, bd2)
+    assert (np.diff(d2, axis=1) >= 0).all()
+    for r in range(len(q)):
+        for j in range(4):
+            if d2[r, j] == d2[r, j + 1]:
+                assert idx[r, j] < idx[r, j + 1]
+
+
+def test_knn_small_maps():
+    mp = np.array([[0, 0, 0, 0], [1, 0, 0, 0], [0, 2, 0, 0]], np.float32)
+    q = np.array([[0.1, 0, 0, 0]], np.float32)
+    idx, d2 = O.KdTree(mp).knn(q, 5)
+    assert list(idx[0]) == [0, 1, 2, -1, -1] and np.isinf(d2[0, 3:]).all()
+    idx, d2 = O.knn5_brute(mp, q)
+    assert list(idx[0]) == [0, 1, 2, -1, -1]
+
+
+def test_radius_search_sorted_strict():
+    rng = np.random.default_rng(12)
+    mp = np.concatenate([rng.uniform(-60, 60, (500, 3)), np.zeros((500, 1))], 1).astype(np.float32)
+    idx, d2 = O.KdTree(mp).radius(mp[-1], 50.0)
+    d = mp[:, :3] - mp[-1, :3]
+    dd = (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2]
+    ref = np.flatnonzero(dd < np.float32(2500.0))
+    ref = ref[np.lexsort((ref, dd[ref]))]
+    assert np.array_equal(idx, ref) and idx[0] == 499
