@@ -1,0 +1,227 @@
+/*
+ * lvreg.h -- C ABI of the B200-native scan-to-map registration library (liblvreg.so).
+ *
+ * Drop-in boundary for ONE path of valentinomario/LiDAR-Visual-Inertial-SLAM: the
+ * LIO-SAM-derived scan-to-map registration inside class mapOptimization.  The reference has
+ * no plugin/FFI interface; the hot path is a set of void member functions that talk through
+ * public data members.  Every entry point below names the reference
+ * member function / data member it replaces.  "MO:" = lidar_odometry/src/mapOptimization.cpp:
+ *
+ * Conventions
+ *   - points: any AoS layout with float x,y,z at byte offsets 0/4/8 and a float intensity at
+ *     `intensity_offset`; pcl::PointXYZI (utility.h:64) is {stride 32, intensity_offset 16},
+ *     packed float4 is {16, 12}.  Pass PCL clouds as cloud->points.data() without a copy.
+ *   - poses: float[6] = {roll, pitch, yaw, x, y, z} = transformTobeMapped order (MO:126).
+ *     Keyframe poses (PointTypePose, MO:29-46) are passed in the same order.
+ *   - every call is synchronous with respect to the host; all device work of one handle runs
+ *     on one CUDA stream.  A handle is not thread-safe; different handles are independent
+ *     (one per robot / sequence / GPU), mirroring the reference's one-mutex design (MO:309).
+ *   - status codes: 0 = ok; the two "soft" outcomes of the reference (not enough features,
+ *     MO:1340-1342; no key poses, MO:1317) return a distinct code and leave the pose untouched.
+ *   - there is no CPU fallback: without a CUDA device lvreg_create fails.
+ */
+#ifndef LVREG_H
+#define LVREG_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LVREG_OK                       0
+#define LVREG_ERR_INVALID              1   /* bad argument */
+#define LVREG_ERR_CUDA                 2   /* CUDA runtime error, see lvreg_last_error */
+#define LVREG_ERR_NOT_ENOUGH_FEATURES  3   /* MO:1320/1340: Nc <= 10 or Ns <= 100; pose unchanged */
+#define LVREG_ERR_NO_KEYFRAMES         4   /* MO:1317: cloudKeyPoses3D empty; pose unchanged */
+#define LVREG_ERR_NO_MAP               5   /* scan2map before a local map was built */
+#define LVREG_ERR_CAPACITY             6   /* output buffer too small */
+
+#define LVREG_MAX_ITERS 32
+
+#define LVREG_CORNER 0
+#define LVREG_SURF   1
+
+/* kNN variants of lvreg_knn5 */
+#define LVREG_KNN_GRID_GATED 0   /* 27-cell search: exact whenever the 5th neighbour is inside the gate */
+#define LVREG_KNN_GRID_EXACT 1   /* ring expansion until provably exact (unbounded) */
+#define LVREG_KNN_BRUTE      2   /* exhaustive, FP32-pipe bound */
+
+typedef struct lvreg_handle lvreg_handle;
+
+/* A read-only point cloud in host (on_device = 0) or device (on_device = 1) memory. */
+typedef struct lvreg_cloud {
+    const void* data;
+    size_t      n;
+    uint32_t    stride;            /* bytes between consecutive points (>= 16, multiple of 4) */
+    uint32_t    intensity_offset;  /* byte offset of the float intensity inside a point */
+    int32_t     on_device;
+    int32_t     reserved;
+} lvreg_cloud;
+
+/* A writable point buffer. */
+typedef struct lvreg_cloud_out {
+    void*    data;
+    size_t   capacity;             /* in points */
+    uint32_t stride;
+    uint32_t intensity_offset;
+    int32_t  on_device;
+    int32_t  reserved;
+} lvreg_cloud_out;
+
+/* Mirrors the ParamServer fields and the hard-coded literals of the hot path. */
+typedef struct lvreg_params {
+    float   corner_leaf;         /* mappingCornerLeafSize   utility.h:266   0.2 */
+    float   surf_leaf;           /* mappingSurfLeafSize     utility.h:268   0.4 */
+    int32_t edge_min_valid;      /* edgeFeatureMinValidNum  utility.h:259   10  */
+    int32_t surf_min_valid;      /* surfFeatureMinValidNum  utility.h:261   100 */
+    int32_t max_iters;           /* MO:1325  20 (<= LVREG_MAX_ITERS) */
+    float   knn_gate_sq;         /* MO:1025, MO:1121  1.0 */
+    float   line_eig_ratio;      /* MO:1052  3 */
+    float   plane_tol;           /* MO:1142  0.2 */
+    float   min_weight;          /* MO:1088, MO:1159  0.1 */
+    int32_t min_matches;         /* MO:1210  50 */
+    float   degeneracy_eig;      /* MO:1272  100 */
+    float   conv_deg;            /* MO:1309  0.05 */
+    float   conv_cm;             /* MO:1309  0.05 */
+    int32_t reference_quirks;    /* 1 = reproduce the shadowed matP (MO:1220 hides MO:132) */
+    float   rotation_tolerance;  /* rotation_tollerance utility.h:273  1000 */
+    float   z_tolerance;         /* z_tollerance        utility.h:271  1000 */
+    float   imu_rpy_weight;      /* imuRPYWeight        utility.h:234  0.01 */
+    int32_t reserved[7];
+} lvreg_params;
+
+/* Outcome of one scan2MapOptimization (MO:1315-1343). */
+typedef struct lvreg_result {
+    int32_t iterations;                       /* iterCount reached (1..max_iters) */
+    int32_t converged;                        /* LMOptimization returned true */
+    int32_t degenerate;                       /* isDegenerate (MO:131) after the call */
+    int32_t n_corner_ds, n_surf_ds;           /* laserCloud{Corner,Surf}LastDSNum */
+    int32_t n_corner_map, n_surf_map;         /* laserCloud{Corner,Surf}FromMapDSNum */
+    int32_t n_sel[LVREG_MAX_ITERS];           /* laserCloudSelNum per iteration */
+    float   pose_iter[LVREG_MAX_ITERS][6];    /* transformTobeMapped after each iteration */
+    float   cost[LVREG_MAX_ITERS];            /* sum of squared residuals per iteration (diagnostic) */
+} lvreg_result;
+
+typedef struct lvreg_map_info {
+    uint64_t n_corner_in, n_surf_in;          /* concatenated keyframe points (laserCloud*FromMap) */
+    uint64_t n_corner_ds, n_surf_ds;          /* after VoxelGrid (laserCloud*FromMapDS) */
+    int32_t  grid_dims[2][3];                 /* search-grid cells per axis, corner / surf */
+    float    grid_cell[2];                    /* search-grid cell edge in metres */
+} lvreg_map_info;
+
+/* Device time (CUDA events on the handle's stream) of the stages of the last call, in ms. */
+typedef struct lvreg_timings {
+    float upload_ms;        /* H2D + pack of the call's input clouds */
+    float downsample_ms;    /* downsampleCurrentScan */
+    float map_build_ms;     /* transform + concat + VoxelGrid of the local map */
+    float grid_build_ms;    /* search-grid build (replaces kdtree->setInputCloud) */
+    float register_ms;      /* the on-device LM loop */
+    float total_ms;         /* first event to last event of the call */
+    int32_t kernel_launches;/* kernels launched by the last call */
+    int32_t reserved;
+} lvreg_timings;
+
+/* ---- lifetime ---------------------------------------------------------------------------- */
+void        lvreg_default_params(lvreg_params* p);
+/* `cuda_stream` is a cudaStream_t (may be NULL = a private non-blocking stream). */
+int         lvreg_create(const lvreg_params* p, int device, void* cuda_stream, lvreg_handle** out);
+void        lvreg_destroy(lvreg_handle* h);
+const char* lvreg_last_error(const lvreg_handle* h);
+const char* lvreg_status_string(int status);
+int         lvreg_version(void);
+/* page-locked host memory for callers that want full-speed uploads */
+void*       lvreg_host_alloc(size_t bytes);
+void        lvreg_host_free(void* p);
+
+/* ---- keyframe store: cornerCloudKeyFrames / surfCloudKeyFrames / cloudKeyPoses6D (MO:83-87) -- */
+/* saveKeyFramesAndFactor's push_back of the DS feature clouds + pose (MO:1600-1610). */
+int lvreg_add_keyframe(lvreg_handle* h, const lvreg_cloud* corner, const lvreg_cloud* surf,
+                       const float pose_rpyxyz[6], int32_t* id_out);
+/* correctPoses after a loop closure (MO:1623-1640): replaces the first n keyframe poses. */
+int lvreg_update_keyframe_poses(lvreg_handle* h, const float* poses_rpyxyz, size_t n);
+int lvreg_num_keyframes(const lvreg_handle* h, size_t* n);
+int lvreg_clear_keyframes(lvreg_handle* h);
+
+/* ---- local map: extractCloud (MO:931-970) ------------------------------------------------- */
+/* ids = keyframe indices in concatenation order (output of extractNearby MO:894-929 after the
+ * distance filter MO:938); duplicates allowed, as in the reference.  Transforms each keyframe by
+ * its pose (transformPointCloud MO:347-366), concatenates, VoxelGrid-filters corner/surf with
+ * corner_leaf/surf_leaf (MO:959-965) and builds the 5-NN search grids (replaces MO:1322-1323). */
+int lvreg_build_local_map(lvreg_handle* h, const int32_t* ids, size_t n, lvreg_map_info* info);
+/* Install already down-sampled maps (laserCloud{Corner,Surf}FromMapDS) and build the grids. */
+int lvreg_set_local_map(lvreg_handle* h, const lvreg_cloud* corner_ds, const lvreg_cloud* surf_ds,
+                        lvreg_map_info* info);
+/* Read back laserCloud{Corner,Surf}FromMapDS (which = LVREG_CORNER / LVREG_SURF). */
+int lvreg_get_local_map(lvreg_handle* h, int which, lvreg_cloud_out* out, size_t* n);
+
+/* ---- current scan ------------------------------------------------------------------------- */
+/* downsampleCurrentScan (MO:987-999): VoxelGrid of laserCloud{Corner,Surf}Last; the results
+ * (laserCloud{Corner,Surf}LastDS) stay on the device for lvreg_scan2map. */
+int lvreg_downsample_scan(lvreg_handle* h, const lvreg_cloud* corner_raw, const lvreg_cloud* surf_raw,
+                          size_t* n_corner_ds, size_t* n_surf_ds);
+/* Install already down-sampled feature clouds as laserCloud{Corner,Surf}LastDS. */
+int lvreg_set_scan_ds(lvreg_handle* h, const lvreg_cloud* corner_ds, const lvreg_cloud* surf_ds);
+int lvreg_get_scan_ds(lvreg_handle* h, int which, lvreg_cloud_out* out, size_t* n);
+
+/* ---- registration ------------------------------------------------------------------------- */
+/* scan2MapOptimization (MO:1315-1343) on the current DS scan and local map: up to max_iters of
+ * {cornerOptimization, surfOptimization, combineOptimizationCoeffs, LMOptimization} in ONE
+ * cooperative kernel launch, then transformUpdate's clamps (MO:1370-1372; IMU slerp via
+ * lvreg_transform_update).  pose is transformTobeMapped, in/out. */
+int lvreg_scan2map(lvreg_handle* h, float pose_rpyxyz[6], lvreg_result* res);
+/* One call per incoming scan = extractCloud (if ids != NULL) + downsampleCurrentScan +
+ * scan2MapOptimization, i.e. the body of laserCloudInfoHandler MO:318-322. */
+int lvreg_register_scan(lvreg_handle* h, const lvreg_cloud* corner_raw, const lvreg_cloud* surf_raw,
+                        const int32_t* ids, size_t n_ids, float pose_rpyxyz[6], lvreg_result* res);
+/* transformUpdate (MO:1345-1375): optional IMU roll/pitch slerp + clamps.  Host arithmetic. */
+int lvreg_transform_update(const lvreg_handle* h, float pose_rpyxyz[6], int imu_available,
+                           float imu_roll_init, float imu_pitch_init);
+/* isDegenerate (MO:131) persists across scans in the reference; read / reset it here. */
+int lvreg_get_degenerate(const lvreg_handle* h, int* is_degenerate);
+int lvreg_reset_lm_state(lvreg_handle* h);
+
+/* ---- stage-level entry points (parity tests, micro-benchmarks) ----------------------------- */
+/* pcl::getTransformation (MO:399-407) on the host, row-major 3x4. */
+void lvreg_pose_to_affine(const float pose_rpyxyz[6], float T[12]);
+/* transformPointCloud (MO:347-385). */
+int lvreg_transform_cloud(lvreg_handle* h, const lvreg_cloud* in, const float pose_rpyxyz[6],
+                          lvreg_cloud_out* out);
+/* pcl::VoxelGrid::filter as used at MO:959-965 / MO:991-997.  voxel_keys_out (optional, host,
+ * out->capacity entries) receives the voxel idx of every output point; passthrough is set when
+ * PCL's "leaf size too small" rule returns the input unchanged. */
+int lvreg_voxelgrid(lvreg_handle* h, const lvreg_cloud* in, float leaf, lvreg_cloud_out* out,
+                    size_t* n_out, uint32_t* voxel_keys_out, int* passthrough);
+/* per-input-point voxel idx (the sort key of VoxelGrid); keys_out is host memory, in->n entries */
+int lvreg_voxel_keys(lvreg_handle* h, const lvreg_cloud* in, float leaf, uint32_t* keys_out);
+/* kdtree->nearestKSearch(q, 5, ...) (MO:1019, MO:1111) for world-frame queries against the current
+ * corner / surf map.  idx_out: n x 5 int32 (indices into the DS map), d2_out: n x 5 float, host. */
+int lvreg_knn5(lvreg_handle* h, int which_map, const lvreg_cloud* queries, int variant,
+               int32_t* idx_out, float* d2_out);
+/* cornerOptimization / surfOptimization (MO:1006-1167) for sensor-frame points at `pose`:
+ * coeff_out n x 4 (coeffSel: s*la, s*lb, s*lc, s*ld2; zero when rejected), flag_out n bytes
+ * (laserCloudOri*Flag), knn_idx_out optional n x 5.  All host memory. */
+int lvreg_corner_residuals(lvreg_handle* h, const lvreg_cloud* pts, const float pose_rpyxyz[6],
+                           float* coeff_out, uint8_t* flag_out, int32_t* knn_idx_out);
+int lvreg_surf_residuals(lvreg_handle* h, const lvreg_cloud* pts, const float pose_rpyxyz[6],
+                         float* coeff_out, uint8_t* flag_out, int32_t* knn_idx_out);
+/* LMOptimization(iterCount) (MO:1190-1313) on explicit laserCloudOri / coeffSel rows (packed
+ * float4 host arrays).  Outputs optional.  *converged = return value of LMOptimization. */
+int lvreg_lm_step(lvreg_handle* h, const float* ori_xyzi, const float* coeff_xyzi, size_t n_sel,
+                  int iter_count, float pose_rpyxyz[6], float AtA_out[36], float Atb_out[6],
+                  float x_out[6], int* converged);
+
+/* ---- measurement -------------------------------------------------------------------------- */
+int lvreg_get_timings(const lvreg_handle* h, lvreg_timings* t);
+/* total kernels launched by this handle since creation */
+int lvreg_get_launch_count(const lvreg_handle* h, uint64_t* n);
+/* kNN micro-benchmark on device-resident data: runs `repeats` launches of the chosen variant on
+ * the current map with the given device queries and returns the mean device time per launch. */
+int lvreg_bench_knn5(lvreg_handle* h, int which_map, const lvreg_cloud* queries, int variant,
+                     int repeats, float* ms_per_launch);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

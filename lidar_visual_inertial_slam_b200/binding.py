@@ -1,0 +1,372 @@
+"""ctypes binding of include/lvreg.h."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIBPATH = os.path.join(_HERE, "liblvreg.so")
+
+OK, ERR_INVALID, ERR_CUDA, ERR_NOT_ENOUGH_FEATURES, ERR_NO_KEYFRAMES, ERR_NO_MAP, ERR_CAPACITY = range(7)
+CORNER, SURF = 0, 1
+KNN_GRID_GATED, KNN_GRID_EXACT, KNN_BRUTE = 0, 1, 2
+MAX_ITERS = 32
+
+
+class LvregError(RuntimeError):
+    def __init__(self, status, msg):
+        super().__init__("lvreg status %d: %s" % (status, msg))
+        self.status = status
+
+
+class Cloud(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("n", C.c_size_t), ("stride", C.c_uint32),
+                ("intensity_offset", C.c_uint32), ("on_device", C.c_int32), ("reserved", C.c_int32)]
+
+
+class CloudOut(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("capacity", C.c_size_t), ("stride", C.c_uint32),
+                ("intensity_offset", C.c_uint32), ("on_device", C.c_int32), ("reserved", C.c_int32)]
+
+
+class Params(C.Structure):
+    _fields_ = [("corner_leaf", C.c_float), ("surf_leaf", C.c_float),
+                ("edge_min_valid", C.c_int32), ("surf_min_valid", C.c_int32),
+                ("max_iters", C.c_int32), ("knn_gate_sq", C.c_float), ("line_eig_ratio", C.c_float),
+                ("plane_tol", C.c_float), ("min_weight", C.c_float), ("min_matches", C.c_int32),
+                ("degeneracy_eig", C.c_float), ("conv_deg", C.c_float), ("conv_cm", C.c_float),
+                ("reference_quirks", C.c_int32), ("rotation_tolerance", C.c_float),
+                ("z_tolerance", C.c_float), ("imu_rpy_weight", C.c_float), ("reserved", C.c_int32 * 7)]
+
+
+class Result(C.Structure):
+    _fields_ = [("iterations", C.c_int32), ("converged", C.c_int32), ("degenerate", C.c_int32),
+                ("n_corner_ds", C.c_int32), ("n_surf_ds", C.c_int32),
+                ("n_corner_map", C.c_int32), ("n_surf_map", C.c_int32),
+                ("n_sel", C.c_int32 * MAX_ITERS), ("pose_iter", (C.c_float * 6) * MAX_ITERS),
+                ("cost", C.c_float * MAX_ITERS)]
+
+
+class MapInfo(C.Structure):
+    _fields_ = [("n_corner_in", C.c_uint64), ("n_surf_in", C.c_uint64),
+                ("n_corner_ds", C.c_uint64), ("n_surf_ds", C.c_uint64),
+                ("grid_dims", (C.c_int32 * 3) * 2), ("grid_cell", C.c_float * 2)]
+
+
+class Timings(C.Structure):
+    _fields_ = [("upload_ms", C.c_float), ("downsample_ms", C.c_float), ("map_build_ms", C.c_float),
+                ("grid_build_ms", C.c_float), ("register_ms", C.c_float), ("total_ms", C.c_float),
+                ("kernel_launches", C.c_int32), ("reserved", C.c_int32)]
+
+
+_lib = None
+
+
+def lib_path():
+    return _LIBPATH
+
+
+def lib():
+    """Load liblvreg.so (in-tree).  Raises if it has not been built: no fallback exists."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIBPATH):
+            raise ImportError("liblvreg.so is missing (%s): run __graft_entry__.build() / "
+                              "python -m lidar_visual_inertial_slam_b200.build" % _LIBPATH)
+        L = C.CDLL(_LIBPATH)
+        L.lvreg_last_error.restype = C.c_char_p
+        L.lvreg_status_string.restype = C.c_char_p
+        L.lvreg_host_alloc.restype = C.c_void_p
+        L.lvreg_host_alloc.argtypes = [C.c_size_t]
+        L.lvreg_host_free.argtypes = [C.c_void_p]
+        L.lvreg_create.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.lvreg_destroy.argtypes = [C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def default_params(**kw):
+    p = Params()
+    lib().lvreg_default_params(C.byref(p))
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+def pose_to_affine(pose):
+    pose = np.ascontiguousarray(pose, np.float32)
+    T = np.zeros(12, np.float32)
+    lib().lvreg_pose_to_affine(pose.ctypes.data_as(C.c_void_p), T.ctypes.data_as(C.c_void_p))
+    return T
+
+
+def host_alloc_f32(shape):
+    """float32 array in page-locked memory (lvreg_host_alloc); keep the returned array alive."""
+    n = int(np.prod(shape))
+    ptr = lib().lvreg_host_alloc(n * 4)
+    if not ptr:
+        raise MemoryError("lvreg_host_alloc failed")
+    buf = (C.c_float * n).from_address(ptr)
+    arr = np.frombuffer(buf, dtype=np.float32).reshape(shape)
+    return arr
+
+
+def _cloud(a):
+    """numpy [n,4] (packed x,y,z,i) or [n,8] (pcl::PointXYZI layout) float32 -> lvreg_cloud"""
+    if isinstance(a, Cloud):
+        return a, None
+    a = np.asarray(a)
+    if a.dtype != np.float32 or not a.flags["C_CONTIGUOUS"]:
+        a = np.ascontiguousarray(a, np.float32)
+    if a.ndim != 2 or a.shape[1] not in (4, 8):
+        raise ValueError("cloud must be [n,4] or [n,8] float32")
+    c = Cloud()
+    c.data = a.ctypes.data if len(a) else None
+    c.n = len(a)
+    c.stride = a.shape[1] * 4
+    c.intensity_offset = 12 if a.shape[1] == 4 else 16
+    c.on_device = 0
+    return c, a
+
+
+def device_cloud(ptr, n, stride=16, intensity_offset=12):
+    c = Cloud()
+    c.data = ptr
+    c.n = n
+    c.stride = stride
+    c.intensity_offset = intensity_offset
+    c.on_device = 1
+    return c
+
+
+def to_pcl_layout(a):
+    """[n,4] packed -> [n,8] pcl::PointXYZI rows {x,y,z,1 | intensity,0,0,0}"""
+    a = np.asarray(a, np.float32)
+    out = np.zeros((len(a), 8), np.float32)
+    out[:, :3] = a[:, :3]
+    out[:, 3] = 1.0
+    out[:, 4] = a[:, 3]
+    return out
+
+
+class Lvreg:
+    """One registration handle = one mapOptimization instance on one GPU / stream."""
+
+    def __init__(self, params=None, device=0, stream=None):
+        self.L = lib()
+        self.params = params or default_params()
+        h = C.c_void_p()
+        st = self.L.lvreg_create(C.byref(self.params), int(device), C.c_void_p(stream or 0), C.byref(h))
+        if st != OK:
+            raise LvregError(st, "lvreg_create failed (no CUDA device? there is no CPU fallback)")
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.lvreg_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, st, soft=()):
+        if st != OK and st not in soft:
+            raise LvregError(st, self.L.lvreg_last_error(self.h).decode())
+        return st
+
+    # ---- keyframes / map ----
+    def add_keyframe(self, corner, surf, pose):
+        c, _k1 = _cloud(corner)
+        s, _k2 = _cloud(surf)
+        pose = np.ascontiguousarray(pose, np.float32)
+        kid = C.c_int32(-1)
+        self._ck(self.L.lvreg_add_keyframe(self.h, C.byref(c), C.byref(s), pose.ctypes.data_as(C.c_void_p), C.byref(kid)))
+        return kid.value
+
+    def update_keyframe_poses(self, poses):
+        poses = np.ascontiguousarray(poses, np.float32).reshape(-1, 6)
+        self._ck(self.L.lvreg_update_keyframe_poses(self.h, poses.ctypes.data_as(C.c_void_p), C.c_size_t(len(poses))))
+
+    def num_keyframes(self):
+        n = C.c_size_t(0)
+        self._ck(self.L.lvreg_num_keyframes(self.h, C.byref(n)))
+        return n.value
+
+    def clear_keyframes(self):
+        self._ck(self.L.lvreg_clear_keyframes(self.h))
+
+    def build_local_map(self, ids):
+        ids = np.ascontiguousarray(ids, np.int32)
+        info = MapInfo()
+        self._ck(self.L.lvreg_build_local_map(self.h, ids.ctypes.data_as(C.c_void_p), C.c_size_t(len(ids)), C.byref(info)))
+        return info
+
+    def set_local_map(self, corner_ds, surf_ds):
+        c, _k1 = _cloud(corner_ds)
+        s, _k2 = _cloud(surf_ds)
+        info = MapInfo()
+        self._ck(self.L.lvreg_set_local_map(self.h, C.byref(c), C.byref(s), C.byref(info)))
+        return info
+
+    def _get_cloud(self, fn, which, pcl_layout=False):
+        n = C.c_size_t(0)
+        self._ck(fn(self.h, which, None, C.byref(n)))
+        cols = 8 if pcl_layout else 4
+        out = np.zeros((n.value, cols), np.float32)
+        co = CloudOut()
+        co.data = out.ctypes.data if n.value else None
+        co.capacity = n.value
+        co.stride = cols * 4
+        co.intensity_offset = 16 if pcl_layout else 12
+        self._ck(fn(self.h, which, C.byref(co), C.byref(n)))
+        return out
+
+    def get_local_map(self, which, pcl_layout=False):
+        return self._get_cloud(self.L.lvreg_get_local_map, which, pcl_layout)
+
+    # ---- scan ----
+    def downsample_scan(self, corner_raw, surf_raw):
+        c, _k1 = _cloud(corner_raw)
+        s, _k2 = _cloud(surf_raw)
+        nc, ns = C.c_size_t(0), C.c_size_t(0)
+        self._ck(self.L.lvreg_downsample_scan(self.h, C.byref(c), C.byref(s), C.byref(nc), C.byref(ns)))
+        return nc.value, ns.value
+
+    def set_scan_ds(self, corner_ds, surf_ds):
+        c, _k1 = _cloud(corner_ds)
+        s, _k2 = _cloud(surf_ds)
+        self._ck(self.L.lvreg_set_scan_ds(self.h, C.byref(c), C.byref(s)))
+
+    def get_scan_ds(self, which, pcl_layout=False):
+        return self._get_cloud(self.L.lvreg_get_scan_ds, which, pcl_layout)
+
+    # ---- registration ----
+    def scan2map(self, pose):
+        pose = np.ascontiguousarray(pose, np.float32).copy()
+        res = Result()
+        st = self._ck(self.L.lvreg_scan2map(self.h, pose.ctypes.data_as(C.c_void_p), C.byref(res)),
+                      soft=(ERR_NOT_ENOUGH_FEATURES, ERR_NO_KEYFRAMES, ERR_NO_MAP))
+        return pose, res, st
+
+    def register_scan(self, corner_raw, surf_raw, ids, pose):
+        c, _k1 = _cloud(corner_raw)
+        s, _k2 = _cloud(surf_raw)
+        pose = np.ascontiguousarray(pose, np.float32).copy()
+        res = Result()
+        if ids is None:
+            idp, nid = None, 0
+        else:
+            ids = np.ascontiguousarray(ids, np.int32)
+            idp, nid = ids.ctypes.data_as(C.c_void_p), len(ids)
+        st = self._ck(self.L.lvreg_register_scan(self.h, C.byref(c), C.byref(s), idp, C.c_size_t(nid),
+                                                 pose.ctypes.data_as(C.c_void_p), C.byref(res)),
+                      soft=(ERR_NOT_ENOUGH_FEATURES, ERR_NO_KEYFRAMES, ERR_NO_MAP))
+        return pose, res, st
+
+    def transform_update(self, pose, imu_available=False, imu_roll=0.0, imu_pitch=0.0):
+        pose = np.ascontiguousarray(pose, np.float32).copy()
+        self._ck(self.L.lvreg_transform_update(self.h, pose.ctypes.data_as(C.c_void_p), int(imu_available),
+                                               C.c_float(imu_roll), C.c_float(imu_pitch)))
+        return pose
+
+    def get_degenerate(self):
+        v = C.c_int(0)
+        self._ck(self.L.lvreg_get_degenerate(self.h, C.byref(v)))
+        return v.value
+
+    def reset_lm_state(self):
+        self._ck(self.L.lvreg_reset_lm_state(self.h))
+
+    # ---- stage level ----
+    def transform_cloud(self, pts, pose):
+        c, keep = _cloud(pts)
+        pose = np.ascontiguousarray(pose, np.float32)
+        out = np.zeros((c.n, 4), np.float32)
+        co = CloudOut()
+        co.data = out.ctypes.data if c.n else None
+        co.capacity = c.n
+        co.stride = 16
+        co.intensity_offset = 12
+        self._ck(self.L.lvreg_transform_cloud(self.h, C.byref(c), pose.ctypes.data_as(C.c_void_p), C.byref(co)))
+        return out
+
+    def voxelgrid(self, pts, leaf, pcl_layout_out=False):
+        """returns (filtered cloud, voxel idx per output point, passthrough flag)"""
+        c, keep = _cloud(pts)
+        cols = 8 if pcl_layout_out else 4
+        out = np.zeros((max(c.n, 1), cols), np.float32)
+        keys = np.zeros(max(c.n, 1), np.uint32)
+        co = CloudOut()
+        co.data = out.ctypes.data
+        co.capacity = c.n
+        co.stride = cols * 4
+        co.intensity_offset = 16 if pcl_layout_out else 12
+        n_out = C.c_size_t(0)
+        pt = C.c_int(0)
+        self._ck(self.L.lvreg_voxelgrid(self.h, C.byref(c), C.c_float(leaf), C.byref(co), C.byref(n_out),
+                                        keys.ctypes.data_as(C.c_void_p), C.byref(pt)))
+        return out[:n_out.value].copy(), keys[:n_out.value].copy(), bool(pt.value)
+
+    def voxel_keys(self, pts, leaf):
+        c, keep = _cloud(pts)
+        keys = np.zeros(max(c.n, 1), np.uint32)
+        self._ck(self.L.lvreg_voxel_keys(self.h, C.byref(c), C.c_float(leaf), keys.ctypes.data_as(C.c_void_p)))
+        return keys[:c.n].copy()
+
+    def knn5(self, which, queries, variant=KNN_GRID_GATED):
+        c, keep = _cloud(queries)
+        idx = np.zeros((c.n, 5), np.int32)
+        d2 = np.zeros((c.n, 5), np.float32)
+        self._ck(self.L.lvreg_knn5(self.h, which, C.byref(c), variant, idx.ctypes.data_as(C.c_void_p),
+                                   d2.ctypes.data_as(C.c_void_p)))
+        return idx, d2
+
+    def bench_knn5(self, which, queries, variant, repeats=10):
+        c, keep = _cloud(queries)
+        ms = C.c_float(0)
+        self._ck(self.L.lvreg_bench_knn5(self.h, which, C.byref(c), variant, repeats, C.byref(ms)))
+        return ms.value
+
+    def _residuals(self, fn, pts, pose):
+        c, keep = _cloud(pts)
+        pose = np.ascontiguousarray(pose, np.float32)
+        coeff = np.zeros((c.n, 4), np.float32)
+        flag = np.zeros(c.n, np.uint8)
+        nn = np.zeros((c.n, 5), np.int32)
+        self._ck(fn(self.h, C.byref(c), pose.ctypes.data_as(C.c_void_p), coeff.ctypes.data_as(C.c_void_p),
+                    flag.ctypes.data_as(C.c_void_p), nn.ctypes.data_as(C.c_void_p)))
+        return coeff, flag, nn
+
+    def corner_residuals(self, pts, pose):
+        return self._residuals(self.L.lvreg_corner_residuals, pts, pose)
+
+    def surf_residuals(self, pts, pose):
+        return self._residuals(self.L.lvreg_surf_residuals, pts, pose)
+
+    def lm_step(self, ori, coeff, it, pose):
+        ori = np.ascontiguousarray(ori, np.float32)
+        coeff = np.ascontiguousarray(coeff, np.float32)
+        pose = np.ascontiguousarray(pose, np.float32).copy()
+        AtA = np.zeros((6, 6), np.float32)
+        Atb = np.zeros(6, np.float32)
+        x = np.zeros(6, np.float32)
+        conv = C.c_int(0)
+        self._ck(self.L.lvreg_lm_step(self.h, ori.ctypes.data_as(C.c_void_p), coeff.ctypes.data_as(C.c_void_p),
+                                      C.c_size_t(len(ori)), int(it), pose.ctypes.data_as(C.c_void_p),
+                                      AtA.ctypes.data_as(C.c_void_p), Atb.ctypes.data_as(C.c_void_p),
+                                      x.ctypes.data_as(C.c_void_p), C.byref(conv)))
+        return conv.value, pose, AtA, Atb, x
+
+    # ---- measurement ----
+    def timings(self):
+        t = Timings()
+        self._ck(self.L.lvreg_get_timings(self.h, C.byref(t)))
+        return t
+
+    def launch_count(self):
+        n = C.c_uint64(0)
+        self._ck(self.L.lvreg_get_launch_count(self.h, C.byref(n)))
+        return n.value

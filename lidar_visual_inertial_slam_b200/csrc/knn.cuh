@@ -1,0 +1,321 @@
+// knn.cuh -- exact 5-nearest-neighbour search over a uniform cell grid in HBM; replaces
+// pcl::KdTreeFLANN::setInputCloud (MO:1322-1323) and nearestKSearch(pointSel, 5, ...)
+// (MO:1019, MO:1111).
+//
+// Structure (built once per local map):
+//   cell_pts[m]        float4 {x, y, z, bits(original index)} sorted by cell key (x fastest), so
+//                      the 3 x-adjacent cells of a row are ONE contiguous, coalesced float4 run
+//   cell_start[nc+1]   exclusive prefix of the per-cell counts (dense array)
+//   cell edge          gate radius * (1 + 1/128): any point closer than the gate (sqrt(1.0 m^2),
+//                      MO:1025/1121) lies in the 3x3x3 block around the query's cell, with margin
+//                      for the fp32 rounding of the cell coordinate (dims are capped at 2048/axis)
+//
+// Search: a group of LPQ lanes owns one query.  Lanes fetch the 9 row ranges in parallel, then
+// stride over each row's points (coalesced), each lane keeping a sorted top-5 of 64-bit keys
+// (bits(d2) << 32 | index): unsigned order on that key IS the (d2, index) lexicographic order of
+// the oracle, so ties break deterministically on the smaller index.  Lane lists are merged with
+// 5 rounds of xor-shuffle minimum.  d2 = ((dx*dx)+dy*dy)+dz*dz without FMA (L2_Simple).
+//
+// GATED mode stops after the 3x3x3 block: exact whenever d2[4] < gate (the only case the
+// reference uses).  EXACT mode keeps adding Chebyshev shells until the 5th distance is provably
+// inside the searched cube (or the whole grid was visited).
+#pragma once
+
+#include "common.cuh"
+
+namespace lvreg {
+
+typedef unsigned long long u64;
+constexpr u64 kKeyNone = 0xffffffffffffffffull;
+
+struct GridView {
+    const float4* pts;           // cell-sorted points, w = original index bits
+    const uint32_t* cell_start;  // ncells + 1
+    float ox, oy, oz;            // grid origin (bbox min of the map)
+    float inv;                   // 1 / cell
+    float cell;
+    int dx, dy, dz;              // cells per axis
+    uint32_t m;                  // number of map points
+};
+
+__device__ __forceinline__ u64 make_key(float d2, float idx_bits) {
+    return ((u64)__float_as_uint(d2) << 32) | (u64)__float_as_uint(idx_bits);
+}
+__device__ __forceinline__ float key_d2(u64 k) {
+    return k == kKeyNone ? __int_as_float(0x7f800000) : __uint_as_float((uint32_t)(k >> 32));
+}
+__device__ __forceinline__ int key_idx(u64 k) { return k == kKeyNone ? -1 : (int)(uint32_t)k; }
+
+__device__ __forceinline__ void top5_insert(u64 (&t)[5], u64 key) {
+    if (key < t[4]) {
+        t[4] = key;
+#pragma unroll
+        for (int i = 4; i > 0; --i) {
+            if (t[i] < t[i - 1]) { u64 tmp = t[i]; t[i] = t[i - 1]; t[i - 1] = tmp; }
+        }
+    }
+}
+
+template <int LPQ>
+__device__ __forceinline__ void scan_range(const GridView& g, uint32_t s, uint32_t e, int gl,
+                                           float qx, float qy, float qz, float skip_d2,
+                                           u64 (&t)[5]) {
+    for (uint32_t c = s + gl; c < e; c += LPQ) {
+        float4 p = __ldg(g.pts + c);
+        float d = sqdist(qx, qy, qz, p.x, p.y, p.z);
+        if (d < skip_d2) top5_insert(t, make_key(d, p.w));
+    }
+}
+
+// merge the lane-local lists of a group; every lane of the group returns the same 5 keys
+template <int LPQ>
+__device__ __forceinline__ void group_merge(unsigned gmask, u64 (&t)[5], u64 (&out)[5]) {
+#pragma unroll
+    for (int r = 0; r < 5; ++r) {
+        u64 m = t[0];
+#pragma unroll
+        for (int o = LPQ / 2; o > 0; o >>= 1) {
+            u64 other = __shfl_xor_sync(gmask, m, o);
+            m = other < m ? other : m;
+        }
+        out[r] = m;
+        if (t[0] == m) {                       // the owner pops (keys are unique except kKeyNone)
+            t[0] = t[1]; t[1] = t[2]; t[2] = t[3]; t[3] = t[4]; t[4] = kKeyNone;
+        }
+    }
+}
+
+// cell coordinate along one axis, clamped into the grid; u (unclamped, in cells) is returned too
+__device__ __forceinline__ int cell_coord(float q, float o, float inv, int dim, float* u_out) {
+    float u = (q - o) * inv;
+    *u_out = u;
+    float f = floorf(u);
+    int c = f < 0.f ? 0 : (f > (float)(dim - 1) ? dim - 1 : (int)f);
+    return c;
+}
+
+// One query, LPQ cooperating lanes (gl = lane index inside the group, gmask = the group's lanes).
+// exact == false: 3x3x3 block only, candidates with d2 >= gate_sq are dropped.
+template <int LPQ>
+__device__ __forceinline__ void group_knn5(const GridView& g, float qx, float qy, float qz, int gl,
+                                           unsigned gmask, bool exact, float gate_sq,
+                                           u64 (&best)[5]) {
+    u64 t[5] = {kKeyNone, kKeyNone, kKeyNone, kKeyNone, kKeyNone};
+    float ux, uy, uz;
+    const int cx = cell_coord(qx, g.ox, g.inv, g.dx, &ux);
+    const int cy = cell_coord(qy, g.oy, g.inv, g.dy, &uy);
+    const int cz = cell_coord(qz, g.oz, g.inv, g.dz, &uz);
+    const float skip = exact ? __int_as_float(0x7f800000) : gate_sq;
+    const int lane_base = (threadIdx.x & 31) - gl;
+
+    if (!exact) {
+        // a query more than one cell outside the grid has nothing within the gate
+        bool far = ux < -1.f || uy < -1.f || uz < -1.f || ux > (float)g.dx + 1.f ||
+                   uy > (float)g.dy + 1.f || uz > (float)g.dz + 1.f;
+        if (far) {
+#pragma unroll
+            for (int i = 0; i < 5; ++i) best[i] = kKeyNone;
+            return;
+        }
+    }
+
+    // ---- 3x3x3 block: 9 rows, ranges fetched in parallel by the group's lanes ----
+    constexpr int RPL = (9 + LPQ - 1) / LPQ;
+    uint32_t rs[RPL], re[RPL];
+    const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.dx - 1);
+#pragma unroll
+    for (int k = 0; k < RPL; ++k) {
+        const int r = gl + k * LPQ;
+        rs[k] = 0; re[k] = 0;
+        if (r < 9) {
+            const int yy = cy + (r % 3) - 1, zz = cz + (r / 3) - 1;
+            if (yy >= 0 && yy < g.dy && zz >= 0 && zz < g.dz) {
+                const uint32_t row = ((uint32_t)zz * g.dy + yy) * g.dx;
+                rs[k] = __ldg(g.cell_start + row + x0);
+                re[k] = __ldg(g.cell_start + row + x1 + 1);
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 9; ++r) {
+        const uint32_t s = __shfl_sync(gmask, rs[r / LPQ], lane_base + (r % LPQ));
+        const uint32_t e = __shfl_sync(gmask, re[r / LPQ], lane_base + (r % LPQ));
+        scan_range<LPQ>(g, s, e, gl, qx, qy, qz, skip, t);
+    }
+    group_merge<LPQ>(gmask, t, best);
+    if (!exact) return;
+
+    // ---- exact mode: grow Chebyshev shells until the 5th neighbour is provably inside ----
+    const float sl_x = 0.002f + 4e-7f * fabsf(ux), sl_y = 0.002f + 4e-7f * fabsf(uy),
+                sl_z = 0.002f + 4e-7f * fabsf(uz);
+    for (int r = 1;; ++r) {
+        // distance (in cells) from the query to the nearest face that still hides unvisited cells
+        float bound = 3.0e38f;
+        bool open = false;
+        if (cx - r > 0)        { bound = fminf(bound, ux - (float)(cx - r) - sl_x); open = true; }
+        if (cx + r < g.dx - 1) { bound = fminf(bound, (float)(cx + r + 1) - ux - sl_x); open = true; }
+        if (cy - r > 0)        { bound = fminf(bound, uy - (float)(cy - r) - sl_y); open = true; }
+        if (cy + r < g.dy - 1) { bound = fminf(bound, (float)(cy + r + 1) - uy - sl_y); open = true; }
+        if (cz - r > 0)        { bound = fminf(bound, uz - (float)(cz - r) - sl_z); open = true; }
+        if (cz + r < g.dz - 1) { bound = fminf(bound, (float)(cz + r + 1) - uz - sl_z); open = true; }
+        if (!open) break;                                   // the whole grid has been visited
+        if (best[4] != kKeyNone && bound > 0.f) {
+            float bm = bound * g.cell;
+            if (key_d2(best[4]) <= bm * bm * 0.9999f) break;
+        }
+        if (r >= 16) {
+            // far from any structure: finish with an exhaustive scan (still exact)
+#pragma unroll
+            for (int i = 0; i < 5; ++i) t[i] = kKeyNone;
+            scan_range<LPQ>(g, 0, g.m, gl, qx, qy, qz, skip, t);
+            group_merge<LPQ>(gmask, t, best);
+            break;
+        }
+        // restart the lane lists from the merged result (lane 0 keeps it) and add shell r+1
+        const int rr = r + 1;
+#pragma unroll
+        for (int i = 0; i < 5; ++i) t[i] = gl == 0 ? best[i] : kKeyNone;
+        for (int dzz = -rr; dzz <= rr; ++dzz) {
+            const int zz = cz + dzz;
+            if (zz < 0 || zz >= g.dz) continue;
+            for (int dyy = -rr; dyy <= rr; ++dyy) {
+                const int yy = cy + dyy;
+                if (yy < 0 || yy >= g.dy) continue;
+                const uint32_t row = ((uint32_t)zz * g.dy + yy) * g.dx;
+                const bool full = (dzz == -rr || dzz == rr || dyy == -rr || dyy == rr);
+                if (full) {
+                    const int a = max(cx - rr, 0), b = min(cx + rr, g.dx - 1);
+                    if (a <= b)
+                        scan_range<LPQ>(g, __ldg(g.cell_start + row + a), __ldg(g.cell_start + row + b + 1),
+                                        gl, qx, qy, qz, skip, t);
+                } else {
+                    const int a = cx - rr, b = cx + rr;
+                    if (a >= 0)
+                        scan_range<LPQ>(g, __ldg(g.cell_start + row + a), __ldg(g.cell_start + row + a + 1),
+                                        gl, qx, qy, qz, skip, t);
+                    if (b < g.dx)
+                        scan_range<LPQ>(g, __ldg(g.cell_start + row + b), __ldg(g.cell_start + row + b + 1),
+                                        gl, qx, qy, qz, skip, t);
+                }
+            }
+        }
+        group_merge<LPQ>(gmask, t, best);
+    }
+}
+
+// ---- stage-level kernel: materialised 5-NN (lvreg_knn5) ---------------------------------------
+template <int LPQ>
+__global__ void __launch_bounds__(256) knn5_grid_kernel(GridView g, const float4* __restrict__ queries,
+                                                        uint32_t nq, int exact, float gate_sq,
+                                                        int32_t* __restrict__ idx_out,
+                                                        float* __restrict__ d2_out) {
+    constexpr int QPB = 256 / LPQ;
+    const int lane = threadIdx.x & 31;
+    const int gl = lane % LPQ;
+    const unsigned gmask = (LPQ == 32) ? 0xffffffffu : (((1u << LPQ) - 1u) << (lane - gl));
+    for (uint32_t q = blockIdx.x * QPB + threadIdx.x / LPQ; q < nq; q += gridDim.x * QPB) {
+        float4 p = __ldg(queries + q);
+        u64 best[5];
+        group_knn5<LPQ>(g, p.x, p.y, p.z, gl, gmask, exact != 0, gate_sq, best);
+        if (gl < 5) {
+            u64 k = best[0];
+#pragma unroll
+            for (int i = 1; i < 5; ++i) if (gl == i) k = best[i];
+            idx_out[(size_t)q * 5 + gl] = key_idx(k);
+            d2_out[(size_t)q * 5 + gl] = key_d2(k);
+        }
+    }
+}
+
+// ---- brute force (FP32-pipe bound variant of the micro-benchmark) -----------------------------
+// thread per query, map staged through shared memory in tiles; blockIdx.y splits the map.
+constexpr int kBruteTile = 1024;
+__global__ void __launch_bounds__(256) knn5_brute_kernel(const float4* __restrict__ map, uint32_t m,
+                                                         const float4* __restrict__ queries,
+                                                         uint32_t nq, uint32_t chunk,
+                                                         u64* __restrict__ partial) {
+    __shared__ float4 tile[kBruteTile];
+    const uint32_t q = blockIdx.x * 256 + threadIdx.x;
+    float4 qp = q < nq ? queries[q] : make_float4(0, 0, 0, 0);
+    u64 t[5] = {kKeyNone, kKeyNone, kKeyNone, kKeyNone, kKeyNone};
+    const uint32_t begin = blockIdx.y * chunk;
+    const uint32_t end = min(m, begin + chunk);
+    for (uint32_t base = begin; base < end; base += kBruteTile) {
+        const uint32_t cnt = min((uint32_t)kBruteTile, end - base);
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < cnt; i += 256) tile[i] = ld_stream(map + base + i);
+        __syncthreads();
+#pragma unroll 4
+        for (uint32_t i = 0; i < cnt; ++i) {
+            float4 p = tile[i];
+            float d = sqdist(qp.x, qp.y, qp.z, p.x, p.y, p.z);
+            u64 key = ((u64)__float_as_uint(d) << 32) | (u64)(base + i);
+            top5_insert(t, key);
+        }
+    }
+    if (q < nq) {
+#pragma unroll
+        for (int i = 0; i < 5; ++i) partial[((size_t)blockIdx.y * nq + q) * 5 + i] = t[i];
+    }
+}
+
+__global__ void __launch_bounds__(256) knn5_brute_merge_kernel(const u64* __restrict__ partial,
+                                                               uint32_t nq, uint32_t splits,
+                                                               int32_t* __restrict__ idx_out,
+                                                               float* __restrict__ d2_out) {
+    const uint32_t q = blockIdx.x * 256 + threadIdx.x;
+    if (q >= nq) return;
+    u64 t[5] = {kKeyNone, kKeyNone, kKeyNone, kKeyNone, kKeyNone};
+    for (uint32_t s = 0; s < splits; ++s)
+#pragma unroll
+        for (int i = 0; i < 5; ++i) top5_insert(t, partial[((size_t)s * nq + q) * 5 + i]);
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        idx_out[(size_t)q * 5 + i] = key_idx(t[i]);
+        d2_out[(size_t)q * 5 + i] = key_d2(t[i]);
+    }
+}
+
+// ---- search-grid build ---------------------------------------------------------------------------
+struct GridSpec {
+    float ox, oy, oz, inv, cell;
+    int dx, dy, dz;
+};
+
+__global__ void __launch_bounds__(256) cell_keys_kernel(const float4* __restrict__ pts, uint32_t m,
+                                                        GridSpec gs, uint32_t* __restrict__ keys,
+                                                        uint32_t* __restrict__ vals,
+                                                        uint32_t* __restrict__ counts) {
+    uint32_t i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= m) return;
+    float4 p = pts[i];
+    float u;
+    int cx = cell_coord(p.x, gs.ox, gs.inv, gs.dx, &u);
+    int cy = cell_coord(p.y, gs.oy, gs.inv, gs.dy, &u);
+    int cz = cell_coord(p.z, gs.oz, gs.inv, gs.dz, &u);
+    uint32_t key = ((uint32_t)cz * gs.dy + cy) * gs.dx + cx;
+    keys[i] = key;
+    vals[i] = i;
+    atomicAdd(&counts[key], 1u);
+}
+
+struct CountIn {
+    const uint32_t* c;
+    __device__ __forceinline__ uint32_t operator()(uint32_t i) const { return c[i]; }
+};
+struct StartOut {
+    uint32_t* s;
+    __device__ __forceinline__ void operator()(uint32_t i, uint32_t, uint32_t pre) const { s[i] = pre; }
+};
+
+__global__ void __launch_bounds__(256) cell_gather_kernel(const float4* __restrict__ pts,
+                                                          const uint32_t* __restrict__ sorted_vals,
+                                                          uint32_t m, float4* __restrict__ out) {
+    uint32_t j = blockIdx.x * 256 + threadIdx.x;
+    if (j >= m) return;
+    uint32_t i = sorted_vals[j];
+    float4 p = __ldg(pts + i);
+    out[j] = make_float4(p.x, p.y, p.z, __uint_as_float(i));
+}
+
+}  // namespace lvreg

@@ -1,0 +1,1192 @@
+// lvreg.cu -- handle, device buffers and the C ABI of include/lvreg.h.
+// Host orchestration only: every data-parallel step is one of the sm_100a kernels in
+// voxelgrid.cuh / prims.cuh / knn.cuh / fit.cuh / register.cuh.  There is no CPU fallback:
+// lvreg_create fails without a CUDA device, and nothing here links or loads oracle/.
+#include "../../include/lvreg.h"
+
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "fit.cuh"
+#include "knn.cuh"
+#include "prims.cuh"
+#include "register.cuh"
+#include "voxelgrid.cuh"
+
+using namespace lvreg;
+
+namespace {
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        size_t want = bytes + bytes / 4 + 256;
+        want = (want + 255) & ~(size_t)255;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct Keyframe {
+    DevBuf cloud[2];          // sensor-frame corner / surf, float4
+    uint32_t n[2] = {0, 0};
+    float pose[6] = {0, 0, 0, 0, 0, 0};
+};
+
+struct MapSide {
+    DevBuf ds;                // laserCloud*FromMapDS, float4, VoxelGrid (ascending idx) order
+    DevBuf cell_pts, cell_start;
+    uint32_t m = 0;
+    uint64_t n_in = 0;
+    GridSpec gs{};
+    bool valid = false;
+};
+
+enum { EV_BEGIN = 0, EV_UPLOAD, EV_MAP, EV_GRID, EV_DS, EV_REG, EV_COUNT };
+
+}  // namespace
+
+struct lvreg_handle {
+    lvreg_params prm;
+    int device = 0;
+    cudaStream_t st = nullptr;
+    bool own_stream = false;
+    int num_sms = kNumSMs;
+    int lpq = 8;
+    std::vector<Keyframe*> kfs;
+    MapSide map[2];
+    DevBuf scan_ds[2];
+    uint32_t n_scan[2] = {0, 0};
+    // scratch
+    DevBuf stage[2], raw[2], concat, keys[2], vals[2], sort_scratch, scan_temp, scan_in, vox_start, vox_keys;
+    DevBuf segs, small, partials, regout, lmstate, posebuf, qbuf, idxbuf, d2buf, brute_partial, coeffbuf, flagbuf;
+    void* pinned = nullptr;       // 64 KB page-locked scratch for small transfers
+    cudaEvent_t ev[EV_COUNT];
+    bool ev_set[EV_COUNT];
+    lvreg_timings last{};
+    int call_launches = 0;
+    uint64_t total_launches = 0;
+    std::string err;
+    int reg_max_blocks_per_sm = 0;
+};
+
+namespace {
+
+#define CK(expr)                                                                         \
+    do {                                                                                 \
+        cudaError_t _e = (expr);                                                         \
+        if (_e != cudaSuccess) {                                                         \
+            char _b[512];                                                                \
+            snprintf(_b, sizeof(_b), "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                     __FILE__, __LINE__);                                                \
+            h->err = _b;                                                                 \
+            return LVREG_ERR_CUDA;                                                       \
+        }                                                                                \
+    } while (0)
+
+#define CKS(expr)                       \
+    do {                                \
+        int _s = (expr);                \
+        if (_s != LVREG_OK) return _s;  \
+    } while (0)
+
+inline int fail(lvreg_handle* h, int code, const char* msg) {
+    h->err = msg;
+    return code;
+}
+
+inline uint32_t nblk(uint32_t n, uint32_t per) { return (n + per - 1) / per; }
+
+// small device scalars inside h->small
+enum { SM_MM = 0 /*6 u32*/, SM_NVOX = 8, SM_TOTAL = 9, SM_CONV = 10, SM_WORDS = 64 };
+
+inline void launched(lvreg_handle* h, int k = 1) { h->call_launches += k; }
+
+inline void begin_call(lvreg_handle* h) {
+    h->call_launches = 0;
+    for (int i = 0; i < EV_COUNT; ++i) h->ev_set[i] = false;
+    memset(&h->last, 0, sizeof(h->last));
+}
+inline void mark(lvreg_handle* h, int which) {
+    cudaEventRecord(h->ev[which], h->st);
+    h->ev_set[which] = true;
+}
+inline float span(lvreg_handle* h, int a, int b) {
+    float ms = 0.f;
+    if (h->ev_set[a] && h->ev_set[b]) cudaEventElapsedTime(&ms, h->ev[a], h->ev[b]);
+    return ms;
+}
+inline void end_call(lvreg_handle* h) {
+    h->total_launches += (uint64_t)h->call_launches;
+    h->last.kernel_launches = h->call_launches;
+}
+
+// ---- cloud transfer ----------------------------------------------------------------------------
+int check_cloud(lvreg_handle* h, const lvreg_cloud* c) {
+    if (!c) return fail(h, LVREG_ERR_INVALID, "null cloud");
+    if (c->n && !c->data) return fail(h, LVREG_ERR_INVALID, "cloud has n > 0 but no data");
+    if (c->stride < 16 || (c->stride & 3) || c->intensity_offset + 4 > c->stride || (c->intensity_offset & 3))
+        return fail(h, LVREG_ERR_INVALID, "bad cloud stride / intensity_offset");
+    if (c->n > 0x7fffffffull) return fail(h, LVREG_ERR_INVALID, "cloud too large");
+    return LVREG_OK;
+}
+
+// any layout (host or device) -> device float4 {x,y,z,intensity}
+int upload_cloud(lvreg_handle* h, const lvreg_cloud* c, DevBuf& dst, int slot) {
+    CKS(check_cloud(h, c));
+    const uint32_t n = (uint32_t)c->n;
+    CK(dst.reserve((size_t)(n ? n : 1) * 16));
+    if (n == 0) return LVREG_OK;
+    const bool packed = c->stride == 16 && c->intensity_offset == 12;
+    if (packed) {
+        CK(cudaMemcpyAsync(dst.p, c->data, (size_t)n * 16,
+                           c->on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->st));
+        return LVREG_OK;
+    }
+    const uint8_t* src = (const uint8_t*)c->data;
+    if (!c->on_device) {
+        CK(h->stage[slot].reserve((size_t)n * c->stride));
+        CK(cudaMemcpyAsync(h->stage[slot].p, c->data, (size_t)n * c->stride, cudaMemcpyHostToDevice, h->st));
+        src = h->stage[slot].as<uint8_t>();
+    }
+    uint32_t stride_flag = c->stride;
+    if (((uintptr_t)src & 15) != 0 && (stride_flag & 15) == 0) {
+        // unaligned device pointer: force the scalar path of pack_kernel
+        return fail(h, LVREG_ERR_INVALID, "device clouds must be 16-byte aligned");
+    }
+    pack_kernel<<<nblk(n, 256), 256, 0, h->st>>>(src, n, c->stride, c->intensity_offset, dst.as<float4>());
+    launched(h);
+    CK(cudaGetLastError());
+    return LVREG_OK;
+}
+
+int download_cloud(lvreg_handle* h, const float4* src, uint32_t n, lvreg_cloud_out* out) {
+    if (!out || (!out->data && n)) return fail(h, LVREG_ERR_INVALID, "null output cloud");
+    if (out->capacity < n) return fail(h, LVREG_ERR_CAPACITY, "output cloud too small");
+    if (out->stride < 16 || (out->stride & 3) || out->intensity_offset + 4 > out->stride)
+        return fail(h, LVREG_ERR_INVALID, "bad output stride / intensity_offset");
+    if (n == 0) return LVREG_OK;
+    const bool packed = out->stride == 16 && out->intensity_offset == 12;
+    if (packed) {
+        CK(cudaMemcpyAsync(out->data, src, (size_t)n * 16,
+                           out->on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, h->st));
+    } else if (out->on_device) {
+        CK(cudaMemsetAsync(out->data, 0, (size_t)n * out->stride, h->st));
+        unpack_kernel<<<nblk(n, 256), 256, 0, h->st>>>(src, n, out->stride, out->intensity_offset, (uint8_t*)out->data);
+        launched(h);
+    } else {
+        CK(h->stage[0].reserve((size_t)n * out->stride));
+        CK(cudaMemsetAsync(h->stage[0].p, 0, (size_t)n * out->stride, h->st));
+        unpack_kernel<<<nblk(n, 256), 256, 0, h->st>>>(src, n, out->stride, out->intensity_offset, h->stage[0].as<uint8_t>());
+        launched(h);
+        CK(cudaMemcpyAsync(out->data, h->stage[0].p, (size_t)n * out->stride, cudaMemcpyDeviceToHost, h->st));
+    }
+    CK(cudaStreamSynchronize(h->st));
+    return LVREG_OK;
+}
+
+// ---- VoxelGrid driver ------------------------------------------------------------------------------
+int bits_for(uint64_t max_value) {
+    int b = 1;
+    while (b < 32 && (max_value >> b) != 0) ++b;
+    return b;
+}
+
+int reset_minmax(lvreg_handle* h) {
+    uint32_t* mm = h->small.as<uint32_t>() + SM_MM;
+    CK(cudaMemsetAsync(mm, 0xff, 3 * sizeof(uint32_t), h->st));
+    CK(cudaMemsetAsync(mm + 3, 0, 3 * sizeof(uint32_t), h->st));
+    return LVREG_OK;
+}
+
+int read_minmax(lvreg_handle* h, float mn[3], float mx[3]) {
+    uint32_t* host = (uint32_t*)h->pinned;
+    CK(cudaMemcpyAsync(host, h->small.as<uint32_t>() + SM_MM, 6 * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    for (int a = 0; a < 3; ++a) {
+        mn[a] = ordered_to_float(host[a]);
+        mx[a] = ordered_to_float(host[3 + a]);
+    }
+    return LVREG_OK;
+}
+
+int ensure_sort_buffers(lvreg_handle* h, uint32_t n) {
+    for (int i = 0; i < 2; ++i) {
+        CK(h->keys[i].reserve((size_t)n * 4));
+        CK(h->vals[i].reserve((size_t)n * 4));
+    }
+    CK(h->sort_scratch.reserve(sort_scratch_words(n) * 4));
+    CK(h->scan_temp.reserve((size_t)(scan_num_tiles(n) + 1) * 4));
+    return LVREG_OK;
+}
+
+// pts: device float4[n] (bbox already in h->small when bbox_known).  Writes the filtered cloud to
+// `out`, the count to *n_out.  d_point_keys (optional device, n) gets the per-point voxel idx.
+int voxelgrid_dev(lvreg_handle* h, const float4* pts, uint32_t n, float leaf, bool bbox_known,
+                  DevBuf& out, uint32_t* n_out, bool want_out_keys, uint32_t* d_point_keys,
+                  int* passthrough) {
+    if (passthrough) *passthrough = 0;
+    *n_out = 0;
+    if (n == 0) {
+        CK(out.reserve(16));
+        return LVREG_OK;
+    }
+    if (!(leaf > 0.f)) return fail(h, LVREG_ERR_INVALID, "leaf size must be positive");
+    if (!bbox_known) {
+        CKS(reset_minmax(h));
+        minmax_kernel<<<min(nblk(n, 256), (uint32_t)h->num_sms * 8), 256, 0, h->st>>>(pts, n, h->small.as<uint32_t>() + SM_MM);
+        launched(h);
+    }
+    float mn[3], mx[3];
+    CKS(read_minmax(h, mn, mx));
+    // PCL voxel_grid.hpp: leaf-size overflow rule and bounds, fp32 exactly as PCL computes them
+    const float inv = 1.0f / leaf;
+    int64_t d[3];
+    for (int a = 0; a < 3; ++a) d[a] = (int64_t)((mx[a] - mn[a]) * inv) + 1;
+    if (d[0] * d[1] * d[2] > (int64_t)INT32_MAX) {
+        CK(out.reserve((size_t)n * 16));
+        CK(cudaMemcpyAsync(out.p, pts, (size_t)n * 16, cudaMemcpyDeviceToDevice, h->st));
+        if (d_point_keys) CK(cudaMemsetAsync(d_point_keys, 0, (size_t)n * 4, h->st));
+        *n_out = n;
+        if (passthrough) *passthrough = 1;
+        return LVREG_OK;
+    }
+    VoxelSpec vs;
+    vs.inv = inv;
+    int div_b[3];
+    for (int a = 0; a < 3; ++a) {
+        vs.min_b[a] = (int)floorf(mn[a] * inv);
+        int max_b = (int)floorf(mx[a] * inv);
+        div_b[a] = max_b - vs.min_b[a] + 1;
+    }
+    vs.mul[0] = 1;
+    vs.mul[1] = div_b[0];
+    vs.mul[2] = div_b[0] * div_b[1];
+    vs.key_bits = bits_for((uint64_t)div_b[0] * div_b[1] * div_b[2] - 1);
+
+    CKS(ensure_sort_buffers(h, n));
+    voxel_keys_kernel<<<nblk(n, 256), 256, 0, h->st>>>(pts, n, vs, h->keys[0].as<uint32_t>(), h->vals[0].as<uint32_t>());
+    launched(h);
+    if (d_point_keys)
+        CK(cudaMemcpyAsync(d_point_keys, h->keys[0].p, (size_t)n * 4, cudaMemcpyDeviceToDevice, h->st));
+    int cur = radix_sort_pairs(h->keys[0].as<uint32_t>(), h->vals[0].as<uint32_t>(), h->keys[1].as<uint32_t>(),
+                               h->vals[1].as<uint32_t>(), n, vs.key_bits, h->sort_scratch.as<uint32_t>(), h->st,
+                               &h->call_launches);
+    const uint32_t* skeys = h->keys[cur].as<uint32_t>();
+    const uint32_t* svals = h->vals[cur].as<uint32_t>();
+    CK(h->vox_start.reserve((size_t)n * 4));
+    uint32_t* d_nvox = h->small.as<uint32_t>() + SM_NVOX;
+    exclusive_scan(HeadFlagIn{skeys}, VoxelStartOut{h->vox_start.as<uint32_t>()}, n, h->scan_temp.as<uint32_t>(),
+                   d_nvox, h->st, &h->call_launches);
+    uint32_t* host = (uint32_t*)h->pinned;
+    CK(cudaMemcpyAsync(host, d_nvox, 4, cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    const uint32_t nvox = host[0];
+    CK(out.reserve((size_t)nvox * 16));
+    uint32_t* okeys = nullptr;
+    if (want_out_keys) {
+        CK(h->vox_keys.reserve((size_t)nvox * 4));
+        okeys = h->vox_keys.as<uint32_t>();
+    }
+    centroid_kernel<<<nblk(nvox, 128), 128, 0, h->st>>>(pts, skeys, svals, h->vox_start.as<uint32_t>(), d_nvox, n,
+                                                        out.as<float4>(), okeys);
+    launched(h);
+    CK(cudaGetLastError());
+    *n_out = nvox;
+    return LVREG_OK;
+}
+
+// ---- search-grid build -----------------------------------------------------------------------------
+int build_grid(lvreg_handle* h, MapSide& ms) {
+    const uint32_t m = ms.m;
+    GridSpec gs;
+    const float gate_r = sqrtf(h->prm.knn_gate_sq);
+    float cell = gate_r * (1.0f + 1.0f / 128.0f);
+    if (m == 0) {
+        gs.ox = gs.oy = gs.oz = 0.f;
+        gs.cell = cell;
+        gs.inv = 1.0f / cell;
+        gs.dx = gs.dy = gs.dz = 1;
+        CK(ms.cell_start.reserve(2 * 4));
+        CK(cudaMemsetAsync(ms.cell_start.p, 0, 8, h->st));
+        CK(ms.cell_pts.reserve(16));
+        ms.gs = gs;
+        return LVREG_OK;
+    }
+    CKS(reset_minmax(h));
+    minmax_kernel<<<min(nblk(m, 256), (uint32_t)h->num_sms * 8), 256, 0, h->st>>>(ms.ds.as<float4>(), m, h->small.as<uint32_t>() + SM_MM);
+    launched(h);
+    float mn[3], mx[3];
+    CKS(read_minmax(h, mn, mx));
+    for (;;) {
+        const float inv = 1.0f / cell;
+        int64_t dims[3];
+        bool ok = true;
+        for (int a = 0; a < 3; ++a) {
+            dims[a] = (int64_t)floorf((mx[a] - mn[a]) * inv) + 1;
+            if (dims[a] > 2048 || dims[a] < 1) ok = false;
+        }
+        if (ok && dims[0] * dims[1] * dims[2] <= (int64_t)(1 << 26)) {
+            gs.ox = mn[0]; gs.oy = mn[1]; gs.oz = mn[2];
+            gs.cell = cell;
+            gs.inv = inv;
+            gs.dx = (int)dims[0]; gs.dy = (int)dims[1]; gs.dz = (int)dims[2];
+            break;
+        }
+        cell *= 2.0f;       // coarser cells stay exact, they only add candidates
+        if (!(cell < 1e30f)) return fail(h, LVREG_ERR_INVALID, "map extent is not finite");
+    }
+    const uint32_t ncells = (uint32_t)gs.dx * gs.dy * gs.dz;
+    CKS(ensure_sort_buffers(h, m));
+    CK(h->scan_in.reserve((size_t)(ncells + 1) * 4));
+    CK(ms.cell_start.reserve((size_t)(ncells + 1) * 4));
+    CK(ms.cell_pts.reserve((size_t)m * 16));
+    CK(h->scan_temp.reserve((size_t)(scan_num_tiles(ncells + 1) + 1) * 4));
+    CK(cudaMemsetAsync(h->scan_in.p, 0, (size_t)(ncells + 1) * 4, h->st));
+    cell_keys_kernel<<<nblk(m, 256), 256, 0, h->st>>>(ms.ds.as<float4>(), m, gs, h->keys[0].as<uint32_t>(),
+                                                      h->vals[0].as<uint32_t>(), h->scan_in.as<uint32_t>());
+    launched(h);
+    exclusive_scan(CountIn{h->scan_in.as<uint32_t>()}, StartOut{ms.cell_start.as<uint32_t>()}, ncells + 1,
+                   h->scan_temp.as<uint32_t>(), h->small.as<uint32_t>() + SM_TOTAL, h->st, &h->call_launches);
+    int cur = radix_sort_pairs(h->keys[0].as<uint32_t>(), h->vals[0].as<uint32_t>(), h->keys[1].as<uint32_t>(),
+                               h->vals[1].as<uint32_t>(), m, bits_for(ncells - 1), h->sort_scratch.as<uint32_t>(),
+                               h->st, &h->call_launches);
+    cell_gather_kernel<<<nblk(m, 256), 256, 0, h->st>>>(ms.ds.as<float4>(), h->vals[cur].as<uint32_t>(), m,
+                                                        ms.cell_pts.as<float4>());
+    launched(h);
+    CK(cudaGetLastError());
+    ms.gs = gs;
+    return LVREG_OK;
+}
+
+GridView grid_view(const MapSide& ms) {
+    GridView g;
+    g.pts = ms.cell_pts.as<float4>();
+    g.cell_start = ms.cell_start.as<uint32_t>();
+    g.ox = ms.gs.ox; g.oy = ms.gs.oy; g.oz = ms.gs.oz;
+    g.inv = ms.gs.inv;
+    g.cell = ms.gs.cell;
+    g.dx = ms.gs.dx; g.dy = ms.gs.dy; g.dz = ms.gs.dz;
+    g.m = ms.m;
+    return g;
+}
+
+RegParams reg_params(const lvreg_handle* h) {
+    RegParams P;
+    P.knn_gate_sq = h->prm.knn_gate_sq;
+    P.line_eig_ratio = h->prm.line_eig_ratio;
+    P.plane_tol = h->prm.plane_tol;
+    P.min_weight = h->prm.min_weight;
+    P.degeneracy_eig = h->prm.degeneracy_eig;
+    P.conv_deg = h->prm.conv_deg;
+    P.conv_cm = h->prm.conv_cm;
+    P.min_matches = h->prm.min_matches;
+    P.max_iters = h->prm.max_iters;
+    P.reference_quirks = h->prm.reference_quirks;
+    return P;
+}
+
+void fill_map_info(const lvreg_handle* h, lvreg_map_info* info) {
+    if (!info) return;
+    memset(info, 0, sizeof(*info));
+    info->n_corner_in = h->map[0].n_in;
+    info->n_surf_in = h->map[1].n_in;
+    info->n_corner_ds = h->map[0].m;
+    info->n_surf_ds = h->map[1].m;
+    for (int s = 0; s < 2; ++s) {
+        info->grid_dims[s][0] = h->map[s].gs.dx;
+        info->grid_dims[s][1] = h->map[s].gs.dy;
+        info->grid_dims[s][2] = h->map[s].gs.dz;
+        info->grid_cell[s] = h->map[s].gs.cell;
+    }
+}
+
+// host restatement of pcl::getTransformation (PCL common/impl/eigen.hpp), fp32, libm sinf/cosf:
+// computed on the host so that the kernels receive bit-identical matrices
+void pose_to_affine_host(const float pose[6], float T[12]) {
+    const float roll = pose[0], pitch = pose[1], yaw = pose[2];
+    float A = cosf(yaw), B = sinf(yaw), C = cosf(pitch), D = sinf(pitch), E = cosf(roll), F = sinf(roll);
+    float DE = D * E, DF = D * F;
+    T[0] = A * C;  T[1] = A * DF - B * E;  T[2]  = B * F + A * DE;  T[3]  = pose[3];
+    T[4] = B * C;  T[5] = A * E + B * DF;  T[6]  = B * DE - A * F;  T[7]  = pose[4];
+    T[8] = -D;     T[9] = C * F;           T[10] = C * E;           T[11] = pose[5];
+}
+
+int build_local_map_impl(lvreg_handle* h, const int32_t* ids, size_t n_ids) {
+    if (h->kfs.empty()) return fail(h, LVREG_ERR_NO_KEYFRAMES, "no keyframes");
+    for (size_t i = 0; i < n_ids; ++i)
+        if (ids[i] < 0 || (size_t)ids[i] >= h->kfs.size()) return fail(h, LVREG_ERR_INVALID, "keyframe id out of range");
+    std::vector<Segment> segs(n_ids ? n_ids : 1);
+    for (int s = 0; s < 2; ++s) {
+        MapSide& ms = h->map[s];
+        uint64_t total = 0;
+        for (size_t i = 0; i < n_ids; ++i) {
+            const Keyframe* kf = h->kfs[ids[i]];
+            segs[i].src = kf->cloud[s].as<float4>();
+            segs[i].begin = (uint32_t)total;
+            segs[i].n = kf->n[s];
+            pose_to_affine_host(kf->pose, segs[i].T.m);
+            total += kf->n[s];
+        }
+        if (total > 0x7fffffffull) return fail(h, LVREG_ERR_INVALID, "local map too large");
+        ms.n_in = total;
+        uint32_t m = 0;
+        if (total > 0) {
+            // drop empty segments so that the binary search over `begin` is well defined
+            std::vector<Segment> live;
+            live.reserve(n_ids);
+            for (size_t i = 0; i < n_ids; ++i)
+                if (segs[i].n) live.push_back(segs[i]);
+            CK(h->segs.reserve(live.size() * sizeof(Segment)));
+            CK(cudaMemcpyAsync(h->segs.p, live.data(), live.size() * sizeof(Segment), cudaMemcpyHostToDevice, h->st));
+            CK(h->concat.reserve((size_t)total * 16));
+            CKS(reset_minmax(h));
+            transform_concat_kernel<<<min(nblk((uint32_t)total, 256), (uint32_t)h->num_sms * 16), 256, 0, h->st>>>(
+                h->segs.as<Segment>(), (uint32_t)live.size(), (uint32_t)total, h->concat.as<float4>(),
+                h->small.as<uint32_t>() + SM_MM);
+            launched(h);
+            CK(cudaStreamSynchronize(h->st));    // `live` must outlive the async copy
+            CKS(voxelgrid_dev(h, h->concat.as<float4>(), (uint32_t)total, s == 0 ? h->prm.corner_leaf : h->prm.surf_leaf,
+                              true, ms.ds, &m, false, nullptr, nullptr));
+        } else {
+            CK(ms.ds.reserve(16));
+        }
+        ms.m = m;
+    }
+    mark(h, EV_MAP);
+    for (int s = 0; s < 2; ++s) {
+        CKS(build_grid(h, h->map[s]));
+        h->map[s].valid = true;
+    }
+    mark(h, EV_GRID);
+    return LVREG_OK;
+}
+
+int downsample_impl(lvreg_handle* h, const lvreg_cloud* corner_raw, const lvreg_cloud* surf_raw) {
+    CKS(upload_cloud(h, corner_raw, h->raw[0], 0));
+    CKS(upload_cloud(h, surf_raw, h->raw[1], 1));
+    mark(h, EV_UPLOAD);
+    CKS(voxelgrid_dev(h, h->raw[0].as<float4>(), (uint32_t)corner_raw->n, h->prm.corner_leaf, false, h->scan_ds[0],
+                      &h->n_scan[0], false, nullptr, nullptr));
+    CKS(voxelgrid_dev(h, h->raw[1].as<float4>(), (uint32_t)surf_raw->n, h->prm.surf_leaf, false, h->scan_ds[1],
+                      &h->n_scan[1], false, nullptr, nullptr));
+    mark(h, EV_DS);
+    return LVREG_OK;
+}
+
+float clampf(float v, float lim) {
+    if (v < -lim) v = -lim;
+    if (v > lim) v = lim;
+    return v;
+}
+
+template <int LPQ>
+int launch_register(lvreg_handle* h, RegArgs& args, int grid) {
+    void* kargs[] = {&args};
+    CK(cudaLaunchCooperativeKernel((void*)register_kernel<LPQ>, dim3(grid), dim3(kRegThreads), kargs, 0, h->st));
+    return LVREG_OK;
+}
+
+template <int LPQ>
+int reg_occupancy(lvreg_handle* h, int* nb) {
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(nb, register_kernel<LPQ>, kRegThreads, 0));
+    return LVREG_OK;
+}
+
+int scan2map_impl(lvreg_handle* h, float pose[6], lvreg_result* res) {
+    if (res) {
+        memset(res, 0, sizeof(*res));
+        res->n_corner_ds = (int)h->n_scan[0];
+        res->n_surf_ds = (int)h->n_scan[1];
+        res->n_corner_map = (int)h->map[0].m;
+        res->n_surf_map = (int)h->map[1].m;
+    }
+    if (!h->map[0].valid || !h->map[1].valid)
+        return fail(h, h->kfs.empty() ? LVREG_ERR_NO_KEYFRAMES : LVREG_ERR_NO_MAP, "no local map");
+    if (!((int)h->n_scan[0] > h->prm.edge_min_valid && (int)h->n_scan[1] > h->prm.surf_min_valid)) {
+        if (res) { /* isDegenerate keeps its previous value (MO:131) */
+            LmState st;
+            cudaMemcpyAsync(&st, h->lmstate.p, sizeof(int), cudaMemcpyDeviceToHost, h->st);
+            cudaStreamSynchronize(h->st);
+            res->degenerate = st.is_degenerate;
+        }
+        return fail(h, LVREG_ERR_NOT_ENOUGH_FEATURES, "not enough features");
+    }
+    float* hp = (float*)h->pinned;
+    memcpy(hp, pose, 6 * sizeof(float));
+    CK(cudaMemcpyAsync(h->posebuf.p, hp, 6 * sizeof(float), cudaMemcpyHostToDevice, h->st));
+
+    RegArgs args;
+    for (int s = 0; s < 2; ++s) {
+        args.grid[s] = grid_view(h->map[s]);
+        args.map[s] = h->map[s].ds.as<float4>();
+        args.scan[s] = h->scan_ds[s].as<float4>();
+        args.n[s] = h->n_scan[s];
+    }
+    args.prm = reg_params(h);
+    args.pose_in = h->posebuf.as<float>();
+    args.out = h->regout.as<RegOut>();
+    args.lm = h->lmstate.as<LmState>();
+
+    if (h->reg_max_blocks_per_sm == 0) {
+        int nb = 0;
+        switch (h->lpq) {
+            case 4: CKS(reg_occupancy<4>(h, &nb)); break;
+            case 16: CKS(reg_occupancy<16>(h, &nb)); break;
+            case 32: CKS(reg_occupancy<32>(h, &nb)); break;
+            default: CKS(reg_occupancy<8>(h, &nb)); break;
+        }
+        if (nb < 1) return fail(h, LVREG_ERR_CUDA, "register_kernel does not fit on an SM");
+        h->reg_max_blocks_per_sm = nb;
+    }
+    const uint32_t tiles = nblk(h->n_scan[0], 32) + nblk(h->n_scan[1], 32);
+    int grid = (int)nblk(tiles, kRegWarps);
+    const int max_grid = h->reg_max_blocks_per_sm * h->num_sms;
+    if (grid > max_grid) grid = max_grid;
+    if (grid < 1) grid = 1;
+    CK(h->partials.reserve((size_t)2 * grid * kRegTerms * sizeof(double)));
+    args.partials = h->partials.as<double>();
+
+    switch (h->lpq) {
+        case 4: CKS(launch_register<4>(h, args, grid)); break;
+        case 16: CKS(launch_register<16>(h, args, grid)); break;
+        case 32: CKS(launch_register<32>(h, args, grid)); break;
+        default: CKS(launch_register<8>(h, args, grid)); break;
+    }
+    launched(h);
+    RegOut* ho = (RegOut*)((char*)h->pinned + 256);
+    CK(cudaMemcpyAsync(ho, h->regout.p, sizeof(RegOut), cudaMemcpyDeviceToHost, h->st));
+    mark(h, EV_REG);
+    CK(cudaStreamSynchronize(h->st));
+    for (int i = 0; i < 6; ++i) pose[i] = ho->pose[i];
+    // transformUpdate's clamps (MO:1370-1372); the IMU slerp is lvreg_transform_update
+    pose[0] = clampf(pose[0], h->prm.rotation_tolerance);
+    pose[1] = clampf(pose[1], h->prm.rotation_tolerance);
+    pose[5] = clampf(pose[5], h->prm.z_tolerance);
+    if (res) {
+        res->iterations = ho->iterations;
+        res->converged = ho->converged;
+        res->degenerate = ho->degenerate;
+        const int k = h->prm.max_iters < LVREG_MAX_ITERS ? h->prm.max_iters : LVREG_MAX_ITERS;
+        for (int i = 0; i < k; ++i) {
+            res->n_sel[i] = i < ho->iterations ? ho->n_sel[i] : 0;
+            res->cost[i] = i < ho->iterations ? ho->cost[i] : 0.f;
+            for (int j = 0; j < 6; ++j) res->pose_iter[i][j] = i < ho->iterations ? ho->pose_iter[i][j] : 0.f;
+        }
+    }
+    return LVREG_OK;
+}
+
+void finish_timings(lvreg_handle* h) {
+    // stages are recorded in call order; absent stages read 0
+    int last = EV_BEGIN;
+    for (int i = 0; i < EV_COUNT; ++i) if (h->ev_set[i]) last = i;
+    h->last.total_ms = span(h, EV_BEGIN, last);
+}
+
+}  // namespace
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+extern "C" {
+
+void lvreg_default_params(lvreg_params* p) {
+    memset(p, 0, sizeof(*p));
+    p->corner_leaf = 0.2f;
+    p->surf_leaf = 0.4f;
+    p->edge_min_valid = 10;
+    p->surf_min_valid = 100;
+    p->max_iters = 20;
+    p->knn_gate_sq = 1.0f;
+    p->line_eig_ratio = 3.0f;
+    p->plane_tol = 0.2f;
+    p->min_weight = 0.1f;
+    p->min_matches = 50;
+    p->degeneracy_eig = 100.0f;
+    p->conv_deg = 0.05f;
+    p->conv_cm = 0.05f;
+    p->reference_quirks = 1;
+    p->rotation_tolerance = 1000.0f;
+    p->z_tolerance = 1000.0f;
+    p->imu_rpy_weight = 0.01f;
+}
+
+int lvreg_version(void) { return 100; }
+
+const char* lvreg_status_string(int s) {
+    switch (s) {
+        case LVREG_OK: return "ok";
+        case LVREG_ERR_INVALID: return "invalid argument";
+        case LVREG_ERR_CUDA: return "CUDA error";
+        case LVREG_ERR_NOT_ENOUGH_FEATURES: return "not enough features";
+        case LVREG_ERR_NO_KEYFRAMES: return "no keyframes";
+        case LVREG_ERR_NO_MAP: return "no local map";
+        case LVREG_ERR_CAPACITY: return "output buffer too small";
+        default: return "unknown status";
+    }
+}
+
+const char* lvreg_last_error(const lvreg_handle* h) { return h ? h->err.c_str() : "null handle"; }
+
+void* lvreg_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) return nullptr;
+    return p;
+}
+void lvreg_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
+int lvreg_create(const lvreg_params* p, int device, void* cuda_stream, lvreg_handle** out) {
+    if (!out) return LVREG_ERR_INVALID;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0 || device < 0 || device >= count)
+        return LVREG_ERR_CUDA;                      // no CPU fallback
+    lvreg_handle* h = new lvreg_handle();
+    if (p) h->prm = *p; else lvreg_default_params(&h->prm);
+    if (h->prm.max_iters < 1) h->prm.max_iters = 1;
+    if (h->prm.max_iters > LVREG_MAX_ITERS) h->prm.max_iters = LVREG_MAX_ITERS;
+    h->device = device;
+    auto bail = [&](int code) { lvreg_destroy(h); return code; };
+    if (cudaSetDevice(device) != cudaSuccess) return bail(LVREG_ERR_CUDA);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return bail(LVREG_ERR_CUDA);
+    if (!prop.cooperativeLaunch) return bail(LVREG_ERR_CUDA);
+    h->num_sms = prop.multiProcessorCount;
+    if (cuda_stream) {
+        h->st = (cudaStream_t)cuda_stream;
+    } else {
+        if (cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking) != cudaSuccess) return bail(LVREG_ERR_CUDA);
+        h->own_stream = true;
+    }
+    for (int i = 0; i < EV_COUNT; ++i) {
+        h->ev[i] = nullptr;
+        if (cudaEventCreate(&h->ev[i]) != cudaSuccess) return bail(LVREG_ERR_CUDA);
+        h->ev_set[i] = false;
+    }
+    if (cudaMallocHost(&h->pinned, 65536) != cudaSuccess) return bail(LVREG_ERR_CUDA);
+    if (h->small.reserve(SM_WORDS * 4) != cudaSuccess || h->regout.reserve(sizeof(RegOut)) != cudaSuccess ||
+        h->lmstate.reserve(sizeof(LmState)) != cudaSuccess || h->posebuf.reserve(256) != cudaSuccess)
+        return bail(LVREG_ERR_CUDA);
+    cudaMemsetAsync(h->lmstate.p, 0, sizeof(LmState), h->st);
+    cudaMemsetAsync(h->small.p, 0, SM_WORDS * 4, h->st);
+    const char* e = getenv("LVREG_LPQ");
+    if (e) {
+        int v = atoi(e);
+        if (v == 4 || v == 8 || v == 16 || v == 32) h->lpq = v;
+    }
+    if (cudaStreamSynchronize(h->st) != cudaSuccess) return bail(LVREG_ERR_CUDA);
+    *out = h;
+    return LVREG_OK;
+}
+
+void lvreg_destroy(lvreg_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->st) cudaStreamSynchronize(h->st);
+    for (Keyframe* kf : h->kfs) {
+        kf->cloud[0].release();
+        kf->cloud[1].release();
+        delete kf;
+    }
+    for (int s = 0; s < 2; ++s) {
+        h->map[s].ds.release(); h->map[s].cell_pts.release(); h->map[s].cell_start.release();
+        h->scan_ds[s].release(); h->stage[s].release(); h->raw[s].release();
+        h->keys[s].release(); h->vals[s].release();
+    }
+    DevBuf* bufs[] = {&h->concat, &h->sort_scratch, &h->scan_temp, &h->scan_in, &h->vox_start, &h->vox_keys,
+                      &h->segs, &h->small, &h->partials, &h->regout, &h->lmstate, &h->posebuf, &h->qbuf,
+                      &h->idxbuf, &h->d2buf, &h->brute_partial, &h->coeffbuf, &h->flagbuf};
+    for (DevBuf* b : bufs) b->release();
+    if (h->pinned) cudaFreeHost(h->pinned);
+    for (int i = 0; i < EV_COUNT; ++i)
+        if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    if (h->own_stream && h->st) cudaStreamDestroy(h->st);
+    delete h;
+}
+
+// ---- keyframes -----------------------------------------------------------------------------------
+int lvreg_add_keyframe(lvreg_handle* h, const lvreg_cloud* corner, const lvreg_cloud* surf,
+                       const float pose[6], int32_t* id_out) {
+    if (!h || !pose) return LVREG_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    begin_call(h);
+    Keyframe* kf = new Keyframe();
+    int s0 = upload_cloud(h, corner, kf->cloud[0], 0);
+    int s1 = s0 == LVREG_OK ? upload_cloud(h, surf, kf->cloud[1], 1) : s0;
+    if (s1 != LVREG_OK || cudaStreamSynchronize(h->st) != cudaSuccess) {
+        kf->cloud[0].release();
+        kf->cloud[1].release();
+        delete kf;
+        return s1 != LVREG_OK ? s1 : LVREG_ERR_CUDA;
+    }
+    kf->n[0] = (uint32_t)corner->n;
+    kf->n[1] = (uint32_t)surf->n;
+    memcpy(kf->pose, pose, sizeof(kf->pose));
+    h->kfs.push_back(kf);
+    if (id_out) *id_out = (int32_t)h->kfs.size() - 1;
+    end_call(h);
+    return LVREG_OK;
+}
+
+int lvreg_update_keyframe_poses(lvreg_handle* h, const float* poses, size_t n) {
+    if (!h || (!poses && n)) return LVREG_ERR_INVALID;
+    if (n > h->kfs.size()) return fail(h, LVREG_ERR_INVALID, "more poses than keyframes");
+    for (size_t i = 0; i < n; ++i) memcpy(h->kfs[i]->pose, poses + 6 * i, 6 * sizeof(float));
+    // the reference drops laserCloudMapContainer here (MO:1623); this library re-transforms on
+    // every build, so only the current local map becomes stale
+    h->map[0].valid = h->map[1].valid = false;
+    return LVREG_OK;
+}
+
+int lvreg_num_keyframes(const lvreg_handle* h, size_t* n) {
+    if (!h || !n) return LVREG_ERR_INVALID;
+    *n = h->kfs.size();
+    return LVREG_OK;
+}
+
+int lvreg_clear_keyframes(lvreg_handle* h) {
+    if (!h) return LVREG_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->st));
+    for (Keyframe* kf : h->kfs) {
+        kf->cloud[0].release();
+        kf->cloud[1].release();
+        delete kf;
+    }
+    h->kfs.clear();
+    h->map[0].valid = h->map[1].valid = false;
+    return LVREG_OK;
+}
+
+// ---- local map -----------------------------------------------------------------------------------
+int lvreg_build_local_map(lvreg_handle* h, const int32_t* ids, size_t n, lvreg_map_info* info) {
+    if (!h || (!ids && n)) return LVREG_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    begin_call(h);
+    mark(h, EV_BEGIN);
+    CKS(build_local_map_impl(h, ids, n));
+    CK(cudaStreamSynchronize(h->st));
+    h->last.map_build_ms = span(h, EV_BEGIN, EV_MAP);
+    h->last.grid_build_ms = span(h, EV_MAP, EV_GRID);
+    finish_timings(h);
+    end_call(h);
+    fill_map_info(h, info);
+    return LVREG_OK;
+}
+
+int lvreg_set_local_map(lvreg_handle* h, const lvreg_cloud* corner_ds, const lvreg_cloud* surf_ds,
+                        lvreg_map_info* info) {
+    if (!h) return LVREG_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    begin_call(h);
+    mark(h, EV_BEGIN);
+    const lvreg_cloud* c[2] = {corner_ds, surf_ds};
+    for (int s = 0; s < 2; ++s) {
+        CKS(upload_cloud(h, c[s], h->map[s].ds, s));
+        h->map[s].m = (uint32_t)c[s]->n;
+        h->map[s].n_in = c[s]->n;
+    }
+    mark(h, EV_MAP);
+    for (int s = 0; s < 2; ++s) {
+        CKS(build_grid(h, h->map[s]));
+        h->map[s].valid = true;
+    }
+    mark(h, EV_GRID);
+    CK(cudaStreamSynchronize(h->st));
+    h->last.upload_ms = span(h, EV_BEGIN, EV_MAP);
+    h->last.grid_build_ms = span(h, EV_MAP, EV_GRID);
+    finish_timings(h);
+    end_call(h);
+    fill_map_info(h, info);
+    return LVREG_OK;
+}
+
+int lvreg_get_local_map(lvreg_handle* h, int which, lvreg_cloud_out* out, size_t* n) {
+    if (!h || which < 0 || which > 1) return LVREG_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    if (!h->map[which].valid) return fail(h, LVREG_ERR_NO_MAP, "no local map");
+    if (n) *n = h->map[which].m;
+    if (!out) return LVREG_OK;
+    return download_cloud(h, h->map[which].ds.as<float4>(), h->map[which].m, out);
+}
+
+// ---- current scan --------------------------------------------------------------------------------
+int lvreg_downsample_scan(lvreg_handle* h, const lvreg_cloud* corner_raw, const lvreg_cloud* surf_raw,
+                          size_t* nc, size_t* ns) {
+    if (!h) return LVREG_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    begin_call(h);
+    mark(h, EV_BEGIN);
+    CKS(downsample_impl(h, corner_raw, surf_raw));
+    CK(cudaStreamSynchronize(h->st));
+    h->last.upload_ms = span(h, EV_BEGIN, EV_UPLOAD);
+    h->last.downsample_ms = span(h, EV_UPLOAD, EV_DS);
+    finish_timings(h);
+    end_call(h);
+    if (nc) *nc = h->n_scan[0];
+    if (ns) *ns = h->n_scan[1];
+    return LVREG_OK;
+}
+
+int lvreg_set_scan_ds(lvreg_handle* h, const lvreg_cloud* corner_ds, const lvreg_cloud* surf_ds) {
+    if (!h) return LVREG_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    begin_call(h);
+    CKS(upload_cloud(h, corner_ds, h->scan_ds[0], 0));
+    CKS(upload_cloud(h, surf_ds, h->scan_ds[1], 1));
+    CK(cudaStreamSynchronize(h->st));
+    h->n_scan[0] = (uint32_t)corner_ds->n;
+    h->n_scan[1] = (uint32_t)surf_ds->n;
+    end_call(h);
+    return LVREG_OK;
+}
+
+int lvreg_get_scan_ds(lvreg_handle* h, int which, lvreg_cloud_out* out, size_t* n) {
+    if (!h || which < 0 || which > 1) return LVREG_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    if (n) *n = h->n_scan[which];
+    if (!out) return LVREG_OK;
+    return download_cloud(h, h->scan_ds[which].as<float4>(), h->n_scan[which], out);
+}
+
+// ---- registration --------------------------------------------------------------------------------
+int lvreg_scan2map(lvreg_handle* h, float pose[6], lvreg_result* res) {
+    if (!h || !pose) return LVREG_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    begin_call(h);
+    mark(h, EV_BEGIN);
+    int s = scan2map_impl(h, pose, res);
+    if (s == LVREG_OK) {
+        h->last.register_ms = span(h, EV_BEGIN, EV_REG);
+        finish_timings(h);
+    }
+    end_call(h);
+    return s;
+}
+
+int lvreg_register_scan(lvreg_handle* h, const lvreg_cloud* corner_raw, const lvreg_cloud* surf_raw,
+                        const int32_t* ids, size_t n_ids, float pose[6], lvreg_result* res) {
+    if (!h || !pose) return LVREG_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    begin_call(h);
+    mark(h, EV_BEGIN);
+    if (ids) CKS(build_local_map_impl(h, ids, n_ids));      // extractSurroundingKeyFrames MO:318
+    CKS(downsample_impl(h, corner_raw, surf_raw));            // downsampleCurrentScan MO:320
+    int s = scan2map_impl(h, pose, res);                      // scan2MapOptimization MO:322
+    if (s == LVREG_OK || s == LVREG_ERR_NOT_ENOUGH_FEATURES) {
+        CK(cudaStreamSynchronize(h->st));
+        const int pre = ids ? EV_GRID : EV_BEGIN;
+        if (ids) {
+            h->last.map_build_ms = span(h, EV_BEGIN, EV_MAP);
+            h->last.grid_build_ms = span(h, EV_MAP, EV_GRID);
+        }
+        h->last.upload_ms = span(h, pre, EV_UPLOAD);
+        h->last.downsample_ms = span(h, EV_UPLOAD, EV_DS);
+        h->last.register_ms = span(h, EV_DS, EV_REG);
+        finish_timings(h);
+    }
+    end_call(h);
+    return s;
+}
+
+int lvreg_transform_update(const lvreg_handle* h, float pose[6], int imu_available, float imu_roll,
+                           float imu_pitch) {
+    if (!h || !pose) return LVREG_ERR_INVALID;
+    if (imu_available && fabs((double)imu_pitch) < 1.4) {
+        // tf2 slerp of two rotations about one axis == interpolation of the angle along the
+        // shortest arc (MO:1349-1366), evaluated in double like tf2
+        const double w = h->prm.imu_rpy_weight;
+        auto slerp_angle = [](double a, double b, double t) {
+            double d = remainder(b - a, 2.0 * M_PI);
+            return remainder(a + t * d, 2.0 * M_PI);
+        };
+        pose[0] = (float)slerp_angle(pose[0], imu_roll, w);
+        pose[1] = (float)slerp_angle(pose[1], imu_pitch, w);
+    }
+    pose[0] = clampf(pose[0], h->prm.rotation_tolerance);
+    pose[1] = clampf(pose[1], h->prm.rotation_tolerance);
+    pose[5] = clampf(pose[5], h->prm.z_tolerance);
+    return LVREG_OK;
+}
+
+int lvreg_get_degenerate(const lvreg_handle* hc, int* is_degenerate) {
+    lvreg_handle* h = const_cast<lvreg_handle*>(hc);
+    if (!h || !is_degenerate) return LVREG_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpyAsync(h->pinned, h->lmstate.p, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    *is_degenerate = *(int*)h->pinned;
+    return LVREG_OK;
+}
+
+int lvreg_reset_lm_state(lvreg_handle* h) {
+    if (!h) return LVREG_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemsetAsync(h->lmstate.p, 0, sizeof(LmState), h->st));
+    CK(cudaStreamSynchronize(h->st));
+    return LVREG_OK;
+}
+
+// ---- stage-level ---------------------------------------------------------------------------------
+void lvreg_pose_to_affine(const float pose[6], float T[12]) { pose_to_affine_host(pose, T); }
+
+int lvreg_transform_cloud(lvreg_handle* h, const lvreg_cloud* in, const float pose[6], lvreg_cloud_out* out) {
+    if (!h || !in || !pose || !out) return LVREG_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    begin_call(h);
+    CKS(upload_cloud(h, in, h->raw[0], 0));
+    const uint32_t n = (uint32_t)in->n;
+    CK(h->concat.reserve((size_t)(n ? n : 1) * 16));
+    Affine T;
+    pose_to_affine_host(pose, T.m);
+    if (n) {
+        transform_kernel<<<nblk(n, 256), 256, 0, h->st>>>(h->raw[0].as<float4>(), n, T, h->concat.as<float4>());
+        launched(h);
+    }
+    int s = download_cloud(h, h->concat.as<float4>(), n, out);
+    end_call(h);
+    return s;
+}
+
+int lvreg_voxelgrid(lvreg_handle* h, const lvreg_cloud* in, float leaf, lvreg_cloud_out* out, size_t* n_out,
+                    uint32_t* voxel_keys_out, int* passthrough) {
+    if (!h || !in || !out) return LVREG_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    begin_call(h);
+    mark(h, EV_BEGIN);
+    CKS(upload_cloud(h, in, h->raw[0], 0));
+    mark(h, EV_UPLOAD);
+    uint32_t m = 0;
+    int pt = 0;
+    CKS(voxelgrid_dev(h, h->raw[0].as<float4>(), (uint32_t)in->n, leaf, false, h->concat, &m,
+                      voxel_keys_out != nullptr, nullptr, &pt));
+    mark(h, EV_DS);
+    if (passthrough) *passthrough = pt;
+    if (n_out) *n_out = m;
+    if (voxel_keys_out && m && !pt) {
+        CK(cudaMemcpyAsync(voxel_keys_out, h->vox_keys.p, (size_t)m * 4, cudaMemcpyDeviceToHost, h->st));
+    } else if (voxel_keys_out && m) {
+        memset(voxel_keys_out, 0, (size_t)m * 4);
+    }
+    int s = download_cloud(h, h->concat.as<float4>(), m, out);
+    CK(cudaStreamSynchronize(h->st));
+    h->last.upload_ms = span(h, EV_BEGIN, EV_UPLOAD);
+    h->last.downsample_ms = span(h, EV_UPLOAD, EV_DS);
+    finish_timings(h);
+    end_call(h);
+    return s;
+}
+
+int lvreg_voxel_keys(lvreg_handle* h, const lvreg_cloud* in, float leaf, uint32_t* keys_out) {
+    if (!h || !in || (!keys_out && in->n)) return LVREG_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    begin_call(h);
+    CKS(upload_cloud(h, in, h->raw[0], 0));
+    const uint32_t n = (uint32_t)in->n;
+    if (n == 0) return LVREG_OK;
+    CK(h->idxbuf.reserve((size_t)n * 4));
+    uint32_t m = 0;
+    CKS(voxelgrid_dev(h, h->raw[0].as<float4>(), n, leaf, false, h->concat, &m, false, h->idxbuf.as<uint32_t>(), nullptr));
+    CK(cudaMemcpyAsync(keys_out, h->idxbuf.p, (size_t)n * 4, cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    end_call(h);
+    return LVREG_OK;
+}
+
+static int knn5_launch(lvreg_handle* h, int which, const float4* q, uint32_t nq, int variant, int32_t* d_idx,
+                       float* d_d2) {
+    const MapSide& ms = h->map[which];
+    if (variant == LVREG_KNN_BRUTE) {
+        const uint32_t qblocks = nblk(nq, 256);
+        uint32_t splits = (uint32_t)(2 * h->num_sms) / (qblocks ? qblocks : 1);
+        if (splits < 1) splits = 1;
+        uint32_t max_splits = nblk(ms.m ? ms.m : 1, kBruteTile);
+        if (splits > max_splits) splits = max_splits;
+        uint32_t chunk = nblk(ms.m ? ms.m : 1, splits);
+        chunk = nblk(chunk, kBruteTile) * kBruteTile;
+        splits = nblk(ms.m ? ms.m : 1, chunk);
+        CK(h->brute_partial.reserve((size_t)splits * nq * 5 * sizeof(u64)));
+        knn5_brute_kernel<<<dim3(qblocks, splits), 256, 0, h->st>>>(ms.ds.as<float4>(), ms.m, q, nq, chunk,
+                                                                   h->brute_partial.as<u64>());
+        knn5_brute_merge_kernel<<<qblocks, 256, 0, h->st>>>(h->brute_partial.as<u64>(), nq, splits, d_idx, d_d2);
+        launched(h, 2);
+    } else {
+        const GridView g = grid_view(ms);
+        const int exact = variant == LVREG_KNN_GRID_EXACT ? 1 : 0;
+        const float gate = h->prm.knn_gate_sq;
+        const uint32_t cap = (uint32_t)h->num_sms * 8;
+        switch (h->lpq) {
+            case 4: knn5_grid_kernel<4><<<min(nblk(nq, 64), cap), 256, 0, h->st>>>(g, q, nq, exact, gate, d_idx, d_d2); break;
+            case 16: knn5_grid_kernel<16><<<min(nblk(nq, 16), cap), 256, 0, h->st>>>(g, q, nq, exact, gate, d_idx, d_d2); break;
+            case 32: knn5_grid_kernel<32><<<min(nblk(nq, 8), cap), 256, 0, h->st>>>(g, q, nq, exact, gate, d_idx, d_d2); break;
+            default: knn5_grid_kernel<8><<<min(nblk(nq, 32), cap), 256, 0, h->st>>>(g, q, nq, exact, gate, d_idx, d_d2); break;
+        }
+        launched(h);
+    }
+    CK(cudaGetLastError());
+    return LVREG_OK;
+}
+
+int lvreg_knn5(lvreg_handle* h, int which, const lvreg_cloud* queries, int variant, int32_t* idx_out, float* d2_out) {
+    if (!h || which < 0 || which > 1 || !queries || variant < 0 || variant > 2) return LVREG_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    if (!h->map[which].valid) return fail(h, LVREG_ERR_NO_MAP, "no local map");
+    begin_call(h);
+    CKS(upload_cloud(h, queries, h->qbuf, 0));
+    const uint32_t nq = (uint32_t)queries->n;
+    if (nq == 0) return LVREG_OK;
+    CK(h->idxbuf.reserve((size_t)nq * 5 * 4));
+    CK(h->d2buf.reserve((size_t)nq * 5 * 4));
+    mark(h, EV_BEGIN);
+    CKS(knn5_launch(h, which, h->qbuf.as<float4>(), nq, variant, h->idxbuf.as<int32_t>(), h->d2buf.as<float>()));
+    mark(h, EV_REG);
+    if (idx_out) CK(cudaMemcpyAsync(idx_out, h->idxbuf.p, (size_t)nq * 5 * 4, cudaMemcpyDeviceToHost, h->st));
+    if (d2_out) CK(cudaMemcpyAsync(d2_out, h->d2buf.p, (size_t)nq * 5 * 4, cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    h->last.register_ms = span(h, EV_BEGIN, EV_REG);
+    finish_timings(h);
+    end_call(h);
+    return LVREG_OK;
+}
+
+int lvreg_bench_knn5(lvreg_handle* h, int which, const lvreg_cloud* queries, int variant, int repeats, float* ms) {
+    if (!h || which < 0 || which > 1 || !queries || repeats < 1 || variant < 0 || variant > 2) return LVREG_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    if (!h->map[which].valid) return fail(h, LVREG_ERR_NO_MAP, "no local map");
+    begin_call(h);
+    CKS(upload_cloud(h, queries, h->qbuf, 0));
+    const uint32_t nq = (uint32_t)queries->n;
+    if (nq == 0) return fail(h, LVREG_ERR_INVALID, "no queries");
+    CK(h->idxbuf.reserve((size_t)nq * 5 * 4));
+    CK(h->d2buf.reserve((size_t)nq * 5 * 4));
+    for (int i = 0; i < 3; ++i)
+        CKS(knn5_launch(h, which, h->qbuf.as<float4>(), nq, variant, h->idxbuf.as<int32_t>(), h->d2buf.as<float>()));
+    mark(h, EV_BEGIN);
+    for (int i = 0; i < repeats; ++i)
+        CKS(knn5_launch(h, which, h->qbuf.as<float4>(), nq, variant, h->idxbuf.as<int32_t>(), h->d2buf.as<float>()));
+    mark(h, EV_REG);
+    CK(cudaStreamSynchronize(h->st));
+    if (ms) *ms = span(h, EV_BEGIN, EV_REG) / (float)repeats;
+    end_call(h);
+    return LVREG_OK;
+}
+
+static int residuals_api(lvreg_handle* h, int cls, const lvreg_cloud* pts, const float pose[6], float* coeff_out,
+                         uint8_t* flag_out, int32_t* knn_idx_out) {
+    if (!h || !pts || !pose) return LVREG_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    if (!h->map[cls].valid) return fail(h, LVREG_ERR_NO_MAP, "no local map");
+    begin_call(h);
+    CKS(upload_cloud(h, pts, h->qbuf, 0));
+    const uint32_t n = (uint32_t)pts->n;
+    if (n == 0) return LVREG_OK;
+    CK(h->coeffbuf.reserve((size_t)n * 16));
+    CK(h->flagbuf.reserve((size_t)n));
+    CK(h->idxbuf.reserve((size_t)n * 5 * 4));
+    Affine T;
+    pose_to_affine_host(pose, T.m);
+    const GridView g = grid_view(h->map[cls]);
+    const RegParams P = reg_params(h);
+    const uint32_t blocks = min(nblk(nblk(n, 32), kRegWarps), (uint32_t)h->num_sms * 8);
+    const float4* map = h->map[cls].ds.as<float4>();
+    const float4* q = h->qbuf.as<float4>();
+    float4* co = h->coeffbuf.as<float4>();
+    uint8_t* fl = h->flagbuf.as<uint8_t>();
+    int32_t* nn = h->idxbuf.as<int32_t>();
+    switch (h->lpq) {
+        case 4: residual_kernel<4><<<blocks, kRegThreads, 0, h->st>>>(g, map, q, n, cls, T, P, co, fl, nn); break;
+        case 16: residual_kernel<16><<<blocks, kRegThreads, 0, h->st>>>(g, map, q, n, cls, T, P, co, fl, nn); break;
+        case 32: residual_kernel<32><<<blocks, kRegThreads, 0, h->st>>>(g, map, q, n, cls, T, P, co, fl, nn); break;
+        default: residual_kernel<8><<<blocks, kRegThreads, 0, h->st>>>(g, map, q, n, cls, T, P, co, fl, nn); break;
+    }
+    launched(h);
+    CK(cudaGetLastError());
+    if (coeff_out) CK(cudaMemcpyAsync(coeff_out, co, (size_t)n * 16, cudaMemcpyDeviceToHost, h->st));
+    if (flag_out) CK(cudaMemcpyAsync(flag_out, fl, (size_t)n, cudaMemcpyDeviceToHost, h->st));
+    if (knn_idx_out) CK(cudaMemcpyAsync(knn_idx_out, nn, (size_t)n * 5 * 4, cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    end_call(h);
+    return LVREG_OK;
+}
+
+int lvreg_corner_residuals(lvreg_handle* h, const lvreg_cloud* pts, const float pose[6], float* coeff_out,
+                           uint8_t* flag_out, int32_t* knn_idx_out) {
+    return residuals_api(h, 0, pts, pose, coeff_out, flag_out, knn_idx_out);
+}
+int lvreg_surf_residuals(lvreg_handle* h, const lvreg_cloud* pts, const float pose[6], float* coeff_out,
+                         uint8_t* flag_out, int32_t* knn_idx_out) {
+    return residuals_api(h, 1, pts, pose, coeff_out, flag_out, knn_idx_out);
+}
+
+int lvreg_lm_step(lvreg_handle* h, const float* ori, const float* coeff, size_t n_sel, int iter, float pose[6],
+                  float AtA_out[36], float Atb_out[6], float x_out[6], int* converged) {
+    if (!h || !pose || (n_sel && (!ori || !coeff))) return LVREG_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    begin_call(h);
+    if (converged) *converged = 0;
+    if ((int)n_sel < h->prm.min_matches) return LVREG_OK;       // MO:1209-1212: no update
+    const uint32_t n = (uint32_t)n_sel;
+    CK(h->qbuf.reserve((size_t)n * 16));
+    CK(h->coeffbuf.reserve((size_t)n * 16));
+    CK(cudaMemcpyAsync(h->qbuf.p, ori, (size_t)n * 16, cudaMemcpyHostToDevice, h->st));
+    CK(cudaMemcpyAsync(h->coeffbuf.p, coeff, (size_t)n * 16, cudaMemcpyHostToDevice, h->st));
+    float* hp = (float*)h->pinned;
+    memcpy(hp, pose, 6 * sizeof(float));
+    float* dscr = h->posebuf.as<float>();        // [0..5] pose, [8..43] AtA, [44..49] Atb, [50..55] x, [56] conv
+    CK(cudaMemcpyAsync(dscr, hp, 6 * sizeof(float), cudaMemcpyHostToDevice, h->st));
+    CK(cudaMemsetAsync(dscr + 8, 0, 49 * sizeof(float), h->st));
+    Trig g;
+    // the reference takes float sin/cos of the pose on the host (MO:1202-1207)
+    g.srx = sinf(pose[1]); g.crx = cosf(pose[1]);
+    g.sry = sinf(pose[2]); g.cry = cosf(pose[2]);
+    g.srz = sinf(pose[0]); g.crz = cosf(pose[0]);
+    lm_step_kernel<<<1, 256, 0, h->st>>>(h->qbuf.as<float4>(), h->coeffbuf.as<float4>(), n, iter, g, reg_params(h), dscr,
+                                         h->lmstate.as<LmState>(), dscr + 8, dscr + 44, dscr + 50, (int*)(dscr + 56));
+    launched(h);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(hp, dscr, 57 * sizeof(float), cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    memcpy(pose, hp, 6 * sizeof(float));
+    if (AtA_out) memcpy(AtA_out, hp + 8, 36 * sizeof(float));
+    if (Atb_out) memcpy(Atb_out, hp + 44, 6 * sizeof(float));
+    if (x_out) memcpy(x_out, hp + 50, 6 * sizeof(float));
+    if (converged) *converged = *(int*)(hp + 56);
+    end_call(h);
+    return LVREG_OK;
+}
+
+// ---- measurement ---------------------------------------------------------------------------------
+int lvreg_get_timings(const lvreg_handle* h, lvreg_timings* t) {
+    if (!h || !t) return LVREG_ERR_INVALID;
+    *t = h->last;
+    return LVREG_OK;
+}
+
+int lvreg_get_launch_count(const lvreg_handle* h, uint64_t* n) {
+    if (!h || !n) return LVREG_ERR_INVALID;
+    *n = h->total_launches;
+    return LVREG_OK;
+}
+
+}  // extern "C"

@@ -54,3 +54,34 @@ def scan_from_world(rng, corner_w, surf_w, pose, n_corner=800, n_surf=4000, nois
         loc += rng.normal(0, noise, loc.shape)
         return np.concatenate([loc, sel[:, 3:4]], axis=1).astype(np.float32)
     return pick(corner_w, n_corner), pick(surf_w, n_surf)
+
+
+def corridor_world(rng, n_surf=40000, n_corner=6000, length=30.0, half_w=2.0, height=3.0, noise=0.01):
+    """corridor along x: walls y=+-half_w, floor/ceiling, edge lines parallel to x -> x is unobservable"""
+    per = n_surf // 4
+    surf = []
+    for k in range(4):
+        p = np.zeros((per, 3))
+        p[:, 0] = rng.uniform(-length, length, per)
+        if k < 2:
+            p[:, 1] = (-1) ** k * half_w
+            p[:, 2] = rng.uniform(-height / 2, height / 2, per)
+        else:
+            p[:, 1] = rng.uniform(-half_w, half_w, per)
+            p[:, 2] = (-1) ** k * height / 2
+        surf.append(p)
+    surf = np.concatenate(surf) + rng.normal(0, noise, (per * 4, 3))
+    per = n_corner // 4
+    corner = []
+    for sy in (-1, 1):
+        for sz in (-1, 1):
+            p = np.zeros((per, 3))
+            p[:, 0] = rng.uniform(-length, length, per)
+            p[:, 1] = sy * half_w
+            p[:, 2] = sz * height / 2
+            corner.append(p)
+    corner = np.concatenate(corner) + rng.normal(0, noise, (per * 4, 3))
+
+    def with_i(p):
+        return np.concatenate([p, rng.uniform(0, 255, (len(p), 1))], axis=1).astype(np.float32)
+    return with_i(corner), with_i(surf)
