@@ -1,0 +1,374 @@
+#!/usr/bin/env python
+"""bench.py -- scan-to-map registrations/s on the BASELINE C3 workload (dense 128-beam scans
+against a ~1M-point local map), one process per GPU.
+
+    python bench.py --gpus 1 --steps 10 --warmup 3            # our arm (CUDA, through the C ABI)
+    python bench.py --impl reference --steps 3 --warmup 1     # CPU arm: the oracle restatement of
+                                                              # the reference's mapOptimization path
+
+A "step" is the body of laserCloudInfoHandler (MO:318-322) for ONE incoming scan, exactly the work
+the reference does per scan: extractCloud (transform + concatenate the selected keyframes,
+VoxelGrid corner 0.2 / surf 0.4), kd-tree / search-grid build, downsampleCurrentScan, and the
+<=20-iteration scan2MapOptimization loop.  Keyframes are resident (device / host) in both arms, as
+they are in the reference.  e2e = the same call with the scan's feature clouds in pinned HOST
+memory (PCL 32-byte layout): H2D of the clouds and D2H of pose + result are inside the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SEED = 0x5EED0000
+N_RING_SCANS = 8            # distinct incoming scans cycled through the steps
+
+
+def lattice_poses(workload):
+    """keyframe poses: 2 m spacing (surroundingKeyframeDensity) on parallel streets, all within the
+    50 m surroundingKeyframeSearchRadius of the last pose at the origin"""
+    if workload == "c1":
+        lanes = ((0.0, 20.0),)
+    else:
+        lanes = ((0.0, 48.0), (-20.0, 44.0), (20.0, 44.0), (-40.0, 28.0), (40.0, 28.0))
+    poses = []
+    for lane, (y, xm) in enumerate(lanes):
+        for x in np.arange(-xm, xm + 1e-6, 2.0):
+            yaw = 0.02 * np.sin(0.1 * x) + (np.pi if lane == 1 else 0.0)
+            poses.append(np.array([0.005 * np.sin(x), 0.005 * np.cos(x), yaw, x, y, 0.0], np.float32))
+    # the most recent keyframe (cloudKeyPoses3D->back()) sits in the middle of the map
+    poses.append(np.array([0.0, 0.0, 0.0, 1.0, 0.3, 0.0], np.float32))
+    return poses
+
+
+def make_dataset(workload, seed, voxelgrid, log):
+    """keyframe clouds (already down-sampled, as the reference stores them), the ring of incoming
+    raw scans, ground truth and initial guesses.  Cached under /tmp for the second arm."""
+    from lidar_visual_inertial_slam_b200 import harness as H
+    cache = "/tmp/lvreg_bench_%s_%x_v3.npz" % (workload, seed)
+    if os.path.exists(cache):
+        z = np.load(cache)
+        log("dataset: loaded %s" % cache)
+        nk = int(z["nk"])
+        return dict(kf_pose=z["kf_pose"], kf_corner=[z["kc%d" % i] for i in range(nk)],
+                    kf_surf=[z["ks%d" % i] for i in range(nk)],
+                    scans=[(z["sc%d" % i], z["ss%d" % i]) for i in range(N_RING_SCANS)],
+                    truth=z["truth"], guess=z["guess"])
+    t0 = time.time()
+    sensor = H.MID360 if workload == "c1" else H.BEAM128
+    gen = H.Generator(sensor, seed)
+    threads = min(32, os.cpu_count() or 8)
+    poses = lattice_poses(workload)
+    kc, ks = [], []
+    for k, pose in enumerate(poses):
+        c, s = gen.scan(pose, 1000 + k, threads)
+        kc.append(voxelgrid(c, 0.2))
+        ks.append(voxelgrid(s, 0.4))
+    rng = np.random.default_rng(seed & 0xffff)
+    truth, guess, scans = [], [], []
+    for i in range(N_RING_SCANS):
+        t = np.array([0.01 * np.sin(i), 0.01 * np.cos(i), 0.05 * np.sin(0.5 * i), 1.0 + 0.9 * (i + 1) / N_RING_SCANS,
+                      0.3 + 0.2 * np.sin(i), 0.02 * np.cos(i)], np.float32)
+        g = t.copy()
+        g[:3] += rng.uniform(-0.035, 0.035, 3).astype(np.float32)       # +-2 deg
+        g[3:] += rng.uniform(-0.10, 0.10, 3).astype(np.float32)         # +-10 cm
+        scans.append(gen.scan(t, 5000 + i, threads))
+        truth.append(t)
+        guess.append(g)
+    d = dict(kf_pose=np.array(poses), kf_corner=kc, kf_surf=ks, scans=scans, truth=np.array(truth), guess=np.array(guess))
+    try:
+        arrs = dict(nk=len(poses), kf_pose=d["kf_pose"], truth=d["truth"], guess=d["guess"])
+        for i in range(len(poses)):
+            arrs["kc%d" % i] = kc[i]
+            arrs["ks%d" % i] = ks[i]
+        for i in range(N_RING_SCANS):
+            arrs["sc%d" % i], arrs["ss%d" % i] = scans[i]
+        np.savez(cache, **arrs)
+    except Exception as e:       # cache is best effort
+        log("dataset cache not written: %s" % e)
+    log("dataset: generated %d keyframes + %d scans in %.1f s" % (len(poses), N_RING_SCANS, time.time() - t0))
+    return d
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)"""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f).get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_arm(ds, n_samples, warmup, threads, log):
+    """the oracle (CPU restatement of the reference) on the same workload; returns (reg/s, per-step ms)"""
+    from oracle import pyoracle as O
+    mo = O.MapOptimization(O.default_params(num_threads=threads))
+    for i in range(len(ds["kf_pose"])):
+        mo.add_keyframe(ds["kf_corner"][i], ds["kf_surf"][i], ds["kf_pose"][i], float(i))
+    ids = np.arange(len(ds["kf_pose"]), dtype=np.int32)           # same explicit selection as the CUDA arm
+    times, poses, results = [], [], []
+    for i in range(warmup + n_samples):
+        c, s = ds["scans"][i % N_RING_SCANS]
+        t0 = time.perf_counter()
+        mo.build_local_map(ids)                                     # extractCloud (cache warm after the first call)
+        pose, res, _, _ = mo.register_scan(c, s, ds["guess"][i % N_RING_SCANS])   # downsample + kd-trees + LM loop
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+        poses.append(pose)
+        results.append(res)
+        log("cpu step %d: %.3f s, iterations %d" % (i, dt, res.iterations))
+    return ids, times, poses, results
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c3", choices=["c3", "c1"])
+    ap.add_argument("--cpu-samples", type=int, default=3, help="registrations timed for cpu_baseline")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    def log(msg):
+        print("[bench rank %d] %s" % (rank, msg), file=sys.stderr, flush=True)
+
+    wl_name = {"c3": "C3: 128-beam 128x2048 scan (~185k returns -> ~68k features) vs ~0.97M-point local map rebuilt "
+                     "from 198 resident keyframes (~13M points) per scan",
+               "c1": "C1: MID360-like scan (~20k returns) vs local map from 22 keyframes"}[args.workload]
+    cores = os.cpu_count() or 1
+
+    # ------------------------------------------------------------------ reference (CPU) arm
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        from oracle import pyoracle as O
+        threads = min(cores, 64)
+        ds = make_dataset(args.workload, SEED, lambda p, leaf: O.voxelgrid(p, leaf)[0], log)
+        ids, times, poses, results = cpu_arm(ds, args.steps, args.warmup, threads, log)
+        ms = 1e3 * float(np.sum(times)) / max(1, len(times))
+        val = 1e3 / ms
+        line = dict(metric="scan-to-map registrations/sec", value=val, unit="registrations/s", n_gpus=0,
+                    steps=args.steps, warmup=args.warmup, ms_per_step=ms, higher_is_better=True, scaling="weak",
+                    vs_baseline=None, dtype="f32", data="synthetic", impl="reference",
+                    config=dict(workload=wl_name, keyframes=len(ds["kf_pose"]), l2="inputs larger than L2"),
+                    cpu_baseline=dict(value=val, unit="registrations/s", cores=threads, kind="port",
+                                      sample="%d full registrations (map rebuild + kd-trees + LM loop) of the same workload" % args.steps),
+                    e2e=dict(value=val, unit="registrations/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                    gpu_launches=0,
+                    note="CPU restatement of the reference's mapOptimization path (oracle/): the reference itself "
+                         "needs ROS 2 + PCL + OpenCV C++ + GTSAM and cannot be built here")
+        print(json.dumps(line), flush=True)
+        return 0
+
+    # ------------------------------------------------------------------ our arm (CUDA)
+    import torch
+    import lidar_visual_inertial_slam_b200 as lv
+    from lidar_visual_inertial_slam_b200.binding import to_pcl_layout, device_cloud, Cloud
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    use_dist = world > 1
+    if use_dist:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    stream = torch.cuda.current_stream().cuda_stream
+    h = lv.Lvreg(device=local_rank, stream=stream)
+    seed = SEED + rank                                                # independent sequence per GPU
+    ds = make_dataset(args.workload, seed, lambda p, leaf: h.voxelgrid(p, leaf)[0], log)
+    for i in range(len(ds["kf_pose"])):
+        h.add_keyframe(ds["kf_corner"][i], ds["kf_surf"][i], ds["kf_pose"][i])
+    # keyframe selection = extractNearby through the C++ mirror's logic is exercised in the tests;
+    # here every keyframe is inside the 50 m radius by construction
+    ids = np.arange(len(ds["kf_pose"]), dtype=np.int32)
+
+    # pinned host copies of the incoming scans in pcl::PointXYZI layout (e2e), device copies (value)
+    host_scans, dev_scans, keep = [], [], []
+    h2d_bytes = []
+    for c, s in ds["scans"]:
+        pc, ps = to_pcl_layout(c), to_pcl_layout(s)
+        hc = lv.host_alloc_f32(pc.shape)
+        hs = lv.host_alloc_f32(ps.shape)
+        hc[:] = pc
+        hs[:] = ps
+        host_scans.append((hc, hs))
+        h2d_bytes.append(hc.nbytes + hs.nbytes)
+        tc = torch.from_numpy(c).cuda()
+        ts = torch.from_numpy(s).cuda()
+        keep.append((tc, ts))
+        dev_scans.append((device_cloud(tc.data_ptr(), len(c)), device_cloud(ts.data_ptr(), len(s))))
+    d2h_bytes = 24 + int(np.dtype(np.int32).itemsize) * 0 + 1192       # pose + RegOut
+
+    def run_steps(n, first, on_device):
+        out = []
+        for i in range(first, first + n):
+            j = i % N_RING_SCANS
+            c, s = dev_scans[j] if on_device else host_scans[j]
+            pose, res, st = h.register_scan(c, s, ids, ds["guess"][j])
+            if st != lv.OK:
+                raise SystemExit("register_scan failed with status %d" % st)
+            out.append((pose, res, h.timings()))
+        return out
+
+    def timed(n, first, on_device):
+        if use_dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+        l0 = h.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        out = run_steps(n, first, on_device)
+        e1.record()
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        if use_dist:
+            dist.barrier()
+        ms = e0.elapsed_time(e1)
+        if use_dist:
+            t = torch.tensor([ms, wall * 1e3], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms, wall = float(t[0]), float(t[1]) / 1e3
+        return ms, wall, out, h.launch_count() - l0
+
+    run_steps(args.warmup, 0, True)
+    run_steps(args.warmup, 0, False)
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ms_dev, wall_dev, out_dev, launches = timed(args.steps, args.warmup, True)       # inputs resident in HBM
+    ms_e2e, wall_e2e, out_e2e, _ = timed(args.steps, args.warmup, False)              # host buffers
+    clocks = sampler.stop()
+
+    # per-stage device time (CUDA events recorded by the library on the launching stream)
+    stage = {k: float(np.mean([getattr(t, k) for _, _, t in out_dev]))
+             for k in ("upload_ms", "map_build_ms", "grid_build_ms", "downsample_ms", "register_ms", "total_ms")}
+    iters = [r.iterations for _, r, _ in out_dev]
+    res0 = out_dev[0][1]
+    nq = res0.n_corner_ds + res0.n_surf_ds
+    mm = res0.n_corner_map + res0.n_surf_map
+    hbm_peak, peak_src = measured_peaks()
+    # dominant kernel: register_kernel (one cooperative launch per registration).  Algorithmic bytes
+    # per launch: iterations x (96 B/query + 16 B/map point) + 27 floats out.
+    reg_bytes = float(np.mean([it * (96.0 * nq + 16.0 * mm) + 108.0 for it in iters]))
+    reg_s = stage["register_ms"] * 1e-3
+    achieved = reg_bytes / reg_s / 1e9 if reg_s > 0 else 0.0
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "r01_register_kernel_traffic.json")
+    if os.path.exists(tp):
+        with open(tp) as f:
+            traffic = json.load(f).get("dram_bytes_per_launch")
+
+    n_total_steps = args.steps * world
+    value = n_total_steps / (ms_dev * 1e-3)
+    e2e = n_total_steps / (ms_e2e * 1e-3)
+
+    line = dict(metric="scan-to-map registrations/sec", value=value, unit="registrations/s", n_gpus=world,
+                steps=args.steps, warmup=args.warmup, ms_per_step=ms_dev / args.steps, higher_is_better=True,
+                scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                config=dict(workload=wl_name, keyframes=len(ids), queries_per_scan=nq, map_points=mm,
+                            keyframe_points_per_rebuild=int(sum(len(a) + len(b) for a, b in zip(ds["kf_corner"], ds["kf_surf"]))),
+                            lm_iterations_mean=float(np.mean(iters)), parallelism="independent sequences, 1 per GPU, no collective",
+                            l2="inputs larger than L2 (keyframe store + concatenated map + sort buffers > 126 MB per step)"),
+                e2e=dict(value=e2e, unit="registrations/s", h2d_bytes_per_step=int(np.mean(h2d_bytes)), d2h_bytes_per_step=d2h_bytes,
+                         ms_per_step=ms_e2e / args.steps),
+                gpu_launches=int(launches),
+                knn_queries_per_s=float(np.sum([it * nq for it in iters]) * world / (ms_dev * 1e-3)),
+                stages_ms=stage,
+                roofline=dict(kernel="register_kernel", bound="hbm", achieved=achieved, peak=hbm_peak, unit="GB/s",
+                              frac=achieved / hbm_peak, traffic=traffic, peak_source=peak_src,
+                              algorithmic_bytes_per_launch=reg_bytes, launch_ms=stage["register_ms"]),
+                clocks=clocks, wall_s=dict(resident=wall_dev, e2e=wall_e2e))
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = min(cores, 64)
+        _, times, cposes, cres = cpu_arm(ds, args.cpu_samples, 1, threads, log)
+        cms = 1e3 * float(np.mean(times))
+        line["cpu_baseline"] = dict(value=1e3 / cms, unit="registrations/s", cores=threads, kind="port",
+                                    sample="%d full registrations of the same workload (1 warm-up), %.2f s each" % (len(times), cms / 1e3))
+        # parity of the timed GPU results against the oracle on the same inputs
+        perr = rerr = 0.0
+        same_iters = True
+        # compare scan j of the ring: GPU step index with the same scan
+        for k, (cp, cr) in enumerate(zip(cposes, cres)):
+            j = k % N_RING_SCANS
+            for (gp, gr, _), i in zip(out_dev, range(args.warmup, args.warmup + args.steps)):
+                if i % N_RING_SCANS == j:
+                    rerr = max(rerr, float(np.abs(gp[:3] - cp[:3]).max()))
+                    perr = max(perr, float(np.abs(gp[3:] - cp[3:]).max()))
+                    same_iters = same_iters and gr.iterations == cr.iterations
+                    break
+        line["parity_vs_oracle"] = dict(max_pos_err_m=perr, max_rot_err_rad=rerr, same_iteration_counts=bool(same_iters))
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    h.close()
+    if use_dist:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -139,6 +139,9 @@ void        lvreg_host_free(void* p);
 /* saveKeyFramesAndFactor's push_back of the DS feature clouds + pose (MO:1600-1610). */
 int lvreg_add_keyframe(lvreg_handle* h, const lvreg_cloud* corner, const lvreg_cloud* surf,
                        const float pose_rpyxyz[6], int32_t* id_out);
+/* Same, taking the device-resident laserCloud{Corner,Surf}LastDS of the current scan (the
+ * pcl::copyPointCloud calls of MO:1600-1606) -- no host round trip. */
+int lvreg_add_keyframe_from_scan(lvreg_handle* h, const float pose_rpyxyz[6], int32_t* id_out);
 /* correctPoses after a loop closure (MO:1623-1640): replaces the first n keyframe poses. */
 int lvreg_update_keyframe_poses(lvreg_handle* h, const float* poses_rpyxyz, size_t n);
 int lvreg_num_keyframes(const lvreg_handle* h, size_t* n);

@@ -749,6 +749,31 @@ int lvreg_add_keyframe(lvreg_handle* h, const lvreg_cloud* corner, const lvreg_c
     return LVREG_OK;
 }
 
+int lvreg_add_keyframe_from_scan(lvreg_handle* h, const float pose[6], int32_t* id_out) {
+    if (!h || !pose) return LVREG_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    Keyframe* kf = new Keyframe();
+    for (int s = 0; s < 2; ++s) {
+        const uint32_t n = h->n_scan[s];
+        cudaError_t e = kf->cloud[s].reserve((size_t)(n ? n : 1) * 16);
+        if (e == cudaSuccess && n)
+            e = cudaMemcpyAsync(kf->cloud[s].p, h->scan_ds[s].p, (size_t)n * 16, cudaMemcpyDeviceToDevice, h->st);
+        if (e != cudaSuccess) {
+            kf->cloud[0].release();
+            kf->cloud[1].release();
+            delete kf;
+            h->err = cudaGetErrorString(e);
+            return LVREG_ERR_CUDA;
+        }
+        kf->n[s] = n;
+    }
+    CK(cudaStreamSynchronize(h->st));
+    memcpy(kf->pose, pose, sizeof(kf->pose));
+    h->kfs.push_back(kf);
+    if (id_out) *id_out = (int32_t)h->kfs.size() - 1;
+    return LVREG_OK;
+}
+
 int lvreg_update_keyframe_poses(lvreg_handle* h, const float* poses, size_t n) {
     if (!h || (!poses && n)) return LVREG_ERR_INVALID;
     if (n > h->kfs.size()) return fail(h, LVREG_ERR_INVALID, "more poses than keyframes");

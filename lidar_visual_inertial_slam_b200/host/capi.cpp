@@ -1,0 +1,112 @@
+// capi.cpp -- C exports of the host library (liblvreg_host.so) for ctypes callers (bench.py,
+// tests): the synthetic generator and the mapOptimization mirror.  Packed {x,y,z,intensity} rows.
+#include <cstring>
+#include <exception>
+#include <string>
+
+#include "harness.hpp"
+
+using namespace lvreg_host;
+
+namespace {
+thread_local std::string g_err;
+struct GenCtx {
+    World world;
+    SensorSpec sensor;
+    std::vector<float> corner, surf;
+};
+}  // namespace
+
+extern "C" {
+
+const char* lvh_last_error() { return g_err.c_str(); }
+
+// sensor: 0 MID360-like + indoor world, 1 128-beam + urban world
+void* lvh_gen_create(int sensor, uint64_t seed) {
+    GenCtx* g = new GenCtx();
+    g->sensor = sensor == 1 ? sensor_128beam() : sensor_mid360();
+    g->world = make_world(seed, sensor == 1 ? world_urban() : world_indoor());
+    return g;
+}
+void lvh_gen_destroy(void* p) { delete (GenCtx*)p; }
+
+// generates one scan; sizes are returned, data is fetched with lvh_gen_fetch
+void lvh_gen_scan(void* p, const float pose[6], uint64_t seed, int threads, size_t* n_corner, size_t* n_surf) {
+    GenCtx* g = (GenCtx*)p;
+    generate_scan(g->world, g->sensor, pose, seed, g->corner, g->surf, threads);
+    *n_corner = g->corner.size() / 4;
+    *n_surf = g->surf.size() / 4;
+}
+void lvh_gen_fetch(void* p, float* corner_out, float* surf_out) {
+    GenCtx* g = (GenCtx*)p;
+    if (corner_out && !g->corner.empty()) std::memcpy(corner_out, g->corner.data(), g->corner.size() * 4);
+    if (surf_out && !g->surf.empty()) std::memcpy(surf_out, g->surf.data(), g->surf.size() * 4);
+}
+
+void lvh_truth_pose(int sensor, uint64_t seed, double scan_period, double speed, int k, float pose[6]) {
+    SequenceSpec s{sensor, seed, 0, scan_period, speed, 0.f, 0.f};
+    truth_pose(s, k, pose);
+}
+void lvh_guess_pose(uint64_t seed, float guess_trans, float guess_rot, int k, const float truth[6], float guess[6]) {
+    SequenceSpec s{0, seed, 0, 0.0, 0.0, guess_trans, guess_rot};
+    guess_pose(s, k, truth, guess);
+}
+
+// ---- mapOptimization mirror ----
+void* lvh_mo_create(const lvreg_params* p, int device) {
+    try {
+        ParamServer ps;
+        if (p) ps.lv = *p;
+        return new mapOptimization(ps, device);
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return nullptr;
+    }
+}
+void lvh_mo_destroy(void* mo) { delete (mapOptimization*)mo; }
+
+// laserCloudInfoHandler for one scan (packed rows).  Returns the lvreg status of scan2map, or -1
+// when throttled, -2 on exception.
+int lvh_mo_handle_scan(void* p, const float* corner, size_t nc, const float* surf, size_t ns, double stamp,
+                       const float guess[6], float pose_out[6], lvreg_result* res, lvreg_timings* tim,
+                       int* n_keyframes) {
+    mapOptimization* mo = (mapOptimization*)p;
+    try {
+        Cloud c = cloud_from_xyzi(corner, nc), s = cloud_from_xyzi(surf, ns);
+        if (!mo->laserCloudInfoHandler(c, s, stamp, guess)) return -1;
+        std::memcpy(pose_out, mo->transformTobeMapped, 6 * sizeof(float));
+        if (res) *res = mo->lastResult;
+        if (tim) *tim = mo->lastTimings;
+        if (n_keyframes) *n_keyframes = (int)mo->cloudKeyPoses3D.size();
+        return mo->lastStatus;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return -2;
+    }
+}
+size_t lvh_mo_selection(void* p, int32_t* ids, size_t cap) {
+    mapOptimization* mo = (mapOptimization*)p;
+    const std::vector<int32_t>& v = mo->lastKeyframeSelection();
+    size_t n = v.size() < cap ? v.size() : cap;
+    if (ids && n) std::memcpy(ids, v.data(), n * sizeof(int32_t));
+    return v.size();
+}
+void* lvh_mo_handle(void* p) { return ((mapOptimization*)p)->handle(); }
+
+// whole-sequence replay (what lvreg_replay runs per sequence)
+int lvh_replay(int sensor, uint64_t seed, int n_scans, double period, double speed, float gt, float gr, int device,
+               int gen_threads, double* out /*10 doubles*/) {
+    try {
+        SequenceSpec s{sensor, seed, n_scans, period, speed, gt, gr};
+        ReplayStats st = replay_sequence(s, device, gen_threads);
+        out[0] = st.scans; out[1] = st.registered; out[2] = st.keyframes; out[3] = st.converged;
+        out[4] = (double)st.iterations; out[5] = (double)st.queries; out[6] = st.wall_s; out[7] = st.device_ms;
+        out[8] = st.max_pos_err; out[9] = st.max_rot_err;
+        return 0;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return -2;
+    }
+}
+
+}  // extern "C"

@@ -1,0 +1,294 @@
+// map_optimization.cpp -- see map_optimization.hpp.  Host logic only (keyframe selection,
+// bookkeeping); all point-level work is done by liblvreg on the GPU.
+#include "map_optimization.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+
+namespace lvreg_host {
+
+PointType make_point(float x, float y, float z, float intensity) {
+    PointType p;
+    p.x = x; p.y = y; p.z = z; p.data3 = 1.0f;
+    p.intensity = intensity; p.pad0 = p.pad1 = p.pad2 = 0.0f;
+    return p;
+}
+
+Cloud cloud_from_xyzi(const float* xyzi, size_t n) {
+    Cloud c(n);
+    for (size_t i = 0; i < n; ++i) c[i] = make_point(xyzi[4 * i], xyzi[4 * i + 1], xyzi[4 * i + 2], xyzi[4 * i + 3]);
+    return c;
+}
+
+lvreg_cloud as_lvreg_cloud(const Cloud& c) {
+    lvreg_cloud lc;
+    lc.data = c.empty() ? nullptr : c.data();
+    lc.n = c.size();
+    lc.stride = sizeof(PointType);
+    lc.intensity_offset = offsetof(PointType, intensity);
+    lc.on_device = 0;
+    lc.reserved = 0;
+    return lc;
+}
+
+static lvreg_cloud_out as_lvreg_out(Cloud& c) {
+    lvreg_cloud_out lo;
+    lo.data = c.empty() ? nullptr : c.data();
+    lo.capacity = c.size();
+    lo.stride = sizeof(PointType);
+    lo.intensity_offset = offsetof(PointType, intensity);
+    lo.on_device = 0;
+    lo.reserved = 0;
+    return lo;
+}
+
+mapOptimization::mapOptimization(const ParamServer& params, int device) : P_(params) {
+    std::memset(&lastResult, 0, sizeof(lastResult));
+    std::memset(&lastTimings, 0, sizeof(lastTimings));
+    int st = lvreg_create(&P_.lv, device, nullptr, &h_);
+    if (st != LVREG_OK)
+        throw std::runtime_error(std::string("lvreg_create failed: ") + lvreg_status_string(st) +
+                                 " (a CUDA device is required; there is no CPU fallback)");
+}
+
+mapOptimization::~mapOptimization() { lvreg_destroy(h_); }
+
+// pointDistance (utility.h:409-412)
+static inline float pointDistance(const PointType& a, const PointType& b) {
+    return std::sqrt((a.x - b.x) * (a.x - b.x) + (a.y - b.y) * (a.y - b.y) + (a.z - b.z) * (a.z - b.z));
+}
+
+std::vector<int32_t> mapOptimization::extractNearby() {
+    std::vector<int32_t> ids;
+    const size_t K = cloudKeyPoses3D.size();
+    if (K == 0) return ids;
+    const PointType& last = cloudKeyPoses3D.back();
+    // kdtreeSurroundingKeyPoses->radiusSearch(back, 50 m): strict d2 < r2, sorted by (d2, index)  MO:902-903
+    const float r2 = P_.surroundingKeyframeSearchRadius * P_.surroundingKeyframeSearchRadius;
+    std::vector<std::pair<float, int>> hits;
+    for (size_t i = 0; i < K; ++i) {
+        const PointType& p = cloudKeyPoses3D[i];
+        float dx = last.x - p.x, dy = last.y - p.y, dz = last.z - p.z;
+        float d2 = dx * dx;
+        d2 += dy * dy;
+        d2 += dz * dz;
+        if (d2 < r2) hits.emplace_back(d2, (int)i);
+    }
+    std::sort(hits.begin(), hits.end());
+    Cloud surroundingKeyPoses(hits.size());
+    for (size_t i = 0; i < hits.size(); ++i) surroundingKeyPoses[i] = cloudKeyPoses3D[hits[i].second];
+    // downSizeFilterSurroundingKeyPoses (2.0 m VoxelGrid) MO:910-911 -- on the GPU, same kernels
+    Cloud surroundingKeyPosesDS(surroundingKeyPoses.size());
+    size_t nds = 0;
+    {
+        lvreg_cloud in = as_lvreg_cloud(surroundingKeyPoses);
+        lvreg_cloud_out out = as_lvreg_out(surroundingKeyPosesDS);
+        int pt = 0;
+        int st = lvreg_voxelgrid(h_, &in, P_.surroundingKeyframeDensity, &out, &nds, nullptr, &pt);
+        if (st != LVREG_OK) throw std::runtime_error(std::string("lvreg_voxelgrid: ") + lvreg_last_error(h_));
+    }
+    surroundingKeyPosesDS.resize(nds);
+    // 1-NN back to a real key pose to recover the integer id (MO:912-916)
+    for (PointType& pt : surroundingKeyPosesDS) {
+        float best = INFINITY;
+        int besti = 0;
+        for (size_t i = 0; i < K; ++i) {
+            const PointType& p = cloudKeyPoses3D[i];
+            float dx = pt.x - p.x, dy = pt.y - p.y, dz = pt.z - p.z;
+            float d2 = dx * dx;
+            d2 += dy * dy;
+            d2 += dz * dz;
+            if (d2 < best) { best = d2; besti = (int)i; }
+        }
+        pt.intensity = cloudKeyPoses3D[besti].intensity;
+    }
+    // keyframes of the last 10 s, newest first (MO:919-926); may duplicate ids
+    for (long long i = (long long)K - 1; i >= 0; --i) {
+        if (timeLaserInfoCur - cloudKeyPoses6D[i].time < 10.0) surroundingKeyPosesDS.push_back(cloudKeyPoses3D[i]);
+        else break;
+    }
+    // extractCloud's filter (MO:938-939)
+    for (const PointType& pt : surroundingKeyPosesDS) {
+        if (pointDistance(pt, last) > P_.surroundingKeyframeSearchRadius) continue;
+        ids.push_back((int32_t)pt.intensity);
+    }
+    return ids;
+}
+
+void mapOptimization::extractSurroundingKeyFrames() {
+    if (cloudKeyPoses3D.empty()) return;                     // MO:974-975
+    std::vector<int32_t> ids = extractNearby();
+    // The reference rebuilds the map on every scan (MO:318); the map is a pure function of the id
+    // list and the keyframe poses, so it is rebuilt only when one of them changed.
+    if (!mapDirty_ && ids == lastIds_) return;
+    lvreg_map_info info;
+    int st = lvreg_build_local_map(h_, ids.data(), ids.size(), &info);
+    if (st != LVREG_OK) throw std::runtime_error(std::string("lvreg_build_local_map: ") + lvreg_last_error(h_));
+    laserCloudCornerFromMapDSNum = (int)info.n_corner_ds;
+    laserCloudSurfFromMapDSNum = (int)info.n_surf_ds;
+    lastIds_ = ids;
+    mapDirty_ = false;
+    lvreg_timings t;
+    lvreg_get_timings(h_, &t);
+    lastTimings.map_build_ms = t.map_build_ms;
+    lastTimings.grid_build_ms = t.grid_build_ms;
+    lastTimings.kernel_launches += t.kernel_launches;
+}
+
+void mapOptimization::downsampleCurrentScan() {
+    lvreg_cloud c = as_lvreg_cloud(laserCloudCornerLast), s = as_lvreg_cloud(laserCloudSurfLast);
+    size_t nc = 0, ns = 0;
+    int st = lvreg_downsample_scan(h_, &c, &s, &nc, &ns);
+    if (st != LVREG_OK) throw std::runtime_error(std::string("lvreg_downsample_scan: ") + lvreg_last_error(h_));
+    laserCloudCornerLastDSNum = (int)nc;
+    laserCloudSurfLastDSNum = (int)ns;
+    scanDownsampled_ = true;
+    lvreg_timings t;
+    lvreg_get_timings(h_, &t);
+    lastTimings.upload_ms = t.upload_ms;
+    lastTimings.downsample_ms = t.downsample_ms;
+    lastTimings.kernel_launches += t.kernel_launches;
+}
+
+void mapOptimization::scan2MapOptimization() {
+    if (cloudKeyPoses3D.empty()) {                           // MO:1317-1318
+        lastStatus = LVREG_ERR_NO_KEYFRAMES;
+        return;
+    }
+    lastStatus = lvreg_scan2map(h_, transformTobeMapped, &lastResult);
+    if (lastStatus == LVREG_ERR_NOT_ENOUGH_FEATURES) {
+        std::fprintf(stderr, "Not enough features! Only %d edge and %d planar features available.\n",
+                     laserCloudCornerLastDSNum, laserCloudSurfLastDSNum);          // MO:1341
+        return;
+    }
+    if (lastStatus != LVREG_OK) throw std::runtime_error(std::string("lvreg_scan2map: ") + lvreg_last_error(h_));
+    isDegenerate = lastResult.degenerate != 0;
+    // transformUpdate (MO:1345-1375): the clamps were applied by lvreg_scan2map; IMU slerp here
+    if (imuAvailable) lvreg_transform_update(h_, transformTobeMapped, 1, imuRollInit, imuPitchInit);
+    lvreg_timings t;
+    lvreg_get_timings(h_, &t);
+    lastTimings.register_ms = t.register_ms;
+    lastTimings.kernel_launches += t.kernel_launches;
+}
+
+static void pose_affine(const float x, const float y, const float z, const float roll, const float pitch,
+                        const float yaw, float T[12]) {
+    const float pose[6] = {roll, pitch, yaw, x, y, z};
+    lvreg_pose_to_affine(pose, T);
+}
+
+bool mapOptimization::saveFrame() {
+    if (cloudKeyPoses3D.empty()) return true;
+    const PointTypePose& b = cloudKeyPoses6D.back();
+    if (P_.sensorIsLivox && timeLaserInfoCur - b.time > 1.0) return true;      // MO:1392-1396
+    float S[12], F[12];
+    pose_affine(b.x, b.y, b.z, b.roll, b.pitch, b.yaw, S);
+    pose_affine(transformTobeMapped[3], transformTobeMapped[4], transformTobeMapped[5], transformTobeMapped[0],
+                transformTobeMapped[1], transformTobeMapped[2], F);
+    // transBetween = transStart.inverse() * transFinal (rigid inverse = [R^T | -R^T t])
+    float B[12];
+    for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j)
+            B[4 * i + j] = S[0 + i] * F[0 + j] + S[4 + i] * F[4 + j] + S[8 + i] * F[8 + j];
+        B[4 * i + 3] = S[0 + i] * (F[3] - S[3]) + S[4 + i] * (F[7] - S[7]) + S[8 + i] * (F[11] - S[11]);
+    }
+    // pcl::getTranslationAndEulerAngles
+    const float x = B[3], y = B[7], z = B[11];
+    const float roll = std::atan2(B[9], B[10]), pitch = std::asin(-B[8]), yaw = std::atan2(B[4], B[0]);
+    if (std::fabs(roll) < P_.surroundingkeyframeAddingAngleThreshold &&
+        std::fabs(pitch) < P_.surroundingkeyframeAddingAngleThreshold &&
+        std::fabs(yaw) < P_.surroundingkeyframeAddingAngleThreshold &&
+        std::sqrt(x * x + y * y + z * z) < P_.surroundingkeyframeAddingDistThreshold)
+        return false;
+    return true;
+}
+
+void mapOptimization::saveKeyFramesAndFactor() {
+    if (!saveFrame()) return;
+    // No iSAM2 here: the optimised estimate is the LM pose itself.
+    PointType p3 = make_point(transformTobeMapped[3], transformTobeMapped[4], transformTobeMapped[5],
+                              (float)cloudKeyPoses3D.size());
+    PointTypePose p6;
+    std::memset(&p6, 0, sizeof(p6));
+    p6.x = p3.x; p6.y = p3.y; p6.z = p3.z; p6.data3 = 1.0f;
+    p6.intensity = p3.intensity;
+    p6.roll = transformTobeMapped[0]; p6.pitch = transformTobeMapped[1]; p6.yaw = transformTobeMapped[2];
+    p6.time = timeLaserInfoCur;
+    // the keyframe clouds are the DS feature clouds of this scan (MO:1600-1606); they are already
+    // on the device, so they are handed over without a host round trip
+    if (!scanDownsampled_) downsampleCurrentScan();
+    int32_t id = -1;
+    int st = lvreg_add_keyframe_from_scan(h_, transformTobeMapped, &id);
+    if (st != LVREG_OK) throw std::runtime_error(std::string("lvreg_add_keyframe_from_scan: ") + lvreg_last_error(h_));
+    cloudKeyPoses3D.push_back(p3);
+    cloudKeyPoses6D.push_back(p6);
+    if (keepHostKeyframeCopies) {
+        cornerCloudKeyFrames.push_back(getLaserCloudLastDS(LVREG_CORNER));
+        surfCloudKeyFrames.push_back(getLaserCloudLastDS(LVREG_SURF));
+    }
+}
+
+void mapOptimization::correctPoses(const std::vector<PointTypePose>& corrected) {
+    std::vector<float> poses(6 * corrected.size());
+    for (size_t i = 0; i < corrected.size() && i < cloudKeyPoses6D.size(); ++i) {
+        cloudKeyPoses6D[i] = corrected[i];
+        cloudKeyPoses3D[i].x = corrected[i].x; cloudKeyPoses3D[i].y = corrected[i].y; cloudKeyPoses3D[i].z = corrected[i].z;
+        float* p = &poses[6 * i];
+        p[0] = corrected[i].roll; p[1] = corrected[i].pitch; p[2] = corrected[i].yaw;
+        p[3] = corrected[i].x; p[4] = corrected[i].y; p[5] = corrected[i].z;
+    }
+    lvreg_update_keyframe_poses(h_, poses.data(), std::min(corrected.size(), cloudKeyPoses6D.size()));
+    mapDirty_ = true;                                       // laserCloudMapContainer.clear() MO:1623
+}
+
+Cloud mapOptimization::transformPointCloud(const Cloud& cloudIn, const PointTypePose& t) {
+    Cloud out(cloudIn.size());
+    const float pose[6] = {t.roll, t.pitch, t.yaw, t.x, t.y, t.z};
+    lvreg_cloud in = as_lvreg_cloud(cloudIn);
+    lvreg_cloud_out lo = as_lvreg_out(out);
+    int st = lvreg_transform_cloud(h_, &in, pose, &lo);
+    if (st != LVREG_OK) throw std::runtime_error(std::string("lvreg_transform_cloud: ") + lvreg_last_error(h_));
+    return out;
+}
+
+Cloud mapOptimization::getLaserCloudLastDS(int which) {
+    size_t n = 0;
+    lvreg_get_scan_ds(h_, which, nullptr, &n);
+    Cloud c(n);
+    lvreg_cloud_out lo = as_lvreg_out(c);
+    int st = lvreg_get_scan_ds(h_, which, &lo, &n);
+    if (st != LVREG_OK) throw std::runtime_error(std::string("lvreg_get_scan_ds: ") + lvreg_last_error(h_));
+    return c;
+}
+
+Cloud mapOptimization::getLaserCloudFromMapDS(int which) {
+    size_t n = 0;
+    if (lvreg_get_local_map(h_, which, nullptr, &n) != LVREG_OK) return Cloud();
+    Cloud c(n);
+    lvreg_cloud_out lo = as_lvreg_out(c);
+    int st = lvreg_get_local_map(h_, which, &lo, &n);
+    if (st != LVREG_OK) throw std::runtime_error(std::string("lvreg_get_local_map: ") + lvreg_last_error(h_));
+    return c;
+}
+
+bool mapOptimization::laserCloudInfoHandler(const Cloud& corner, const Cloud& surf, double stamp, const float* guess) {
+    timeLaserInfoCur = stamp;
+    laserCloudCornerLast = corner;
+    laserCloudSurfLast = surf;
+    if (!(timeLaserInfoCur - timeLastProcessing_ >= P_.mappingProcessInterval)) return false;   // MO:311-314
+    timeLastProcessing_ = timeLaserInfoCur;
+    std::memset(&lastTimings, 0, sizeof(lastTimings));
+    scanDownsampled_ = false;
+    if (guess) std::memcpy(transformTobeMapped, guess, sizeof(transformTobeMapped));   // updateInitialGuess
+    extractSurroundingKeyFrames();
+    downsampleCurrentScan();
+    scan2MapOptimization();
+    saveKeyFramesAndFactor();
+    return true;
+}
+
+}  // namespace lvreg_host

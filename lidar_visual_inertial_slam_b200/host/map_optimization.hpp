@@ -1,0 +1,106 @@
+// map_optimization.hpp -- C++ host mirror of the reference's `class mapOptimization`
+// (lidar_odometry/src/mapOptimization.cpp:49-1782) for the scan-to-map path only.  Member
+// functions and data members keep the reference's names and meaning so that a maintainer can
+// swap the bodies one for one; every data-parallel step goes through the C ABI
+// of liblvreg (include/lvreg.h).  Not mirrored (out of scope): iSAM2 factors,
+// loop closure, GPS, ROS publishing -- saveKeyFramesAndFactor takes the LM pose as the keyframe
+// pose, which is what the replay harness needs.
+#pragma once
+
+#include <cstdint>
+#include <vector>
+
+#include "../../include/lvreg.h"
+
+namespace lvreg_host {
+
+// pcl::PointXYZI layout (utility.h:64): 32 bytes, {x,y,z,1 | intensity,0,0,0}
+struct PointType {
+    float x, y, z, data3;
+    float intensity, pad0, pad1, pad2;
+};
+static_assert(sizeof(PointType) == 32, "pcl::PointXYZI is 32 bytes");
+
+// PointXYZIRPYT (MO:29-46): 48 bytes, time at offset 32
+struct PointTypePose {
+    float x, y, z, data3;
+    float intensity, roll, pitch, yaw;
+    double time;
+    double pad;
+};
+static_assert(sizeof(PointTypePose) == 48, "PointXYZIRPYT is 48 bytes");
+
+typedef std::vector<PointType> Cloud;
+
+// the ParamServer fields the path reads (utility.h:119-140, 256-303)
+struct ParamServer {
+    lvreg_params lv;
+    float surroundingKeyframeSearchRadius = 50.0f;          // utility.h:285
+    float surroundingKeyframeDensity = 2.0f;                // utility.h:287
+    float surroundingkeyframeAddingDistThreshold = 1.0f;    // utility.h:279
+    float surroundingkeyframeAddingAngleThreshold = 0.2f;   // utility.h:281
+    bool  sensorIsLivox = true;                             // MO:1392-1396: keyframe every > 1.0 s
+    double mappingProcessInterval = 0.15;                   // utility.h:283, MO:311-314
+    ParamServer() { lvreg_default_params(&lv); }
+};
+
+class mapOptimization {
+  public:
+    explicit mapOptimization(const ParamServer& params = ParamServer(), int device = 0);
+    ~mapOptimization();
+    mapOptimization(const mapOptimization&) = delete;
+    mapOptimization& operator=(const mapOptimization&) = delete;
+
+    // ---- data members that are de-facto API in the reference ----
+    std::vector<Cloud> cornerCloudKeyFrames, surfCloudKeyFrames;     // MO:83-84 (host copies)
+    std::vector<PointType> cloudKeyPoses3D;                          // MO:86 (intensity = index)
+    std::vector<PointTypePose> cloudKeyPoses6D;                      // MO:87
+    Cloud laserCloudCornerLast, laserCloudSurfLast;                  // MO:91-92
+    int laserCloudCornerLastDSNum = 0, laserCloudSurfLastDSNum = 0;
+    int laserCloudCornerFromMapDSNum = 0, laserCloudSurfFromMapDSNum = 0;   // MO:134-135
+    float transformTobeMapped[6] = {0, 0, 0, 0, 0, 0};               // MO:126
+    bool isDegenerate = false;                                       // MO:131
+    double timeLaserInfoCur = 0.0;
+    bool imuAvailable = false;                                       // cloudInfo.imu_available
+    float imuRollInit = 0.f, imuPitchInit = 0.f;
+    lvreg_result lastResult;                                         // iterations, n_sel, ...
+    lvreg_timings lastTimings;
+    int lastStatus = LVREG_OK;
+    bool keepHostKeyframeCopies = false;
+
+    // ---- the path, same names as the reference ----
+    void extractSurroundingKeyFrames();      // MO:972-985 -> extractNearby + extractCloud
+    void downsampleCurrentScan();            // MO:987-999
+    void scan2MapOptimization();             // MO:1315-1343
+    bool saveFrame();                        // MO:1387-1412
+    void saveKeyFramesAndFactor();           // MO:1529-1613 without GTSAM
+    void correctPoses(const std::vector<PointTypePose>& corrected);   // MO:1615-1646
+    Cloud transformPointCloud(const Cloud& cloudIn, const PointTypePose& transformIn);   // MO:347-366
+    // laserCloudInfoHandler body MO:316-326 for one incoming scan; `guess` replaces
+    // updateInitialGuess (MO:806-877, out of scope).  Returns false when throttled (MO:311-314).
+    bool laserCloudInfoHandler(const Cloud& corner, const Cloud& surf, double stamp, const float* guess);
+
+    // read-backs of device-resident clouds (laserCloud*LastDS / *FromMapDS)
+    Cloud getLaserCloudLastDS(int which);
+    Cloud getLaserCloudFromMapDS(int which);
+    const std::vector<int32_t>& lastKeyframeSelection() const { return lastIds_; }
+    lvreg_handle* handle() { return h_; }
+
+    // extractNearby's id list (MO:894-929 + the distance filter of MO:938-939)
+    std::vector<int32_t> extractNearby();
+
+  private:
+    ParamServer P_;
+    lvreg_handle* h_ = nullptr;
+    std::vector<int32_t> lastIds_;
+    bool mapDirty_ = true;
+    double timeLastProcessing_ = -1;
+    bool scanDownsampled_ = false;
+};
+
+// helpers shared with the harness
+PointType make_point(float x, float y, float z, float intensity);
+Cloud cloud_from_xyzi(const float* xyzi, size_t n);
+lvreg_cloud as_lvreg_cloud(const Cloud& c);
+
+}  // namespace lvreg_host
