@@ -109,7 +109,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -294,11 +294,10 @@ def main():
             ms, wall = float(t[0]), float(t[1]) / 1e3
         return ms, wall, out, h.launch_count() - l0
 
+    sampler = ClockSampler(local_rank)        # sampled under load: warm-up + both timed regions
+    sampler.start()
     run_steps(args.warmup, 0, True)
     run_steps(args.warmup, 0, False)
-
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     ms_dev, wall_dev, out_dev, launches = timed(args.steps, args.warmup, True)       # inputs resident in HBM
     ms_e2e, wall_e2e, out_e2e, _ = timed(args.steps, args.warmup, False)              # host buffers
     clocks = sampler.stop()
