@@ -217,6 +217,11 @@ int lvreg_lm_step(lvreg_handle* h, const float* ori_xyzi, const float* coeff_xyz
 
 /* ---- measurement -------------------------------------------------------------------------- */
 int lvreg_get_timings(const lvreg_handle* h, lvreg_timings* t);
+/* Phase profile of the last lvreg_scan2map / lvreg_register_scan launch, from block 0's
+ * globaltimer stamps inside the cooperative kernel: for each executed iteration
+ * us[iter][0..3] = {tile work (kNN + fits + reduction), wait at the grid barrier, grid reduction,
+ * 6x6 solve + pose update} in microseconds.  `us` has room for LVREG_MAX_ITERS x 4 floats. */
+int lvreg_get_iteration_profile(const lvreg_handle* h, float* us, int* iterations);
 /* total kernels launched by this handle since creation */
 int lvreg_get_launch_count(const lvreg_handle* h, uint64_t* n);
 /* kNN micro-benchmark on device-resident data: runs `repeats` launches of the chosen variant on

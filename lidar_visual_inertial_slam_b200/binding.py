@@ -366,6 +366,13 @@ class Lvreg:
         self._ck(self.L.lvreg_get_timings(self.h, C.byref(t)))
         return t
 
+    def iteration_profile(self):
+        """[iterations, 4] microseconds: tile work, barrier wait, grid reduction, solve (block 0)"""
+        us = np.zeros((MAX_ITERS, 4), np.float32)
+        n = C.c_int(0)
+        self._ck(self.L.lvreg_get_iteration_profile(self.h, us.ctypes.data_as(C.c_void_p), C.byref(n)))
+        return us[:n.value].copy()
+
     def launch_count(self):
         n = C.c_uint64(0)
         self._ck(self.L.lvreg_get_launch_count(self.h, C.byref(n)))

@@ -355,11 +355,15 @@ __device__ __forceinline__ void jacobian_row(const Trig& g, float orix, float or
 __device__ inline bool qr_solve6(const float* Ain, const float* bin, float* x) {
     constexpr int n = 6;
     float A[36], b[6], vl[6], hf[6];
+#pragma unroll
     for (int i = 0; i < 36; ++i) A[i] = Ain[i];
+#pragma unroll
     for (int i = 0; i < 6; ++i) b[i] = bin[i];
+#pragma unroll
     for (int l = 0; l < n; ++l) {
         const int sz = n - l;
         float nrm = 0.0f;
+#pragma unroll
         for (int i = 0; i < sz; ++i) {
             vl[i] = A[(l + i) * n + l];
             nrm += vl[i] * vl[i];
@@ -368,23 +372,34 @@ __device__ inline bool qr_solve6(const float* Ain, const float* bin, float* x) {
         const float sgn = (vl[0] >= 0.0f) ? 1.0f : -1.0f;
         vl[0] = vl[0] + sgn * sqrtf(nrm);
         nrm = sqrtf(nrm + vl[0] * vl[0] - head * head);
+#pragma unroll
         for (int i = 0; i < sz; ++i) vl[i] /= nrm;
+#pragma unroll
         for (int j = l; j < n; ++j) {
             float dot = 0.0f;
+#pragma unroll
             for (int i = l; i < n; ++i) dot += vl[i - l] * A[i * n + j];
+#pragma unroll
             for (int i = l; i < n; ++i) A[i * n + j] -= 2 * vl[i - l] * dot;
         }
         hf[l] = vl[0] * vl[0];
+#pragma unroll
         for (int i = 1; i < sz; ++i) A[(l + i) * n + l] = vl[i] / vl[0];
     }
+#pragma unroll
     for (int l = 0; l < n; ++l) {
         vl[0] = 1.0f;
+#pragma unroll
         for (int j = 1; j < n - l; ++j) vl[j] = A[(j + l) * n + l];
         float dot = 0.0f;
+#pragma unroll
         for (int i = l; i < n; ++i) dot += vl[i - l] * b[i];
+#pragma unroll
         for (int i = l; i < n; ++i) b[i] -= 2 * vl[i - l] * dot * hf[l];
     }
+#pragma unroll
     for (int i = n - 1; i >= 0; --i) {
+#pragma unroll
         for (int j = n - 1; j > i; --j) b[i] -= b[j] * A[i * n + j];
         if (fabsf(A[i * n + i]) < FLT_EPSILON * 10.0f) {
             for (int k = 0; k < 6; ++k) x[k] = 0.0f;
@@ -430,6 +445,35 @@ __device__ inline bool lu_solve6(const float* Ain, const float* Bin, float* X) {
     return true;
 }
 
+// Rigorous shortcut for the degeneracy test (MO:1262-1281): if JtJ - mu*I admits a Cholesky
+// factorisation (fp64) with mu = threshold + a bound on the fp32 Jacobi eigenvalue error
+// (64 * eps * trace, far above the backward error of the sweep), then lambda_min > mu and the
+// Jacobi result would have every eigenvalue >= threshold.  Returns false when in doubt.
+__device__ inline bool clearly_well_conditioned(const float* AtA, float threshold) {
+    double tr = 0.0;
+    for (int i = 0; i < 6; ++i) tr += (double)AtA[i * 6 + i];
+    if (!(tr > 0.0) || !(tr < 1e30)) return false;
+    const double mu = (double)threshold * 1.01 + 64.0 * 1.1920929e-07 * tr;
+    double L[6][6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+        double d = (double)AtA[j * 6 + j] - mu;
+#pragma unroll
+        for (int k = 0; k < j; ++k) d -= L[j][k] * L[j][k];
+        if (!(d > 1e-12 * tr)) return false;
+        const double ljj = sqrt(d);
+        L[j][j] = ljj;
+#pragma unroll
+        for (int i = j + 1; i < 6; ++i) {
+            double v = 0.5 * ((double)AtA[i * 6 + j] + (double)AtA[j * 6 + i]);
+#pragma unroll
+            for (int k = 0; k < j; ++k) v -= L[i][k] * L[j][k];
+            L[i][j] = v / ljj;
+        }
+    }
+    return true;
+}
+
 struct LmState {            // isDegenerate (MO:131) and matP (MO:132) persist across scans
     int is_degenerate;
     float matP[36];
@@ -443,7 +487,11 @@ __device__ inline bool lm_solve(const float* AtA, const float* Atb, int iter, fl
     qr_solve6(AtA, Atb, X);
     float matP_local[36];
     for (int i = 0; i < 36; ++i) matP_local[i] = 0.0f;     // the shadowing local cv::Mat matP (MO:1220)
-    if (iter == 0) {
+    if (iter == 0 && clearly_well_conditioned(AtA, P.degeneracy_eig)) {
+        // every eigenvalue is provably above the threshold: cv::eigen would report the same
+        // (isDegenerate = false, matP unused), so the 6x6 Jacobi sweep is skipped
+        st->is_degenerate = 0;
+    } else if (iter == 0) {
         float A[36], E[6], V[36], V2[36];
         for (int i = 0; i < 36; ++i) A[i] = AtA[i];
         jacobi_eigen<6>(A, E, V);

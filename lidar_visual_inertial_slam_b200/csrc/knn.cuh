@@ -94,6 +94,159 @@ __device__ __forceinline__ int cell_coord(float q, float o, float inv, int dim, 
     return c;
 }
 
+// scan [s, e) keeping only candidates with d2 <= tau (ties at tau are resolved by the key order)
+template <int LPQ>
+__device__ __forceinline__ void scan_range_le(const GridView& g, uint32_t s, uint32_t e, int gl,
+                                              float qx, float qy, float qz, float tau, u64 (&t)[5]) {
+    for (uint32_t c = s + gl; c < e; c += LPQ) {
+        float4 p = __ldg(g.pts + c);
+        float d = sqdist(qx, qy, qz, p.x, p.y, p.z);
+        if (d <= tau) top5_insert(t, make_key(d, p.w));
+    }
+}
+
+// GATED search with geometric pruning.  The centre row (3 x-cells) is scanned first and merged;
+// its 5th distance (or the gate) becomes tau.  A remaining row / x-cell is visited only when its
+// lower-bound distance to the query (gap to the cell slab, minus a rounding slack) does not
+// exceed tau, so a typical query touches 6-8 of the 27 cells.  Results are identical to the
+// unpruned search: a skipped cell cannot hold a point with d2 <= tau.
+template <int LPQ>
+__device__ __forceinline__ void group_knn5_gated(const GridView& g, float qx, float qy, float qz, int gl,
+                                                 unsigned gmask, float gate_sq, u64 (&best)[5]) {
+    float ux, uy, uz;
+    const int cx = cell_coord(qx, g.ox, g.inv, g.dx, &ux);
+    const int cy = cell_coord(qy, g.oy, g.inv, g.dy, &uy);
+    const int cz = cell_coord(qz, g.oz, g.inv, g.dz, &uz);
+    const int lane_base = (threadIdx.x & 31) - gl;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) best[i] = kKeyNone;
+    const bool far = ux < -1.f || uy < -1.f || uz < -1.f || ux > (float)g.dx + 1.f ||
+                     uy > (float)g.dy + 1.f || uz > (float)g.dz + 1.f;
+    if (far) return;                           // nothing within the gate
+
+    // every lane fetches the 4 cell boundaries {cx-1, cx, cx+1, cx+2} of "its" rows
+    constexpr int RPL = (9 + LPQ - 1) / LPQ;
+    uint32_t b0[RPL], b1[RPL], b2[RPL], b3[RPL];
+#pragma unroll
+    for (int k = 0; k < RPL; ++k) {
+        const int r = gl + k * LPQ;
+        b0[k] = b1[k] = b2[k] = b3[k] = 0;
+        if (r < 9) {
+            const int yy = cy + (r % 3) - 1, zz = cz + (r / 3) - 1;
+            if (yy >= 0 && yy < g.dy && zz >= 0 && zz < g.dz) {
+                const uint32_t* row = g.cell_start + ((uint32_t)zz * g.dy + yy) * g.dx;
+                const uint32_t c1 = __ldg(row + cx), c2 = __ldg(row + cx + 1);
+                b1[k] = c1; b2[k] = c2;
+                b0[k] = cx > 0 ? __ldg(row + cx - 1) : c1;
+                b3[k] = cx + 1 < g.dx ? __ldg(row + cx + 2) : c2;
+            }
+        }
+    }
+    // gaps (in cells, shrunk by the rounding slack) from the query to the neighbouring slabs
+    const float slx = 0.002f + 4e-7f * fabsf(ux), sly = 0.002f + 4e-7f * fabsf(uy), slz = 0.002f + 4e-7f * fabsf(uz);
+    const float gxm = fmaxf(ux - (float)cx - slx, 0.f) * g.cell, gxp = fmaxf((float)(cx + 1) - ux - slx, 0.f) * g.cell;
+    const float gym = fmaxf(uy - (float)cy - sly, 0.f) * g.cell, gyp = fmaxf((float)(cy + 1) - uy - sly, 0.f) * g.cell;
+    const float gzm = fmaxf(uz - (float)cz - slz, 0.f) * g.cell, gzp = fmaxf((float)(cz + 1) - uz - slz, 0.f) * g.cell;
+
+    u64 t[5] = {kKeyNone, kKeyNone, kKeyNone, kKeyNone, kKeyNone};
+    float tau = gate_sq;                        // candidates need d2 < gate: handled by the final filter
+    // ---- centre row (row index 4), all three x cells ----
+    {
+        const uint32_t s = __shfl_sync(gmask, b0[4 / LPQ], lane_base + (4 % LPQ));
+        const uint32_t e = __shfl_sync(gmask, b3[4 / LPQ], lane_base + (4 % LPQ));
+        scan_range_le<LPQ>(g, s, e, gl, qx, qy, qz, tau, t);
+        group_merge<LPQ>(gmask, t, best);
+        if (best[4] != kKeyNone) tau = fminf(tau, key_d2(best[4]));
+#pragma unroll
+        for (int i = 0; i < 5; ++i) t[i] = gl == 0 ? best[i] : kKeyNone;
+    }
+    // ---- the other 8 rows, pruned by tau ----
+#pragma unroll
+    for (int r = 0; r < 9; ++r) {
+        if (r == 4) continue;
+        const uint32_t c0 = __shfl_sync(gmask, b0[r / LPQ], lane_base + (r % LPQ));
+        const uint32_t c1 = __shfl_sync(gmask, b1[r / LPQ], lane_base + (r % LPQ));
+        const uint32_t c2 = __shfl_sync(gmask, b2[r / LPQ], lane_base + (r % LPQ));
+        const uint32_t c3 = __shfl_sync(gmask, b3[r / LPQ], lane_base + (r % LPQ));
+        const int dyy = (r % 3) - 1, dzz = (r / 3) - 1;
+        const float gy = dyy == 0 ? 0.f : (dyy < 0 ? gym : gyp);
+        const float gz = dzz == 0 ? 0.f : (dzz < 0 ? gzm : gzp);
+        const float rb = gy * gy + gz * gz;
+        if (rb > tau) continue;
+        const uint32_t s = (rb + gxm * gxm > tau) ? c1 : c0;
+        const uint32_t e = (rb + gxp * gxp > tau) ? c2 : c3;
+        scan_range_le<LPQ>(g, s, e, gl, qx, qy, qz, tau, t);
+    }
+    group_merge<LPQ>(gmask, t, best);
+    // gate: only distances strictly below the gate count (MO:1025 / MO:1121 test d2[4] < 1.0)
+#pragma unroll
+    for (int i = 0; i < 5; ++i)
+        if (best[i] != kKeyNone && !(key_d2(best[i]) < gate_sq)) best[i] = kKeyNone;
+}
+
+// ---- thread-per-query GATED search -------------------------------------------------------------
+// One lane owns one query and keeps the exact top-5 itself, so there is no merge and the pruning
+// threshold tau = min(gate, current 5th distance) is always up to date.  Rows are visited nearest
+// first (centre, the four face neighbours, the four diagonals); a row / x-cell whose slab gap
+// exceeds tau is skipped.  Candidates are fetched four at a time to keep loads in flight.
+__device__ __forceinline__ void thread_scan(const GridView& g, uint32_t s, uint32_t e, float qx, float qy,
+                                            float qz, float gate_sq, u64 (&t)[5]) {
+    for (uint32_t c = s; c < e; c += 4) {
+        const uint32_t last = e - 1;
+        const float4 p0 = __ldg(g.pts + c);
+        const float4 p1 = __ldg(g.pts + min(c + 1, last));
+        const float4 p2 = __ldg(g.pts + min(c + 2, last));
+        const float4 p3 = __ldg(g.pts + min(c + 3, last));
+        const float inf = __int_as_float(0x7f800000);
+        const float d0 = sqdist(qx, qy, qz, p0.x, p0.y, p0.z);
+        const float d1 = c + 1 < e ? sqdist(qx, qy, qz, p1.x, p1.y, p1.z) : inf;
+        const float d2 = c + 2 < e ? sqdist(qx, qy, qz, p2.x, p2.y, p2.z) : inf;
+        const float d3 = c + 3 < e ? sqdist(qx, qy, qz, p3.x, p3.y, p3.z) : inf;
+        if (d0 < gate_sq) top5_insert(t, make_key(d0, p0.w));
+        if (d1 < gate_sq) top5_insert(t, make_key(d1, p1.w));
+        if (d2 < gate_sq) top5_insert(t, make_key(d2, p2.w));
+        if (d3 < gate_sq) top5_insert(t, make_key(d3, p3.w));
+    }
+}
+
+__device__ __forceinline__ void thread_knn5_gated(const GridView& g, float qx, float qy, float qz,
+                                                  float gate_sq, u64 (&t)[5]) {
+#pragma unroll
+    for (int i = 0; i < 5; ++i) t[i] = kKeyNone;
+    float ux, uy, uz;
+    const int cx = cell_coord(qx, g.ox, g.inv, g.dx, &ux);
+    const int cy = cell_coord(qy, g.oy, g.inv, g.dy, &uy);
+    const int cz = cell_coord(qz, g.oz, g.inv, g.dz, &uz);
+    const bool far = ux < -1.f || uy < -1.f || uz < -1.f || ux > (float)g.dx + 1.f ||
+                     uy > (float)g.dy + 1.f || uz > (float)g.dz + 1.f;
+    if (far) return;
+    const float slx = 0.002f + 4e-7f * fabsf(ux), sly = 0.002f + 4e-7f * fabsf(uy), slz = 0.002f + 4e-7f * fabsf(uz);
+    const float gxm = fmaxf(ux - (float)cx - slx, 0.f) * g.cell, gxp = fmaxf((float)(cx + 1) - ux - slx, 0.f) * g.cell;
+    const float gym = fmaxf(uy - (float)cy - sly, 0.f) * g.cell, gyp = fmaxf((float)(cy + 1) - uy - sly, 0.f) * g.cell;
+    const float gzm = fmaxf(uz - (float)cz - slz, 0.f) * g.cell, gzp = fmaxf((float)(cz + 1) - uz - slz, 0.f) * g.cell;
+    const float gxm2 = gxm * gxm, gxp2 = gxp * gxp;
+    // (dy, dz) visiting order: centre, faces, diagonals
+    const int ody[9] = {0, -1, 1, 0, 0, -1, 1, -1, 1};
+    const int odz[9] = {0, 0, 0, -1, 1, -1, -1, 1, 1};
+#pragma unroll
+    for (int r = 0; r < 9; ++r) {
+        const int dyy = ody[r], dzz = odz[r];
+        const int yy = cy + dyy, zz = cz + dzz;
+        if (yy < 0 || yy >= g.dy || zz < 0 || zz >= g.dz) continue;
+        const float gy = dyy == 0 ? 0.f : (dyy < 0 ? gym : gyp);
+        const float gz = dzz == 0 ? 0.f : (dzz < 0 ? gzm : gzp);
+        const float rb = gy * gy + gz * gz;
+        // tau: only points with d2 <= tau can still enter the list (strictly below the gate)
+        const float tau = t[4] == kKeyNone ? gate_sq : key_d2(t[4]);
+        if (rb > tau) continue;
+        const int xa = (cx > 0 && !(rb + gxm2 > tau)) ? cx - 1 : cx;
+        const int xb = (cx + 1 < g.dx && !(rb + gxp2 > tau)) ? cx + 1 : cx;
+        const uint32_t* row = g.cell_start + ((uint32_t)zz * g.dy + yy) * g.dx;
+        const uint32_t s = __ldg(row + xa), e = __ldg(row + xb + 1);
+        thread_scan(g, s, e, qx, qy, qz, gate_sq, t);
+    }
+}
+
 // One query, LPQ cooperating lanes (gl = lane index inside the group, gmask = the group's lanes).
 // exact == false: 3x3x3 block only, candidates with d2 >= gate_sq are dropped.
 template <int LPQ>
@@ -216,13 +369,14 @@ __global__ void __launch_bounds__(256) knn5_grid_kernel(GridView g, const float4
     for (uint32_t q = blockIdx.x * QPB + threadIdx.x / LPQ; q < nq; q += gridDim.x * QPB) {
         float4 p = __ldg(queries + q);
         u64 best[5];
-        group_knn5<LPQ>(g, p.x, p.y, p.z, gl, gmask, exact != 0, gate_sq, best);
-        if (gl < 5) {
-            u64 k = best[0];
+        if (exact) group_knn5<LPQ>(g, p.x, p.y, p.z, gl, gmask, true, gate_sq, best);
+        else group_knn5_gated<LPQ>(g, p.x, p.y, p.z, gl, gmask, gate_sq, best);
+        if (gl == 0) {
 #pragma unroll
-            for (int i = 1; i < 5; ++i) if (gl == i) k = best[i];
-            idx_out[(size_t)q * 5 + gl] = key_idx(k);
-            d2_out[(size_t)q * 5 + gl] = key_d2(k);
+            for (int i = 0; i < 5; ++i) {
+                idx_out[(size_t)q * 5 + i] = key_idx(best[i]);
+                d2_out[(size_t)q * 5 + i] = key_d2(best[i]);
+            }
         }
     }
 }

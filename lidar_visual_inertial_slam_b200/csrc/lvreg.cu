@@ -70,14 +70,17 @@ struct lvreg_handle {
     cudaStream_t st = nullptr;
     bool own_stream = false;
     int num_sms = kNumSMs;
-    int lpq = 8;
+    int lpq = 4;
+    int tile = 16;
+    int force_tpq = -1;           // -1 auto, 0 grouped, 1 thread-per-query (LVREG_TPQ)
+    bool reg_occ_is_tpq = false;
     std::vector<Keyframe*> kfs;
     MapSide map[2];
     DevBuf scan_ds[2];
     uint32_t n_scan[2] = {0, 0};
     // scratch
     DevBuf stage[2], raw[2], concat, keys[2], vals[2], sort_scratch, scan_temp, scan_in, vox_start, vox_keys;
-    DevBuf segs, small, partials, regout, lmstate, posebuf, qbuf, idxbuf, d2buf, brute_partial, coeffbuf, flagbuf;
+    DevBuf segs, small, partials, regout, lmstate, posebuf, tilectr, qbuf, idxbuf, d2buf, brute_partial, coeffbuf, flagbuf;
     void* pinned = nullptr;       // 64 KB page-locked scratch for small transfers
     cudaEvent_t ev[EV_COUNT];
     bool ev_set[EV_COUNT];
@@ -498,18 +501,34 @@ float clampf(float v, float lim) {
     return v;
 }
 
-template <int LPQ>
+template <int LPQ, int TILE>
 int launch_register(lvreg_handle* h, RegArgs& args, int grid) {
     void* kargs[] = {&args};
-    CK(cudaLaunchCooperativeKernel((void*)register_kernel<LPQ>, dim3(grid), dim3(kRegThreads), kargs, 0, h->st));
+    CK(cudaLaunchCooperativeKernel((void*)register_kernel<LPQ, TILE>, dim3(grid), dim3(kRegThreads), kargs, 0, h->st));
     return LVREG_OK;
 }
 
-template <int LPQ>
+template <int LPQ, int TILE>
 int reg_occupancy(lvreg_handle* h, int* nb) {
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(nb, register_kernel<LPQ>, kRegThreads, 0));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(nb, register_kernel<LPQ, TILE>, kRegThreads, 0));
     return LVREG_OK;
 }
+
+// (lanes per query, queries per warp tile) variants compiled in; selected by LVREG_LPQ / LVREG_TILE
+#define LVREG_REG_DISPATCH(FN, ...)                                             \
+    do {                                                                        \
+        const int key_ = h->lpq * 100 + h->tile;                                \
+        switch (key_) {                                                         \
+            case 408: CKS((FN<4, 8>(__VA_ARGS__))); break;                      \
+            case 416: CKS((FN<4, 16>(__VA_ARGS__))); break;                     \
+            case 432: CKS((FN<4, 32>(__VA_ARGS__))); break;                     \
+            case 808: CKS((FN<8, 8>(__VA_ARGS__))); break;                      \
+            case 832: CKS((FN<8, 32>(__VA_ARGS__))); break;                     \
+            case 1616: CKS((FN<16, 16>(__VA_ARGS__))); break;                   \
+            case 1632: CKS((FN<16, 32>(__VA_ARGS__))); break;                   \
+            default: CKS((FN<8, 16>(__VA_ARGS__))); break;                      \
+        }                                                                       \
+    } while (0)
 
 int scan2map_impl(lvreg_handle* h, float pose[6], lvreg_result* res) {
     if (res) {
@@ -546,18 +565,25 @@ int scan2map_impl(lvreg_handle* h, float pose[6], lvreg_result* res) {
     args.out = h->regout.as<RegOut>();
     args.lm = h->lmstate.as<LmState>();
 
+    // thread-per-query when every warp scheduler gets >= 2 warps of queries, else lane groups
+    const bool tpq = h->force_tpq > 0 || (h->force_tpq < 0 &&
+                     (h->n_scan[0] + h->n_scan[1]) / 32 >= (uint32_t)h->num_sms * 8);
+    if (tpq != h->reg_occ_is_tpq) h->reg_max_blocks_per_sm = 0;
+    h->reg_occ_is_tpq = tpq;
+    if (h->reg_max_blocks_per_sm == 0 && tpq) {
+        int nb = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, register_tpq_kernel, kRegThreads, 0));
+        if (nb < 1) return fail(h, LVREG_ERR_CUDA, "register_tpq_kernel does not fit on an SM");
+        h->reg_max_blocks_per_sm = nb;
+    }
     if (h->reg_max_blocks_per_sm == 0) {
         int nb = 0;
-        switch (h->lpq) {
-            case 4: CKS(reg_occupancy<4>(h, &nb)); break;
-            case 16: CKS(reg_occupancy<16>(h, &nb)); break;
-            case 32: CKS(reg_occupancy<32>(h, &nb)); break;
-            default: CKS(reg_occupancy<8>(h, &nb)); break;
-        }
+        LVREG_REG_DISPATCH(reg_occupancy, h, &nb);
         if (nb < 1) return fail(h, LVREG_ERR_CUDA, "register_kernel does not fit on an SM");
         h->reg_max_blocks_per_sm = nb;
     }
-    const uint32_t tiles = nblk(h->n_scan[0], 32) + nblk(h->n_scan[1], 32);
+    const int tile_q = tpq ? 32 : h->tile;
+    const uint32_t tiles = nblk(h->n_scan[0], tile_q) + nblk(h->n_scan[1], tile_q);
     int grid = (int)nblk(tiles, kRegWarps);
     const int max_grid = h->reg_max_blocks_per_sm * h->num_sms;
     if (grid > max_grid) grid = max_grid;
@@ -565,11 +591,13 @@ int scan2map_impl(lvreg_handle* h, float pose[6], lvreg_result* res) {
     CK(h->partials.reserve((size_t)2 * grid * kRegTerms * sizeof(double)));
     args.partials = h->partials.as<double>();
 
-    switch (h->lpq) {
-        case 4: CKS(launch_register<4>(h, args, grid)); break;
-        case 16: CKS(launch_register<16>(h, args, grid)); break;
-        case 32: CKS(launch_register<32>(h, args, grid)); break;
-        default: CKS(launch_register<8>(h, args, grid)); break;
+    CK(cudaMemsetAsync(h->tilectr.p, 0, LVREG_MAX_ITERS * sizeof(uint32_t), h->st));
+    args.tile_counter = h->tilectr.as<uint32_t>();
+    if (tpq) {
+        void* kargs[] = {&args};
+        CK(cudaLaunchCooperativeKernel((void*)register_tpq_kernel, dim3(grid), dim3(kRegThreads), kargs, 0, h->st));
+    } else {
+        LVREG_REG_DISPATCH(launch_register, h, args, grid);
     }
     launched(h);
     RegOut* ho = (RegOut*)((char*)h->pinned + 256);
@@ -686,7 +714,8 @@ int lvreg_create(const lvreg_params* p, int device, void* cuda_stream, lvreg_han
     }
     if (cudaMallocHost(&h->pinned, 65536) != cudaSuccess) return bail(LVREG_ERR_CUDA);
     if (h->small.reserve(SM_WORDS * 4) != cudaSuccess || h->regout.reserve(sizeof(RegOut)) != cudaSuccess ||
-        h->lmstate.reserve(sizeof(LmState)) != cudaSuccess || h->posebuf.reserve(256) != cudaSuccess)
+        h->lmstate.reserve(sizeof(LmState)) != cudaSuccess || h->posebuf.reserve(256) != cudaSuccess ||
+        h->tilectr.reserve(LVREG_MAX_ITERS * sizeof(uint32_t)) != cudaSuccess)
         return bail(LVREG_ERR_CUDA);
     cudaMemsetAsync(h->lmstate.p, 0, sizeof(LmState), h->st);
     cudaMemsetAsync(h->small.p, 0, SM_WORDS * 4, h->st);
@@ -694,6 +723,13 @@ int lvreg_create(const lvreg_params* p, int device, void* cuda_stream, lvreg_han
     if (e) {
         int v = atoi(e);
         if (v == 4 || v == 8 || v == 16 || v == 32) h->lpq = v;
+    }
+    e = getenv("LVREG_TPQ");
+    if (e) h->force_tpq = atoi(e) ? 1 : 0;
+    e = getenv("LVREG_TILE");
+    if (e) {
+        int v = atoi(e);
+        if (v == 8 || v == 16 || v == 32) h->tile = v;
     }
     if (cudaStreamSynchronize(h->st) != cudaSuccess) return bail(LVREG_ERR_CUDA);
     *out = h;
@@ -715,7 +751,7 @@ void lvreg_destroy(lvreg_handle* h) {
         h->keys[s].release(); h->vals[s].release();
     }
     DevBuf* bufs[] = {&h->concat, &h->sort_scratch, &h->scan_temp, &h->scan_in, &h->vox_start, &h->vox_keys,
-                      &h->segs, &h->small, &h->partials, &h->regout, &h->lmstate, &h->posebuf, &h->qbuf,
+                      &h->segs, &h->small, &h->partials, &h->regout, &h->lmstate, &h->posebuf, &h->tilectr, &h->qbuf,
                       &h->idxbuf, &h->d2buf, &h->brute_partial, &h->coeffbuf, &h->flagbuf};
     for (DevBuf* b : bufs) b->release();
     if (h->pinned) cudaFreeHost(h->pinned);
@@ -1205,6 +1241,19 @@ int lvreg_lm_step(lvreg_handle* h, const float* ori, const float* coeff, size_t 
 int lvreg_get_timings(const lvreg_handle* h, lvreg_timings* t) {
     if (!h || !t) return LVREG_ERR_INVALID;
     *t = h->last;
+    return LVREG_OK;
+}
+
+int lvreg_get_iteration_profile(const lvreg_handle* h, float* us, int* iterations) {
+    if (!h || !us) return LVREG_ERR_INVALID;
+    const RegOut* ho = (const RegOut*)((const char*)h->pinned + 256);    // last D2H copy of RegOut
+    int n = ho->iterations;
+    if (n < 0) n = 0;
+    if (n > h->prm.max_iters) n = h->prm.max_iters;
+    for (int i = 0; i < n; ++i)
+        for (int k = 0; k < 4; ++k)
+            us[i * 4 + k] = (float)((double)(ho->stamp[i][k + 1] - ho->stamp[i][k]) * 1e-3);
+    if (iterations) *iterations = n;
     return LVREG_OK;
 }
 

@@ -39,6 +39,9 @@ struct RegOut {                          // device mirror of lvreg_result's dyna
     float pose_iter[32][6];
     float cost[32];
     float pose[6];                       // final transformTobeMapped
+    // block 0's phase timestamps per iteration (globaltimer ns): start, tiles done, barrier
+    // passed, reduction done, solve done -- diagnostics for lvreg_get_iteration_profile
+    unsigned long long stamp[32][5];
 };
 
 struct RegArgs {
@@ -49,11 +52,18 @@ struct RegArgs {
     RegParams prm;
     const float* pose_in;                // transformTobeMapped on entry
     double* partials;                    // [2][gridDim.x][kRegTerms]
+    uint32_t* tile_counter;              // [LVREG max iters] zeroed by the host before the launch
     RegOut* out;
     LmState* lm;
 };
 
 // term t (0..27) -> the (i, j) pair, i <= j over 7 columns
+__device__ __forceinline__ unsigned long long gtimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
 __device__ __forceinline__ void term_pair(int t, int* i, int* j) {
     int a = 0, rem = t;
     while (rem >= 7 - a) { rem -= 7 - a; ++a; }
@@ -80,15 +90,18 @@ __device__ __forceinline__ bool fit_query(int cls, const float4* __restrict__ ma
     return ok;
 }
 
-template <int LPQ>
-__global__ void __launch_bounds__(kRegThreads) register_kernel(RegArgs a) {
+template <int LPQ, int TILE>
+__global__ void __launch_bounds__(kRegThreads, 2) register_kernel(RegArgs a) {
+    constexpr int GROUPS = 32 / LPQ;                 // lane groups per warp
+    constexpr int QPG = TILE / GROUPS;               // queries searched by one group per tile
+    static_assert(TILE % GROUPS == 0 && QPG >= 1, "tile / group mismatch");
     cg::grid_group grid = cg::this_grid();
     __shared__ Affine sT;
     __shared__ Trig sTrig;
     __shared__ float sPose[6];
-    __shared__ int sNN[kRegWarps][32][5];
-    __shared__ float sD5[kRegWarps][32];
-    __shared__ float sRow[kRegWarps][32][8];
+    __shared__ int sNN[kRegWarps][TILE][5];
+    __shared__ float sD5[kRegWarps][TILE];
+    __shared__ float sRow[kRegWarps][TILE][9];
     __shared__ double sRed[kRegWarps][kRegTerms];
     __shared__ double sSum[kRegTerms];
     __shared__ int sStop;
@@ -98,8 +111,7 @@ __global__ void __launch_bounds__(kRegThreads) register_kernel(RegArgs a) {
     const int gl = lane % LPQ, grp = lane / LPQ;
     const unsigned gmask = (LPQ == 32) ? 0xffffffffu : (((1u << LPQ) - 1u) << (lane - gl));
     const RegParams P = a.prm;
-    const uint32_t nc = a.n[0], ns = a.n[1];
-    const uint32_t tiles_c = (nc + 31) / 32, tiles_s = (ns + 31) / 32;
+    const uint32_t tiles_c = (a.n[0] + TILE - 1) / TILE, tiles_s = (a.n[1] + TILE - 1) / TILE;
     const uint32_t tiles = tiles_c + tiles_s;
 
     if (threadIdx.x < 6) sPose[threadIdx.x] = a.pose_in[threadIdx.x];
@@ -112,31 +124,39 @@ __global__ void __launch_bounds__(kRegThreads) register_kernel(RegArgs a) {
     int iter = 0;
     int converged = 0;
     for (; iter < P.max_iters; ++iter) {
-        if (threadIdx.x == 0) pose_to_affine_dev(sPose, &sT, &sTrig);
+        if (threadIdx.x == 0) {
+            if (blockIdx.x == 0) a.out->stamp[iter][0] = gtimer();
+            pose_to_affine_dev(sPose, &sT, &sTrig);
+        }
         __syncthreads();
         const Affine T = sT;
         const Trig trig = sTrig;
         double acc = 0.0;                                   // this lane's term, over the warp's tiles
 
-        for (uint32_t tile = blockIdx.x * kRegWarps + warp; tile < tiles; tile += gridDim.x * kRegWarps) {
+        // dynamic tile scheduler: corner tiles (denser cells, costlier) are handed out first
+        for (;;) {
+            uint32_t tile = 0;
+            if (lane == 0) tile = atomicAdd(a.tile_counter + iter, 1u);
+            tile = __shfl_sync(0xffffffffu, tile, 0);
+            if (tile >= tiles) break;
             const int cls = tile < tiles_c ? 0 : 1;
-            const uint32_t base = (cls == 0 ? tile : tile - tiles_c) * 32;
+            const uint32_t base = (cls == 0 ? tile : tile - tiles_c) * TILE;
             const uint32_t cnt = a.n[cls];
             const uint32_t qi = base + lane;
-            const bool valid = qi < cnt;
+            const bool valid = lane < TILE && qi < cnt;
             float4 ori = valid ? __ldg(a.scan[cls] + qi) : make_float4(0.f, 0.f, 0.f, 0.f);
             const float3 sel = apply_affine(T, ori.x, ori.y, ori.z);
 
-            // phase A: each lane group searches LPQ of the tile's 32 queries
+            // phase A: each lane group searches QPG of the tile's queries
 #pragma unroll 1
-            for (int k = 0; k < LPQ; ++k) {
-                const int ql = grp * LPQ + k;                // query (= lane) inside the tile
+            for (int k = 0; k < QPG; ++k) {
+                const int ql = grp * QPG + k;                // query (= lane) inside the tile
                 const float qx = __shfl_sync(0xffffffffu, sel.x, ql);
                 const float qy = __shfl_sync(0xffffffffu, sel.y, ql);
                 const float qz = __shfl_sync(0xffffffffu, sel.z, ql);
                 u64 best[5];
                 if (base + ql < cnt) {
-                    group_knn5<LPQ>(a.grid[cls], qx, qy, qz, gl, gmask, false, P.knn_gate_sq, best);
+                    group_knn5_gated<LPQ>(a.grid[cls], qx, qy, qz, gl, gmask, P.knn_gate_sq, best);
                 } else {
 #pragma unroll
                     for (int i = 0; i < 5; ++i) best[i] = kKeyNone;
@@ -150,27 +170,29 @@ __global__ void __launch_bounds__(kRegThreads) register_kernel(RegArgs a) {
             __syncwarp();
 
             // phase B: lane l fits query l
-            int nn[5];
+            if (lane < TILE) {
+                int nn[5];
 #pragma unroll
-            for (int i = 0; i < 5; ++i) nn[i] = sNN[warp][lane][i];
-            float4 coeff;
-            const bool ok = valid && fit_query(cls, a.map[cls], nn, sD5[warp][lane], ori, sel, P, &coeff);
-            float row[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            if (ok) jacobian_row(trig, ori.x, ori.y, ori.z, coeff, row);
+                for (int i = 0; i < 5; ++i) nn[i] = sNN[warp][lane][i];
+                float4 coeff;
+                const bool ok = valid && fit_query(cls, a.map[cls], nn, sD5[warp][lane], ori, sel, P, &coeff);
+                float row[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                if (ok) jacobian_row(trig, ori.x, ori.y, ori.z, coeff, row);
 #pragma unroll
-            for (int i = 0; i < 7; ++i) sRow[warp][lane][i] = row[i];
-            sRow[warp][lane][7] = ok ? 1.0f : 0.0f;
+                for (int i = 0; i < 7; ++i) sRow[warp][lane][i] = row[i];
+                sRow[warp][lane][7] = ok ? 1.0f : 0.0f;
+            }
             __syncwarp();
 
-            // phase C: lane t adds term t of the 32 rows, in row order
+            // phase C: lane t adds term t of the tile's rows, in row order
             if (lane < kRegTerms) {
                 if (lane < 28) {
 #pragma unroll 8
-                    for (int r = 0; r < 32; ++r)
+                    for (int r = 0; r < TILE; ++r)
                         acc += (double)sRow[warp][r][ti] * (double)sRow[warp][r][tj];
                 } else {
 #pragma unroll 8
-                    for (int r = 0; r < 32; ++r) acc += (double)sRow[warp][r][7];
+                    for (int r = 0; r < TILE; ++r) acc += (double)sRow[warp][r][7];
                 }
             }
             __syncwarp();
@@ -186,7 +208,9 @@ __global__ void __launch_bounds__(kRegThreads) register_kernel(RegArgs a) {
             for (int w = 0; w < kRegWarps; ++w) s += sRed[w][threadIdx.x];
             part[threadIdx.x] = s;
         }
+        if (blockIdx.x == 0 && threadIdx.x == 0) a.out->stamp[iter][1] = gtimer();
         grid.sync();
+        if (blockIdx.x == 0 && threadIdx.x == 0) a.out->stamp[iter][2] = gtimer();
 
         // every block: grid reduction in block order, then the 6x6 solve (bit-identical everywhere)
         {
@@ -208,12 +232,15 @@ __global__ void __launch_bounds__(kRegThreads) register_kernel(RegArgs a) {
             __syncthreads();
         }
         if (threadIdx.x == 0) {
+            if (blockIdx.x == 0) a.out->stamp[iter][3] = gtimer();
             const int n_sel = (int)(sSum[28] + 0.5);
             int conv = 0;
             if (n_sel >= P.min_matches) {
                 float AtA[36], Atb[6];
                 int t = 0;
+#pragma unroll
                 for (int i = 0; i < 7; ++i)
+#pragma unroll
                     for (int j = i; j < 7; ++j, ++t) {
                         if (j < 6) { AtA[i * 6 + j] = (float)sSum[t]; AtA[j * 6 + i] = (float)sSum[t]; }
                         else if (i < 6) Atb[i] = (float)sSum[t];
@@ -228,6 +255,163 @@ __global__ void __launch_bounds__(kRegThreads) register_kernel(RegArgs a) {
                 a.out->n_sel[iter] = n_sel;
                 a.out->cost[iter] = (float)sSum[27];
                 for (int i = 0; i < 6; ++i) a.out->pose_iter[iter][i] = sPose[i];
+                a.out->stamp[iter][4] = gtimer();
+            }
+        }
+        __syncthreads();
+        const int stop = sStop;
+        if (stop == 1) { converged = 1; ++iter; break; }
+        if (stop == 2) {
+            if (blockIdx.x == 0 && threadIdx.x == 0)
+                for (int k = iter + 1; k < P.max_iters; ++k) {
+                    a.out->n_sel[k] = a.out->n_sel[iter];
+                    a.out->cost[k] = a.out->cost[iter];
+                    for (int i = 0; i < 6; ++i) a.out->pose_iter[k][i] = sPose[i];
+                }
+            iter = P.max_iters;
+            break;
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        a.out->iterations = iter;
+        a.out->converged = converged;
+        a.out->degenerate = sLm.is_degenerate;
+        for (int i = 0; i < 6; ++i) a.out->pose[i] = sPose[i];
+        *a.lm = sLm;
+    }
+}
+
+// ---- thread-per-query variant ---------------------------------------------------------------------
+// Same loop, but one lane owns one query end to end (search + fit in registers, no shared-memory
+// hand-off, no shuffles in the search).  Preferred when there are enough queries to give every
+// scheduler several warps; the grouped variant above wins for small scans.
+__global__ void __launch_bounds__(kRegThreads, 2) register_tpq_kernel(RegArgs a) {
+    constexpr int TILE = 32;
+    cg::grid_group grid = cg::this_grid();
+    __shared__ Affine sT;
+    __shared__ Trig sTrig;
+    __shared__ float sPose[6];
+    __shared__ float sRow[kRegWarps][TILE][9];
+    __shared__ double sRed[kRegWarps][kRegTerms];
+    __shared__ double sSum[kRegTerms];
+    __shared__ int sStop;
+    __shared__ LmState sLm;
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const RegParams P = a.prm;
+    const uint32_t tiles_c = (a.n[0] + TILE - 1) / TILE, tiles_s = (a.n[1] + TILE - 1) / TILE;
+    const uint32_t tiles = tiles_c + tiles_s;
+
+    if (threadIdx.x < 6) sPose[threadIdx.x] = a.pose_in[threadIdx.x];
+    if (threadIdx.x == 0) { sLm = *a.lm; sStop = 0; }
+    __syncthreads();
+
+    int ti = 0, tj = 0;
+    if (lane < 28) term_pair(lane, &ti, &tj);
+
+    int iter = 0;
+    int converged = 0;
+    for (; iter < P.max_iters; ++iter) {
+        if (threadIdx.x == 0) {
+            if (blockIdx.x == 0) a.out->stamp[iter][0] = gtimer();
+            pose_to_affine_dev(sPose, &sT, &sTrig);
+        }
+        __syncthreads();
+        const Affine T = sT;
+        const Trig trig = sTrig;
+        double acc = 0.0;
+
+        for (;;) {
+            uint32_t tile = 0;
+            if (lane == 0) tile = atomicAdd(a.tile_counter + iter, 1u);
+            tile = __shfl_sync(0xffffffffu, tile, 0);
+            if (tile >= tiles) break;
+            const int cls = tile < tiles_c ? 0 : 1;
+            const uint32_t base = (cls == 0 ? tile : tile - tiles_c) * TILE;
+            const uint32_t qi = base + lane;
+            const bool valid = qi < a.n[cls];
+            float4 ori = valid ? __ldg(a.scan[cls] + qi) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float3 sel = apply_affine(T, ori.x, ori.y, ori.z);
+            float row[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            bool ok = false;
+            if (valid) {
+                u64 best[5];
+                thread_knn5_gated(a.grid[cls], sel.x, sel.y, sel.z, P.knn_gate_sq, best);
+                int nn[5];
+#pragma unroll
+                for (int i = 0; i < 5; ++i) nn[i] = key_idx(best[i]);
+                float4 coeff;
+                ok = fit_query(cls, a.map[cls], nn, key_d2(best[4]), ori, sel, P, &coeff);
+                if (ok) jacobian_row(trig, ori.x, ori.y, ori.z, coeff, row);
+            }
+#pragma unroll
+            for (int i = 0; i < 7; ++i) sRow[warp][lane][i] = row[i];
+            sRow[warp][lane][7] = ok ? 1.0f : 0.0f;
+            __syncwarp();
+            if (lane < kRegTerms) {
+                if (lane < 28) {
+#pragma unroll 8
+                    for (int r = 0; r < TILE; ++r)
+                        acc += (double)sRow[warp][r][ti] * (double)sRow[warp][r][tj];
+                } else {
+#pragma unroll 8
+                    for (int r = 0; r < TILE; ++r) acc += (double)sRow[warp][r][7];
+                }
+            }
+            __syncwarp();
+        }
+
+        if (lane < kRegTerms) sRed[warp][lane] = acc;
+        __syncthreads();
+        double* part = a.partials + ((size_t)(iter & 1) * gridDim.x + blockIdx.x) * kRegTerms;
+        if (threadIdx.x < kRegTerms) {
+            double s = 0.0;
+#pragma unroll
+            for (int w = 0; w < kRegWarps; ++w) s += sRed[w][threadIdx.x];
+            part[threadIdx.x] = s;
+        }
+        if (blockIdx.x == 0 && threadIdx.x == 0) a.out->stamp[iter][1] = gtimer();
+        grid.sync();
+        if (blockIdx.x == 0 && threadIdx.x == 0) a.out->stamp[iter][2] = gtimer();
+        {
+            const double* all = a.partials + (size_t)(iter & 1) * gridDim.x * kRegTerms;
+            const int t = threadIdx.x % 32, chain = threadIdx.x / 32;
+            double s = 0.0;
+            if (t < kRegTerms)
+                for (uint32_t b = chain; b < gridDim.x; b += kRegWarps) s += all[(size_t)b * kRegTerms + t];
+            __syncthreads();
+            if (t < kRegTerms) sRed[chain][t] = s;
+            __syncthreads();
+            if (threadIdx.x < kRegTerms) {
+                double tot = 0.0;
+#pragma unroll
+                for (int w = 0; w < kRegWarps; ++w) tot += sRed[w][threadIdx.x];
+                sSum[threadIdx.x] = tot;
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+            if (blockIdx.x == 0) a.out->stamp[iter][3] = gtimer();
+            const int n_sel = (int)(sSum[28] + 0.5);
+            int conv = 0;
+            if (n_sel >= P.min_matches) {
+                float AtA[36], Atb[6];
+                int t = 0;
+#pragma unroll
+                for (int i = 0; i < 7; ++i)
+#pragma unroll
+                    for (int j = i; j < 7; ++j, ++t) {
+                        if (j < 6) { AtA[i * 6 + j] = (float)sSum[t]; AtA[j * 6 + i] = (float)sSum[t]; }
+                        else if (i < 6) Atb[i] = (float)sSum[t];
+                    }
+                conv = lm_solve(AtA, Atb, iter, sPose, &sLm, P, nullptr) ? 1 : 0;
+            }
+            sStop = conv ? 1 : (n_sel < P.min_matches ? 2 : 0);
+            if (blockIdx.x == 0) {
+                a.out->n_sel[iter] = n_sel;
+                a.out->cost[iter] = (float)sSum[27];
+                for (int i = 0; i < 6; ++i) a.out->pose_iter[iter][i] = sPose[i];
+                a.out->stamp[iter][4] = gtimer();
             }
         }
         __syncthreads();
@@ -280,7 +464,7 @@ __global__ void __launch_bounds__(kRegThreads) residual_kernel(GridView g, const
             const float qz = __shfl_sync(0xffffffffu, sel.z, ql);
             u64 best[5];
             if (base + ql < n) {
-                group_knn5<LPQ>(g, qx, qy, qz, gl, gmask, false, P.knn_gate_sq, best);
+                group_knn5_gated<LPQ>(g, qx, qy, qz, gl, gmask, P.knn_gate_sq, best);
             } else {
 #pragma unroll
                 for (int i = 0; i < 5; ++i) best[i] = kKeyNone;
