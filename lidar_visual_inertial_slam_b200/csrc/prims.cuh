@@ -132,94 +132,75 @@ inline void exclusive_scan(In in, Out out, uint32_t n, uint32_t* temp, uint32_t*
 }
 
 // ------------------------------------------------------------------------------------------
-// stable LSD radix sort, 8 bits per pass
+// stable LSD radix sort, 8 bits per pass, one kernel per pass ("onesweep" organisation):
+//   rs_global_hist_kernel   one read of the keys -> global digit histograms of ALL passes
+//   rs_onesweep_kernel      per pass: tile ranking (warp match), tile offsets resolved by
+//                           decoupled look-back over the preceding tiles (no separate scan
+//                           kernel, no second read of the keys), scatter staged through shared
+//                           memory so that every digit run leaves the SM as one coalesced burst
+// HBM traffic per pass: 8 B read + 8 B written per pair (+ 4 B per pair once for the histograms).
+// Tiles take their index from an atomic ticket, so a tile only ever waits on tiles that are
+// already running; within a tile the element order is (warp, round, lane) == index order, which
+// makes the sort stable.
 // ------------------------------------------------------------------------------------------
 constexpr int kSortThreads = 256;
 constexpr int kSortItems = 16;
-constexpr int kSortTile = kSortThreads * kSortItems;   // 4096 pairs per block
+constexpr int kSortTile = kSortThreads * kSortItems;   // 4096 pairs per tile
 constexpr int kSortWarps = kSortThreads / 32;
+constexpr int kSortMaxPasses = 4;
+constexpr uint32_t kFlagAgg = 1u << 30, kFlagIncl = 2u << 30, kFlagMask = 3u << 30;
 
-// per-tile digit histogram -> table[digit * nblocks + block]; digit totals -> totals[digit]
-__global__ void __launch_bounds__(kSortThreads) rs_hist_kernel(const uint32_t* __restrict__ keys,
-                                                               uint32_t n, int shift,
-                                                               uint32_t* __restrict__ table,
-                                                               uint32_t* __restrict__ totals,
-                                                               uint32_t nblocks) {
-    __shared__ uint32_t hist[256];
-    hist[threadIdx.x] = 0;
+__global__ void __launch_bounds__(256) rs_global_hist_kernel(const uint32_t* __restrict__ keys, uint32_t n,
+                                                             int passes, uint32_t* __restrict__ ghist) {
+    __shared__ uint32_t hist[8][kSortMaxPasses][256];       // one copy per warp: conflicts stay intra-warp
+    const int warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < 8 * kSortMaxPasses * 256; i += 256) (&hist[0][0][0])[i] = 0;
     __syncthreads();
-    const uint32_t base = blockIdx.x * kSortTile;
-#pragma unroll 4
-    for (int k = 0; k < kSortItems; ++k) {
-        uint32_t i = base + k * kSortThreads + threadIdx.x;
-        if (i < n) atomicAdd(&hist[(keys[i] >> shift) & 255u], 1u);
+    for (uint32_t i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+        const uint32_t k = keys[i];
+#pragma unroll
+        for (int p = 0; p < kSortMaxPasses; ++p)
+            if (p < passes) atomicAdd(&hist[warp][p][(k >> (8 * p)) & 255u], 1u);
     }
     __syncthreads();
-    uint32_t c = hist[threadIdx.x];
-    table[threadIdx.x * nblocks + blockIdx.x] = c;
-    if (c) atomicAdd(&totals[threadIdx.x], c);
-}
-
-// one block per digit: table row -> exclusive global offsets
-__global__ void __launch_bounds__(256) rs_scan_kernel(uint32_t* __restrict__ table,
-                                                      const uint32_t* __restrict__ totals,
-                                                      uint32_t nblocks) {
-    __shared__ uint32_t red[256];
-    __shared__ uint32_t warp_sums[8];
-    __shared__ uint32_t carry_s;
-    const int d = blockIdx.x;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // base offset of this digit = sum of totals of all smaller digits
-    red[threadIdx.x] = (int)threadIdx.x < d ? totals[threadIdx.x] : 0;
-    __syncthreads();
-    for (int s = 128; s > 0; s >>= 1) {
-        if ((int)threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) carry_s = red[0];
-    __syncthreads();
-    uint32_t* row = table + (size_t)d * nblocks;
-    for (uint32_t base = 0; base < nblocks; base += 256) {
-        uint32_t i = base + threadIdx.x;
-        uint32_t v = i < nblocks ? row[i] : 0;
-        uint32_t inc = warp_inclusive_scan(v, lane);
-        if (lane == 31) warp_sums[warp] = inc;
-        __syncthreads();
-        if (warp == 0) {
-            uint32_t w = lane < 8 ? warp_sums[lane] : 0;
-            uint32_t winc = warp_inclusive_scan(w, lane);
-            if (lane < 8) warp_sums[lane] = winc - w;
-        }
-        __syncthreads();
-        uint32_t exc = inc - v + warp_sums[warp] + carry_s;
-        if (i < nblocks) row[i] = exc;
-        __syncthreads();
-        if (threadIdx.x == 255) carry_s = exc + v;
-        __syncthreads();
+    for (int i = threadIdx.x; i < passes * 256; i += 256) {
+        uint32_t s = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) s += (&hist[w][0][0])[i];
+        if (s) atomicAdd(&ghist[i], s);
     }
 }
 
-// stable scatter: element order inside a tile is (warp, round, lane) == index order
-__global__ void __launch_bounds__(kSortThreads) rs_scatter_kernel(
+__global__ void __launch_bounds__(kSortThreads) rs_onesweep_kernel(
     const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
-    uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
-    const uint32_t* __restrict__ table, uint32_t n, int shift, uint32_t nblocks) {
+    uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, uint32_t n, int shift,
+    const uint32_t* __restrict__ ghist /*256, this pass*/, volatile uint32_t* status /*[tiles][256]*/,
+    uint32_t* ticket) {
+    __shared__ uint32_t sk[kSortTile];
+    __shared__ uint32_t sv[kSortTile];
     __shared__ uint32_t wcnt[kSortWarps][256];
-    __shared__ uint32_t gbase[256];
+    __shared__ uint32_t gofs[256];          // global offset of a digit run minus its tile-local start
+    __shared__ uint32_t scan_ws[8];
+    __shared__ uint32_t tile_s;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) tile_s = atomicAdd(ticket, 1u);
     for (int i = threadIdx.x; i < kSortWarps * 256; i += kSortThreads) (&wcnt[0][0])[i] = 0;
-    gbase[threadIdx.x] = table[threadIdx.x * nblocks + blockIdx.x];
     __syncthreads();
+    const uint32_t tile = tile_s;
 
-    const uint32_t base = blockIdx.x * kSortTile + warp * (32 * kSortItems);
+    // ---- rank the tile's elements (stable) ----
+    const uint32_t base = tile * kSortTile + warp * (32 * kSortItems);
     uint32_t k[kSortItems], v[kSortItems];
     uint16_t rank[kSortItems];
 #pragma unroll
     for (int r = 0; r < kSortItems; ++r) {
         const uint32_t i = base + r * 32 + lane;
         const bool valid = i < n;
-        k[r] = valid ? keys_in[i] : 0xffffffffu;
+        k[r] = valid ? keys_in[i] : 0xffffffffu;     // padding sorts last inside the (final) tile
         v[r] = valid ? vals_in[i] : 0u;
+    }
+#pragma unroll
+    for (int r = 0; r < kSortItems; ++r) {
         const uint32_t d = (k[r] >> shift) & 255u;
         const uint32_t peers = __match_any_sync(0xffffffffu, d);
         const int leader = __ffs(peers) - 1;
@@ -233,31 +214,86 @@ __global__ void __launch_bounds__(kSortThreads) rs_scatter_kernel(
         __syncwarp();
     }
     __syncthreads();
-    {   // per-digit exclusive prefix over the warps of this block
-        uint32_t run = 0;
+
+    // ---- per digit: tile count, exclusive prefix over warps, publish, look back ----
+    const int d = threadIdx.x;               // one thread per digit
+    uint32_t cnt = 0;
 #pragma unroll
-        for (int w = 0; w < kSortWarps; ++w) {
-            uint32_t c = wcnt[w][threadIdx.x];
-            wcnt[w][threadIdx.x] = run;
-            run += c;
-        }
+    for (int w = 0; w < kSortWarps; ++w) {
+        const uint32_t c = wcnt[w][d];
+        wcnt[w][d] = cnt;
+        cnt += c;
     }
+    // the padding of the last tile was counted under digit 255: remove it from the published count
+    uint32_t pad = 0;
+    if (d == 255) {
+        const uint32_t tile_end = (tile + 1) * kSortTile;
+        pad = tile_end > n ? tile_end - n : 0;
+    }
+    const uint32_t real_cnt = cnt - pad;
+    status[(size_t)tile * 256 + d] = (tile == 0 ? kFlagIncl : kFlagAgg) | real_cnt;
+
+    // exclusive scan of the global histogram (digit bases) and of the tile counts (tile-local starts)
+    uint32_t gb, tl;
+    {
+        const uint32_t gh = ghist[d];
+        uint32_t a = warp_inclusive_scan(gh, lane);
+        if (lane == 31) scan_ws[warp] = a;
+        __syncthreads();
+        uint32_t wp = 0;
+        for (int w = 0; w < warp; ++w) wp += scan_ws[w];
+        gb = a - gh + wp;
+        __syncthreads();
+        uint32_t b = warp_inclusive_scan(cnt, lane);
+        if (lane == 31) scan_ws[warp] = b;
+        __syncthreads();
+        wp = 0;
+        for (int w = 0; w < warp; ++w) wp += scan_ws[w];
+        tl = b - cnt + wp;
+    }
+    uint32_t excl = 0;
+    if (tile > 0) {
+        for (int pred = (int)tile - 1; pred >= 0; --pred) {
+            uint32_t s;
+            do { s = status[(size_t)pred * 256 + d]; } while ((s & kFlagMask) == 0);
+            excl += s & ~kFlagMask;
+            if (s & kFlagIncl) break;
+        }
+        status[(size_t)tile * 256 + d] = kFlagIncl | (excl + real_cnt);
+    }
+    gofs[d] = gb + excl - tl;
+    // tile-local start of each (warp, digit) run
+#pragma unroll
+    for (int w = 0; w < kSortWarps; ++w) wcnt[w][d] += tl;
     __syncthreads();
+
+    // ---- stage in shared memory in tile-sorted order, then write coalesced runs ----
 #pragma unroll
     for (int r = 0; r < kSortItems; ++r) {
-        const uint32_t i = base + r * 32 + lane;
-        if (i < n) {
-            const uint32_t d = (k[r] >> shift) & 255u;
-            const uint32_t pos = gbase[d] + wcnt[warp][d] + rank[r];
-            keys_out[pos] = k[r];
-            vals_out[pos] = v[r];
+        const uint32_t dd = (k[r] >> shift) & 255u;
+        const uint32_t pos = wcnt[warp][dd] + rank[r];
+        sk[pos] = k[r];
+        sv[pos] = v[r];
+    }
+    __syncthreads();
+    const uint32_t tile_n = min((uint32_t)kSortTile, n - tile * kSortTile);
+#pragma unroll
+    for (int r = 0; r < kSortItems; ++r) {
+        const uint32_t e = r * kSortThreads + threadIdx.x;
+        if (e < tile_n) {
+            const uint32_t key = sk[e];
+            const uint32_t dst = gofs[(key >> shift) & 255u] + e;
+            keys_out[dst] = key;
+            vals_out[dst] = sv[e];
         }
     }
 }
 
 inline uint32_t sort_num_blocks(uint32_t n) { return (n + kSortTile - 1) / kSortTile; }
-// scratch needed by radix_sort_pairs, in uint32 words
-inline size_t sort_scratch_words(uint32_t n) { return (size_t)256 * sort_num_blocks(n) + 256; }
+// scratch needed by radix_sort_pairs, in uint32 words: look-back status per pass + histograms + tickets
+inline size_t sort_scratch_words(uint32_t n) {
+    return (size_t)kSortMaxPasses * 256 * sort_num_blocks(n) + kSortMaxPasses * 256 + 8;
+}
 
 // Sorts (keys, vals) by the low `key_bits` bits of key, stable.  Ping-pongs between the two
 // buffer pairs; returns 0 when the result is in (keys0, vals0), 1 when in (keys1, vals1).
@@ -266,22 +302,27 @@ inline int radix_sort_pairs(uint32_t* keys0, uint32_t* vals0, uint32_t* keys1, u
                             int* launches) {
     if (n == 0) return 0;
     const uint32_t nblocks = sort_num_blocks(n);
-    uint32_t* table = scratch;
-    uint32_t* totals = scratch + (size_t)256 * nblocks;
+    int passes = key_bits <= 0 ? 1 : (key_bits + 7) / 8;
+    if (passes > kSortMaxPasses) passes = kSortMaxPasses;
+    uint32_t* status = scratch;
+    uint32_t* ghist = scratch + (size_t)kSortMaxPasses * 256 * nblocks;
+    uint32_t* tickets = ghist + kSortMaxPasses * 256;
+    cudaMemsetAsync(scratch, 0, ((size_t)passes * 256 * nblocks) * sizeof(uint32_t), st);
+    cudaMemsetAsync(ghist, 0, (kSortMaxPasses * 256 + 8) * sizeof(uint32_t), st);
+    uint32_t hb = (n + 256 * 16 - 1) / (256 * 16);
+    if (hb > (uint32_t)kNumSMs * 8) hb = kNumSMs * 8;
+    rs_global_hist_kernel<<<hb, 256, 0, st>>>(keys0, n, passes, ghist);
     int cur = 0;
-    const int passes = key_bits <= 0 ? 1 : (key_bits + 7) / 8;
     for (int p = 0; p < passes; ++p) {
         const uint32_t* kin = cur ? keys1 : keys0;
         const uint32_t* vin = cur ? vals1 : vals0;
         uint32_t* kout = cur ? keys0 : keys1;
         uint32_t* vout = cur ? vals0 : vals1;
-        cudaMemsetAsync(totals, 0, 256 * sizeof(uint32_t), st);
-        rs_hist_kernel<<<nblocks, kSortThreads, 0, st>>>(kin, n, 8 * p, table, totals, nblocks);
-        rs_scan_kernel<<<256, 256, 0, st>>>(table, totals, nblocks);
-        rs_scatter_kernel<<<nblocks, kSortThreads, 0, st>>>(kin, vin, kout, vout, table, n, 8 * p, nblocks);
-        if (launches) *launches += 3;
+        rs_onesweep_kernel<<<nblocks, kSortThreads, 0, st>>>(kin, vin, kout, vout, n, 8 * p, ghist + 256 * p,
+                                                             status + (size_t)p * 256 * nblocks, tickets + p);
         cur ^= 1;
     }
+    if (launches) *launches += 1 + passes;
     return cur;
 }
 
