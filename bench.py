@@ -187,9 +187,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    from lidar_visual_inertial_slam_b200 import multi
+    rank, world, local_rank = multi.rank_info()
 
     def log(msg):
         print("[bench rank %d] %s" % (rank, msg), file=sys.stderr, flush=True)
@@ -231,13 +230,11 @@ def main():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     use_dist = world > 1
-    if use_dist:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    multi.init(backend="nccl", device=torch.device("cuda", local_rank))     # barrier + timing reduce only
 
     stream = torch.cuda.current_stream().cuda_stream
     h = lv.Lvreg(device=local_rank, stream=stream)
-    seed = SEED + rank                                                # independent sequence per GPU
+    seed = multi.sequence_seed(SEED, rank)                            # independent sequence per GPU
     ds = make_dataset(args.workload, seed, lambda p, leaf: h.voxelgrid(p, leaf)[0], log)
     for i in range(len(ds["kf_pose"])):
         h.add_keyframe(ds["kf_corner"][i], ds["kf_surf"][i], ds["kf_pose"][i])
@@ -274,8 +271,7 @@ def main():
         return out
 
     def timed(n, first, on_device):
-        if use_dist:
-            dist.barrier()
+        multi.barrier()
         torch.cuda.synchronize()
         l0 = h.launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -285,14 +281,10 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
-        if use_dist:
-            dist.barrier()
-        ms = e0.elapsed_time(e1)
-        if use_dist:
-            t = torch.tensor([ms, wall * 1e3], device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms, wall = float(t[0]), float(t[1]) / 1e3
-        return ms, wall, out, h.launch_count() - l0
+        multi.barrier()
+        ms, _ = multi.reduce_timing(e0.elapsed_time(e1), n, device="cuda")       # max over ranks
+        wall_ms, _ = multi.reduce_timing(wall * 1e3, n, device="cuda")
+        return ms, wall_ms / 1e3, out, h.launch_count() - l0
 
     sampler = ClockSampler(local_rank)        # sampled under load: warm-up + both timed regions
     sampler.start()
@@ -365,6 +357,7 @@ def main():
         print(json.dumps(line), flush=True)
     h.close()
     if use_dist:
+        import torch.distributed as dist
         dist.destroy_process_group()
     return 0
 

@@ -253,11 +253,28 @@ __global__ void __launch_bounds__(kSortThreads) rs_onesweep_kernel(
     }
     uint32_t excl = 0;
     if (tile > 0) {
-        for (int pred = (int)tile - 1; pred >= 0; --pred) {
-            uint32_t s;
-            do { s = status[(size_t)pred * 256 + d]; } while ((s & kFlagMask) == 0);
-            excl += s & ~kFlagMask;
-            if (s & kFlagIncl) break;
+        // decoupled look-back, 16 predecessors per round trip (independent loads in flight)
+        constexpr int LB = 16;
+        int pred = (int)tile - 1;
+        bool done = false;
+        while (!done) {
+            uint32_t s[LB];
+#pragma unroll
+            for (int j = 0; j < LB; ++j) {
+                const int idx = pred - j;
+                s[j] = 0x80000000u;                                            // before tile 0: inclusive prefix 0
+                if (idx >= 0) s[j] = status[(size_t)idx * 256 + d];
+            }
+#pragma unroll
+            for (int j = 0; j < LB; ++j) {
+                if (!done) {
+                    uint32_t v = s[j];
+                    while ((v & kFlagMask) == 0) v = status[(size_t)(pred - j) * 256 + d];
+                    excl += v & ~kFlagMask;
+                    if (v & kFlagIncl) done = true;
+                }
+            }
+            pred -= LB;
         }
         status[(size_t)tile * 256 + d] = kFlagIncl | (excl + real_cnt);
     }
