@@ -1,0 +1,78 @@
+#!/usr/bin/env python
+"""BASELINE C4: kNN micro-benchmark sweep, Nq in {1k..100k} x M in {10k..4M}, grid (gated / exact)
+vs brute force, device-resident data, CUDA-event timing inside the library (lvreg_bench_knn5).
+
+    python benchmarks/knn_sweep.py [--quick] > profiles/r01_knn_sweep.json
+
+HBM fraction (grid) uses the algorithmic bytes of SURVEY 8d: 56 B/query + 16 B/map point per launch.
+FP32 fraction (brute) uses 8 flops per pair against the nominal 148 SM x 128 lanes x 1.965 GHz."""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import lidar_visual_inertial_slam_b200 as lv   # noqa: E402
+
+
+def make_map(rng, m):
+    """ground + facades at ~6 pts/m^2 (what a 0.4 m VoxelGrid leaves on planar structure)"""
+    side = float(np.sqrt(m / 6.0))
+    n_ground = int(0.7 * m)
+    g = np.stack([rng.uniform(0, side, n_ground), rng.uniform(0, side, n_ground), rng.normal(0, 0.02, n_ground)], 1)
+    n_wall = m - n_ground
+    wx = rng.integers(0, max(2, int(side / 10)), n_wall) * 10.0 + rng.normal(0, 0.02, n_wall)
+    w = np.stack([wx, rng.uniform(0, side, n_wall), rng.uniform(0, 8, n_wall)], 1)
+    pts = np.concatenate([g, w]).astype(np.float32)
+    return np.concatenate([pts, np.zeros((m, 1), np.float32)], 1), side
+
+
+def make_queries(rng, mp, side, nq):
+    near = mp[rng.integers(0, len(mp), int(0.9 * nq))][:, :3] + rng.normal(0, 0.05, (int(0.9 * nq), 3))
+    far = np.stack([rng.uniform(0, side, nq - len(near)), rng.uniform(0, side, nq - len(near)),
+                    rng.uniform(0, 8, nq - len(near))], 1)
+    q = np.concatenate([near, far]).astype(np.float32)
+    return np.concatenate([q, np.zeros((nq, 1), np.float32)], 1)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--quick", action="store_true")
+    args = ap.parse_args()
+    nqs = [1000, 10000, 100000] if args.quick else [1000, 3000, 10000, 30000, 100000]
+    ms_ = [10000, 1000000] if args.quick else [10000, 100000, 1000000, 4000000]
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+    hbm = peaks.get("hbm_gbs", 6650.0)
+    fp32_peak = 148 * 128 * 1.965e9          # lane-ops/s, nominal
+    rng = np.random.default_rng(4)
+    h = lv.Lvreg()
+    rows = []
+    for m in ms_:
+        mp, side = make_map(rng, m)
+        info = h.set_local_map(mp[:16], mp)
+        for nq in nqs:
+            q = make_queries(rng, mp, side, nq)
+            for name, variant in (("grid_gated", lv.KNN_GRID_GATED), ("grid_exact", lv.KNN_GRID_EXACT), ("brute", lv.KNN_BRUTE)):
+                if variant == lv.KNN_BRUTE and nq * m > 4e11:
+                    continue
+                reps = 3 if variant == lv.KNN_BRUTE and nq * m > 1e10 else 10
+                ms = h.bench_knn5(lv.SURF, q, variant, reps)
+                row = dict(M=m, Nq=nq, variant=name, ms=ms, queries_per_s=nq / (ms * 1e-3))
+                if variant == lv.KNN_BRUTE:
+                    row["tflops"] = 8.0 * nq * m / (ms * 1e-3) / 1e12
+                    row["fp32_frac_of_nominal"] = 8.0 * nq * m / (ms * 1e-3) / fp32_peak
+                else:
+                    gbs = (56.0 * nq + 16.0 * m) / (ms * 1e-3) / 1e9
+                    row["algorithmic_gbs"] = gbs
+                    row["hbm_frac_of_measured"] = gbs / hbm
+                rows.append(row)
+                print(json.dumps(row), file=sys.stderr, flush=True)
+    print(json.dumps(dict(benchmark="C4 kNN sweep", grid_cell_m=float(info.grid_cell[1]), hbm_peak_gbs=hbm, rows=rows)))
+    h.close()
+
+
+if __name__ == "__main__":
+    main()
