@@ -222,6 +222,9 @@ int lvreg_get_timings(const lvreg_handle* h, lvreg_timings* t);
  * us[iter][0..3] = {tile work (kNN + fits + reduction), wait at the grid barrier, grid reduction,
  * 6x6 solve + pose update} in microseconds.  `us` has room for LVREG_MAX_ITERS x 4 floats. */
 int lvreg_get_iteration_profile(const lvreg_handle* h, float* us, int* iterations);
+/* Diagnostics (set LVREG_DEBUG_TILES=1 before lvreg_create): duration in ns of every query tile of
+ * iteration 1 of the last registration, in tile order (corner tiles first). */
+int lvreg_debug_tile_times(lvreg_handle* h, uint32_t* ns_out, size_t cap, size_t* n_tiles);
 /* total kernels launched by this handle since creation */
 int lvreg_get_launch_count(const lvreg_handle* h, uint64_t* n);
 /* kNN micro-benchmark on device-resident data: runs `repeats` launches of the chosen variant on

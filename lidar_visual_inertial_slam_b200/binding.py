@@ -373,6 +373,14 @@ class Lvreg:
         self._ck(self.L.lvreg_get_iteration_profile(self.h, us.ctypes.data_as(C.c_void_p), C.byref(n)))
         return us[:n.value].copy()
 
+    def debug_tile_times(self):
+        n = C.c_size_t(0)
+        self._ck(self.L.lvreg_debug_tile_times(self.h, None, C.c_size_t(0), C.byref(n)))
+        out = np.zeros(n.value, np.uint32)
+        if n.value:
+            self._ck(self.L.lvreg_debug_tile_times(self.h, out.ctypes.data_as(C.c_void_p), C.c_size_t(n.value), C.byref(n)))
+        return out
+
     def launch_count(self):
         n = C.c_uint64(0)
         self._ck(self.L.lvreg_get_launch_count(self.h, C.byref(n)))

@@ -456,10 +456,22 @@ __global__ void __launch_bounds__(256) cell_keys_kernel(const float4* __restrict
 struct CountIn {
     const uint32_t* c;
     __device__ __forceinline__ uint32_t operator()(uint32_t i) const { return c[i]; }
+    __device__ __forceinline__ void load_vec(uint32_t i, uint32_t (&v)[8]) const {
+        const uint4 a = *reinterpret_cast<const uint4*>(c + i);
+        const uint4 b = *reinterpret_cast<const uint4*>(c + i + 4);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    }
 };
 struct StartOut {
     uint32_t* s;
     __device__ __forceinline__ void operator()(uint32_t i, uint32_t, uint32_t pre) const { s[i] = pre; }
+    __device__ __forceinline__ void store_vec(uint32_t i, const uint32_t (&v)[8], uint32_t pre) const {
+        uint4 a, b;
+        a.x = pre; a.y = a.x + v[0]; a.z = a.y + v[1]; a.w = a.z + v[2];
+        b.x = a.w + v[3]; b.y = b.x + v[4]; b.z = b.y + v[5]; b.w = b.z + v[6];
+        *reinterpret_cast<uint4*>(s + i) = a;
+        *reinterpret_cast<uint4*>(s + i + 4) = b;
+    }
 };
 
 __global__ void __launch_bounds__(256) cell_gather_kernel(const float4* __restrict__ pts,

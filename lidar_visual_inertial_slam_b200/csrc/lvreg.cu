@@ -72,6 +72,8 @@ struct lvreg_handle {
     int num_sms = kNumSMs;
     int lpq = 4;
     int tile = 16;
+    int debug_tiles = 0;          // LVREG_DEBUG_TILES=1: record per-tile durations of iteration 1
+    uint32_t debug_ntiles = 0;
     int force_tpq = -1;           // -1 auto, 0 grouped, 1 thread-per-query (LVREG_TPQ)
     bool reg_occ_is_tpq = false;
     std::vector<Keyframe*> kfs;
@@ -80,7 +82,7 @@ struct lvreg_handle {
     uint32_t n_scan[2] = {0, 0};
     // scratch
     DevBuf stage[2], raw[2], concat, keys[2], vals[2], sort_scratch, scan_temp, scan_in, vox_start, vox_keys;
-    DevBuf segs, small, partials, regout, lmstate, posebuf, tilectr, qbuf, idxbuf, d2buf, brute_partial, coeffbuf, flagbuf;
+    DevBuf segs, small, partials, regout, lmstate, posebuf, tilectr, tilens, qbuf, idxbuf, d2buf, brute_partial, coeffbuf, flagbuf;
     void* pinned = nullptr;       // 64 KB page-locked scratch for small transfers
     cudaEvent_t ev[EV_COUNT];
     bool ev_set[EV_COUNT];
@@ -237,7 +239,7 @@ int ensure_sort_buffers(lvreg_handle* h, uint32_t n) {
         CK(h->vals[i].reserve((size_t)n * 4));
     }
     CK(h->sort_scratch.reserve(sort_scratch_words(n) * 4));
-    CK(h->scan_temp.reserve((size_t)(scan_num_tiles(n) + 1) * 4));
+    CK(h->scan_temp.reserve((size_t)(scan_num_tiles(n) + 2) * 4));
     return LVREG_OK;
 }
 
@@ -362,7 +364,7 @@ int build_grid(lvreg_handle* h, MapSide& ms) {
     CK(h->scan_in.reserve((size_t)(ncells + 1) * 4));
     CK(ms.cell_start.reserve((size_t)(ncells + 1) * 4));
     CK(ms.cell_pts.reserve((size_t)m * 16));
-    CK(h->scan_temp.reserve((size_t)(scan_num_tiles(ncells + 1) + 1) * 4));
+    CK(h->scan_temp.reserve((size_t)(scan_num_tiles(ncells + 1) + 2) * 4));
     CK(cudaMemsetAsync(h->scan_in.p, 0, (size_t)(ncells + 1) * 4, h->st));
     cell_keys_kernel<<<nblk(m, 256), 256, 0, h->st>>>(ms.ds.as<float4>(), m, gs, h->keys[0].as<uint32_t>(),
                                                       h->vals[0].as<uint32_t>(), h->scan_in.as<uint32_t>());
@@ -593,6 +595,13 @@ int scan2map_impl(lvreg_handle* h, float pose[6], lvreg_result* res) {
 
     CK(cudaMemsetAsync(h->tilectr.p, 0, LVREG_MAX_ITERS * sizeof(uint32_t), h->st));
     args.tile_counter = h->tilectr.as<uint32_t>();
+    args.tile_ns = nullptr;
+    if (h->debug_tiles) {
+        CK(h->tilens.reserve((size_t)(tiles + 1) * 4));
+        CK(cudaMemsetAsync(h->tilens.p, 0, (size_t)(tiles + 1) * 4, h->st));
+        args.tile_ns = h->tilens.as<uint32_t>();
+        h->debug_ntiles = tiles;
+    }
     if (tpq) {
         void* kargs[] = {&args};
         CK(cudaLaunchCooperativeKernel((void*)register_tpq_kernel, dim3(grid), dim3(kRegThreads), kargs, 0, h->st));
@@ -719,11 +728,15 @@ int lvreg_create(const lvreg_params* p, int device, void* cuda_stream, lvreg_han
         return bail(LVREG_ERR_CUDA);
     cudaMemsetAsync(h->lmstate.p, 0, sizeof(LmState), h->st);
     cudaMemsetAsync(h->small.p, 0, SM_WORDS * 4, h->st);
+    // the sort pass keeps 42 KB of staging per block: ask for the large shared-memory carveout
+    cudaFuncSetAttribute(rs_onesweep_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     const char* e = getenv("LVREG_LPQ");
     if (e) {
         int v = atoi(e);
         if (v == 4 || v == 8 || v == 16 || v == 32) h->lpq = v;
     }
+    e = getenv("LVREG_DEBUG_TILES");
+    if (e) h->debug_tiles = atoi(e);
     e = getenv("LVREG_TPQ");
     if (e) h->force_tpq = atoi(e) ? 1 : 0;
     e = getenv("LVREG_TILE");
@@ -751,7 +764,7 @@ void lvreg_destroy(lvreg_handle* h) {
         h->keys[s].release(); h->vals[s].release();
     }
     DevBuf* bufs[] = {&h->concat, &h->sort_scratch, &h->scan_temp, &h->scan_in, &h->vox_start, &h->vox_keys,
-                      &h->segs, &h->small, &h->partials, &h->regout, &h->lmstate, &h->posebuf, &h->tilectr, &h->qbuf,
+                      &h->segs, &h->small, &h->partials, &h->regout, &h->lmstate, &h->posebuf, &h->tilectr, &h->tilens, &h->qbuf,
                       &h->idxbuf, &h->d2buf, &h->brute_partial, &h->coeffbuf, &h->flagbuf};
     for (DevBuf* b : bufs) b->release();
     if (h->pinned) cudaFreeHost(h->pinned);
@@ -1254,6 +1267,17 @@ int lvreg_get_iteration_profile(const lvreg_handle* h, float* us, int* iteration
         for (int k = 0; k < 4; ++k)
             us[i * 4 + k] = (float)((double)(ho->stamp[i][k + 1] - ho->stamp[i][k]) * 1e-3);
     if (iterations) *iterations = n;
+    return LVREG_OK;
+}
+
+int lvreg_debug_tile_times(lvreg_handle* h, uint32_t* ns_out, size_t cap, size_t* n_tiles) {
+    if (!h || !n_tiles) return LVREG_ERR_INVALID;
+    *n_tiles = h->debug_tiles ? h->debug_ntiles : 0;
+    if (!ns_out || !*n_tiles) return LVREG_OK;
+    CK(cudaSetDevice(h->device));
+    size_t n = *n_tiles < cap ? *n_tiles : cap;
+    CK(cudaMemcpyAsync(ns_out, h->tilens.p, n * 4, cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
     return LVREG_OK;
 }
 

@@ -46,15 +46,25 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* t
     return res;
 }
 
+// Reduce-then-scan in three launches (tile sums, one-block scan of the sums, apply).  A single-pass
+// look-back scan was measured SLOWER here: the tiles are short, so the look-back latency of the
+// ~1000 tiles in flight dominates.  Loads are 2 x 128-bit per thread where the functor allows.
 template <class In>
 __global__ void __launch_bounds__(kScanThreads) scan_tile_sums_kernel(In in, uint32_t n,
                                                                       uint32_t* tile_sums) {
     const uint32_t base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
     uint32_t s = 0;
+    if (base + kScanItems <= n) {
+        uint32_t v[kScanItems];
+        in.load_vec(base, v);
 #pragma unroll
-    for (int k = 0; k < kScanItems; ++k) {
-        uint32_t i = base + k;
-        if (i < n) s += in(i);
+        for (int k = 0; k < kScanItems; ++k) s += v[k];
+    } else {
+#pragma unroll
+        for (int k = 0; k < kScanItems; ++k) {
+            uint32_t i = base + k;
+            if (i < n) s += in(i);
+        }
     }
     uint32_t total;
     block_exclusive_scan(s, &total);
@@ -98,19 +108,30 @@ __global__ void __launch_bounds__(kScanThreads) scan_tile_apply_kernel(In in, ui
     const uint32_t base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
     uint32_t v[kScanItems];
     uint32_t s = 0;
+    const bool full = base + kScanItems <= n;
+    if (full) {
+        in.load_vec(base, v);
 #pragma unroll
-    for (int k = 0; k < kScanItems; ++k) {
-        uint32_t i = base + k;
-        v[k] = i < n ? in(i) : 0;
-        s += v[k];
+        for (int k = 0; k < kScanItems; ++k) s += v[k];
+    } else {
+#pragma unroll
+        for (int k = 0; k < kScanItems; ++k) {
+            uint32_t i = base + k;
+            v[k] = i < n ? in(i) : 0;
+            s += v[k];
+        }
     }
     uint32_t total;
     uint32_t pre = block_exclusive_scan(s, &total) + tile_offsets[blockIdx.x];
+    if (full) {
+        out.store_vec(base, v, pre);
+    } else {
 #pragma unroll
-    for (int k = 0; k < kScanItems; ++k) {
-        uint32_t i = base + k;
-        if (i < n) out(i, v[k], pre);
-        pre += v[k];
+        for (int k = 0; k < kScanItems; ++k) {
+            uint32_t i = base + k;
+            if (i < n) out(i, v[k], pre);
+            pre += v[k];
+        }
     }
 }
 
@@ -171,7 +192,7 @@ __global__ void __launch_bounds__(256) rs_global_hist_kernel(const uint32_t* __r
     }
 }
 
-__global__ void __launch_bounds__(kSortThreads) rs_onesweep_kernel(
+__global__ void __launch_bounds__(kSortThreads, 4) rs_onesweep_kernel(
     const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
     uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, uint32_t n, int shift,
     const uint32_t* __restrict__ ghist /*256, this pass*/, volatile uint32_t* status /*[tiles][256]*/,
@@ -199,19 +220,18 @@ __global__ void __launch_bounds__(kSortThreads) rs_onesweep_kernel(
         k[r] = valid ? keys_in[i] : 0xffffffffu;     // padding sorts last inside the (final) tile
         v[r] = valid ? vals_in[i] : 0u;
     }
+    // all matches first (independent, pipelined), then the short serial chain of counter updates
+    uint32_t peers[kSortItems];
+#pragma unroll
+    for (int r = 0; r < kSortItems; ++r) peers[r] = __match_any_sync(0xffffffffu, (k[r] >> shift) & 255u);
 #pragma unroll
     for (int r = 0; r < kSortItems; ++r) {
         const uint32_t d = (k[r] >> shift) & 255u;
-        const uint32_t peers = __match_any_sync(0xffffffffu, d);
-        const int leader = __ffs(peers) - 1;
+        const int leader = __ffs(peers[r]) - 1;
         uint32_t old = 0;
-        if (lane == leader) {
-            old = wcnt[warp][d];
-            wcnt[warp][d] = old + __popc(peers);
-        }
+        if (lane == leader) old = atomicAdd(&wcnt[warp][d], (uint32_t)__popc(peers[r]));
         old = __shfl_sync(0xffffffffu, old, leader);
-        rank[r] = (uint16_t)(old + __popc(peers & ((1u << lane) - 1u)));
-        __syncwarp();
+        rank[r] = (uint16_t)(old + __popc(peers[r] & ((1u << lane) - 1u)));
     }
     __syncthreads();
 

@@ -53,6 +53,7 @@ struct RegArgs {
     const float* pose_in;                // transformTobeMapped on entry
     double* partials;                    // [2][gridDim.x][kRegTerms]
     uint32_t* tile_counter;              // [LVREG max iters] zeroed by the host before the launch
+    uint32_t* tile_ns;                   // optional diagnostics: duration of every tile in iteration 1 (ns)
     RegOut* out;
     LmState* lm;
 };
@@ -326,6 +327,7 @@ __global__ void __launch_bounds__(kRegThreads, 2) register_tpq_kernel(RegArgs a)
             if (lane == 0) tile = atomicAdd(a.tile_counter + iter, 1u);
             tile = __shfl_sync(0xffffffffu, tile, 0);
             if (tile >= tiles) break;
+            const unsigned long long tile_t0 = (a.tile_ns && iter == 1) ? gtimer() : 0ull;
             const int cls = tile < tiles_c ? 0 : 1;
             const uint32_t base = (cls == 0 ? tile : tile - tiles_c) * TILE;
             const uint32_t qi = base + lane;
@@ -359,6 +361,7 @@ __global__ void __launch_bounds__(kRegThreads, 2) register_tpq_kernel(RegArgs a)
                 }
             }
             __syncwarp();
+            if (a.tile_ns && iter == 1 && lane == 0) a.tile_ns[tile] = (uint32_t)(gtimer() - tile_t0);
         }
 
         if (lane < kRegTerms) sRed[warp][lane] = acc;

@@ -159,11 +159,26 @@ struct HeadFlagIn {
     __device__ __forceinline__ uint32_t operator()(uint32_t i) const {
         return (i == 0 || keys[i] != keys[i - 1]) ? 1u : 0u;
     }
+    // 8 consecutive flags starting at a multiple of 8 (two 128-bit loads + one scalar)
+    __device__ __forceinline__ void load_vec(uint32_t i, uint32_t (&v)[8]) const {
+        const uint4 a = *reinterpret_cast<const uint4*>(keys + i);
+        const uint4 b = *reinterpret_cast<const uint4*>(keys + i + 4);
+        const uint32_t prev = i ? keys[i - 1] : ~a.x;
+        v[0] = a.x != prev; v[1] = a.y != a.x; v[2] = a.z != a.y; v[3] = a.w != a.z;
+        v[4] = b.x != a.w;  v[5] = b.y != b.x; v[6] = b.z != b.y; v[7] = b.w != b.z;
+    }
 };
 struct VoxelStartOut {
     uint32_t* start;
     __device__ __forceinline__ void operator()(uint32_t i, uint32_t flag, uint32_t pre) const {
         if (flag) start[pre] = i;
+    }
+    __device__ __forceinline__ void store_vec(uint32_t i, const uint32_t (&v)[8], uint32_t pre) const {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if (v[k]) start[pre] = i + k;
+            pre += v[k];
+        }
     }
 };
 
