@@ -62,6 +62,20 @@ struct MapSide {
 
 enum { EV_BEGIN = 0, EV_UPLOAD, EV_MAP, EV_GRID, EV_DS, EV_REG, EV_COUNT };
 
+// Four independent pipelines ("lanes"), each with its own stream and scratch, so that the
+// corner / surf local-map builds and the corner / surf scan down-sampling of one call run
+// concurrently and share their host synchronisation points (2 per call instead of 2 per cloud).
+constexpr int kLanes = 4;
+enum { LANE_MAP_CORNER = 0, LANE_MAP_SURF = 1, LANE_SCAN_CORNER = 2, LANE_SCAN_SURF = 3 };
+
+struct Lane {
+    cudaStream_t st = nullptr;
+    cudaEvent_t ev = nullptr;
+    DevBuf stage, raw, concat, keys[2], vals[2], sort_scratch, scan_temp, scan_in, vox_start, vox_keys, segs, small;
+    uint32_t* pinned = nullptr;             // 64 words of page-locked host memory
+    std::vector<Segment> seg_host;
+};
+
 }  // namespace
 
 struct lvreg_handle {
@@ -69,6 +83,8 @@ struct lvreg_handle {
     int device = 0;
     cudaStream_t st = nullptr;
     bool own_stream = false;
+    cudaEvent_t ev_main = nullptr;
+    Lane lane[kLanes];
     int num_sms = kNumSMs;
     int lpq = 4;
     int tile = 16;
@@ -80,10 +96,9 @@ struct lvreg_handle {
     MapSide map[2];
     DevBuf scan_ds[2];
     uint32_t n_scan[2] = {0, 0};
-    // scratch
-    DevBuf stage[2], raw[2], concat, keys[2], vals[2], sort_scratch, scan_temp, scan_in, vox_start, vox_keys;
-    DevBuf segs, small, partials, regout, lmstate, posebuf, tilectr, tilens, qbuf, idxbuf, d2buf, brute_partial, coeffbuf, flagbuf;
-    void* pinned = nullptr;       // 64 KB page-locked scratch for small transfers
+    // scratch of the main stream
+    DevBuf vgout, partials, regout, lmstate, posebuf, tilectr, tilens, qbuf, idxbuf, d2buf, brute_partial, coeffbuf, flagbuf;
+    void* pinned = nullptr;       // 64 KB page-locked scratch: lanes use [0, 1 KB), RegOut lives at +4 KB
     cudaEvent_t ev[EV_COUNT];
     bool ev_set[EV_COUNT];
     lvreg_timings last{};
@@ -144,6 +159,24 @@ inline void end_call(lvreg_handle* h) {
     h->last.kernel_launches = h->call_launches;
 }
 
+// ---- lanes -------------------------------------------------------------------------------------
+inline void lanes_fork(lvreg_handle* h, unsigned mask) {          // lane streams wait for the main stream
+    cudaEventRecord(h->ev_main, h->st);
+    for (int l = 0; l < kLanes; ++l)
+        if (mask & (1u << l)) cudaStreamWaitEvent(h->lane[l].st, h->ev_main, 0);
+}
+inline void lanes_join(lvreg_handle* h, unsigned mask) {          // main stream waits for the lanes
+    for (int l = 0; l < kLanes; ++l)
+        if (mask & (1u << l)) {
+            cudaEventRecord(h->lane[l].ev, h->lane[l].st);
+            cudaStreamWaitEvent(h->st, h->lane[l].ev, 0);
+        }
+}
+inline cudaError_t lanes_sync(lvreg_handle* h, unsigned mask) {   // ONE host wait for all lanes in mask
+    lanes_join(h, mask);
+    return cudaStreamSynchronize(h->st);
+}
+
 // ---- cloud transfer ----------------------------------------------------------------------------
 int check_cloud(lvreg_handle* h, const lvreg_cloud* c) {
     if (!c) return fail(h, LVREG_ERR_INVALID, "null cloud");
@@ -154,8 +187,8 @@ int check_cloud(lvreg_handle* h, const lvreg_cloud* c) {
     return LVREG_OK;
 }
 
-// any layout (host or device) -> device float4 {x,y,z,intensity}
-int upload_cloud(lvreg_handle* h, const lvreg_cloud* c, DevBuf& dst, int slot) {
+// any layout (host or device) -> device float4 {x,y,z,intensity}, on stream `st`
+int upload_cloud(lvreg_handle* h, const lvreg_cloud* c, DevBuf& dst, DevBuf& stage, cudaStream_t st) {
     CKS(check_cloud(h, c));
     const uint32_t n = (uint32_t)c->n;
     CK(dst.reserve((size_t)(n ? n : 1) * 16));
@@ -163,26 +196,24 @@ int upload_cloud(lvreg_handle* h, const lvreg_cloud* c, DevBuf& dst, int slot) {
     const bool packed = c->stride == 16 && c->intensity_offset == 12;
     if (packed) {
         CK(cudaMemcpyAsync(dst.p, c->data, (size_t)n * 16,
-                           c->on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->st));
+                           c->on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
         return LVREG_OK;
     }
     const uint8_t* src = (const uint8_t*)c->data;
     if (!c->on_device) {
-        CK(h->stage[slot].reserve((size_t)n * c->stride));
-        CK(cudaMemcpyAsync(h->stage[slot].p, c->data, (size_t)n * c->stride, cudaMemcpyHostToDevice, h->st));
-        src = h->stage[slot].as<uint8_t>();
+        CK(stage.reserve((size_t)n * c->stride));
+        CK(cudaMemcpyAsync(stage.p, c->data, (size_t)n * c->stride, cudaMemcpyHostToDevice, st));
+        src = stage.as<uint8_t>();
     }
-    uint32_t stride_flag = c->stride;
-    if (((uintptr_t)src & 15) != 0 && (stride_flag & 15) == 0) {
-        // unaligned device pointer: force the scalar path of pack_kernel
+    if (((uintptr_t)src & 15) != 0 && (c->stride & 15) == 0)
         return fail(h, LVREG_ERR_INVALID, "device clouds must be 16-byte aligned");
-    }
-    pack_kernel<<<nblk(n, 256), 256, 0, h->st>>>(src, n, c->stride, c->intensity_offset, dst.as<float4>());
+    pack_kernel<<<nblk(n, 256), 256, 0, st>>>(src, n, c->stride, c->intensity_offset, dst.as<float4>());
     launched(h);
     CK(cudaGetLastError());
     return LVREG_OK;
 }
 
+// main-stream download (synchronous)
 int download_cloud(lvreg_handle* h, const float4* src, uint32_t n, lvreg_cloud_out* out) {
     if (!out || (!out->data && n)) return fail(h, LVREG_ERR_INVALID, "null output cloud");
     if (out->capacity < n) return fail(h, LVREG_ERR_CAPACITY, "output cloud too small");
@@ -190,6 +221,7 @@ int download_cloud(lvreg_handle* h, const float4* src, uint32_t n, lvreg_cloud_o
         return fail(h, LVREG_ERR_INVALID, "bad output stride / intensity_offset");
     if (n == 0) return LVREG_OK;
     const bool packed = out->stride == 16 && out->intensity_offset == 12;
+    DevBuf& stage = h->lane[LANE_SCAN_CORNER].stage;
     if (packed) {
         CK(cudaMemcpyAsync(out->data, src, (size_t)n * 16,
                            out->on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, h->st));
@@ -198,129 +230,157 @@ int download_cloud(lvreg_handle* h, const float4* src, uint32_t n, lvreg_cloud_o
         unpack_kernel<<<nblk(n, 256), 256, 0, h->st>>>(src, n, out->stride, out->intensity_offset, (uint8_t*)out->data);
         launched(h);
     } else {
-        CK(h->stage[0].reserve((size_t)n * out->stride));
-        CK(cudaMemsetAsync(h->stage[0].p, 0, (size_t)n * out->stride, h->st));
-        unpack_kernel<<<nblk(n, 256), 256, 0, h->st>>>(src, n, out->stride, out->intensity_offset, h->stage[0].as<uint8_t>());
+        CK(stage.reserve((size_t)n * out->stride));
+        CK(cudaMemsetAsync(stage.p, 0, (size_t)n * out->stride, h->st));
+        unpack_kernel<<<nblk(n, 256), 256, 0, h->st>>>(src, n, out->stride, out->intensity_offset, stage.as<uint8_t>());
         launched(h);
-        CK(cudaMemcpyAsync(out->data, h->stage[0].p, (size_t)n * out->stride, cudaMemcpyDeviceToHost, h->st));
+        CK(cudaMemcpyAsync(out->data, stage.p, (size_t)n * out->stride, cudaMemcpyDeviceToHost, h->st));
     }
     CK(cudaStreamSynchronize(h->st));
     return LVREG_OK;
 }
 
-// ---- VoxelGrid driver ------------------------------------------------------------------------------
+// ---- VoxelGrid driver (batched over lanes) -------------------------------------------------------
 int bits_for(uint64_t max_value) {
     int b = 1;
     while (b < 32 && (max_value >> b) != 0) ++b;
     return b;
 }
 
-int reset_minmax(lvreg_handle* h) {
-    uint32_t* mm = h->small.as<uint32_t>() + SM_MM;
-    CK(cudaMemsetAsync(mm, 0xff, 3 * sizeof(uint32_t), h->st));
-    CK(cudaMemsetAsync(mm + 3, 0, 3 * sizeof(uint32_t), h->st));
-    return LVREG_OK;
-}
-
-int read_minmax(lvreg_handle* h, float mn[3], float mx[3]) {
-    uint32_t* host = (uint32_t*)h->pinned;
-    CK(cudaMemcpyAsync(host, h->small.as<uint32_t>() + SM_MM, 6 * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->st));
-    CK(cudaStreamSynchronize(h->st));
-    for (int a = 0; a < 3; ++a) {
-        mn[a] = ordered_to_float(host[a]);
-        mx[a] = ordered_to_float(host[3 + a]);
-    }
-    return LVREG_OK;
-}
-
-int ensure_sort_buffers(lvreg_handle* h, uint32_t n) {
+int ensure_sort_buffers(lvreg_handle* h, Lane& L, uint32_t n) {
     for (int i = 0; i < 2; ++i) {
-        CK(h->keys[i].reserve((size_t)n * 4));
-        CK(h->vals[i].reserve((size_t)n * 4));
+        CK(L.keys[i].reserve((size_t)n * 4));
+        CK(L.vals[i].reserve((size_t)n * 4));
     }
-    CK(h->sort_scratch.reserve(sort_scratch_words(n) * 4));
-    CK(h->scan_temp.reserve((size_t)(scan_num_tiles(n) + 2) * 4));
+    CK(L.sort_scratch.reserve(sort_scratch_words(n) * 4));
+    CK(L.scan_temp.reserve((size_t)(scan_num_tiles(n) + 2) * 4));
     return LVREG_OK;
 }
 
-// pts: device float4[n] (bbox already in h->small when bbox_known).  Writes the filtered cloud to
-// `out`, the count to *n_out.  d_point_keys (optional device, n) gets the per-point voxel idx.
-int voxelgrid_dev(lvreg_handle* h, const float4* pts, uint32_t n, float leaf, bool bbox_known,
-                  DevBuf& out, uint32_t* n_out, bool want_out_keys, uint32_t* d_point_keys,
-                  int* passthrough) {
-    if (passthrough) *passthrough = 0;
-    *n_out = 0;
-    if (n == 0) {
-        CK(out.reserve(16));
-        return LVREG_OK;
-    }
-    if (!(leaf > 0.f)) return fail(h, LVREG_ERR_INVALID, "leaf size must be positive");
-    if (!bbox_known) {
-        CKS(reset_minmax(h));
-        minmax_kernel<<<min(nblk(n, 256), (uint32_t)h->num_sms * 8), 256, 0, h->st>>>(pts, n, h->small.as<uint32_t>() + SM_MM);
+struct VgJob {
+    int lane = 0;
+    const float4* pts = nullptr;       // device input (ignored when from_segments)
+    uint32_t n = 0;
+    bool from_segments = false;        // input = Lane::seg_host, transformed + concatenated into Lane::concat
+    float leaf = 0.f;
+    DevBuf* out = nullptr;
+    uint32_t* n_out = nullptr;
+    bool want_out_keys = false;        // per-voxel idx into Lane::vox_keys
+    uint32_t* d_point_keys = nullptr;  // optional device array (n): per-point idx
+    // results
+    float mn[3] = {0, 0, 0}, mx[3] = {0, 0, 0};   // bbox of the input cloud
+    int passthrough = 0;
+    // internal
+    VoxelSpec vs{};
+    int cur = 0;
+};
+
+// Runs up to kLanes VoxelGrid filters concurrently.  Two host synchronisation points in total
+// (bounding boxes, voxel counts).  On return the centroid kernels are enqueued on the lane
+// streams; the caller joins the lanes before consuming `out` on the main stream.
+int voxelgrid_batch(lvreg_handle* h, VgJob* jobs, int nj) {
+    unsigned mask = 0;
+    for (int j = 0; j < nj; ++j) mask |= 1u << jobs[j].lane;
+    // ---- phase 1: (transform + concatenate +) bounding box ----
+    for (int j = 0; j < nj; ++j) {
+        VgJob& J = jobs[j];
+        Lane& L = h->lane[J.lane];
+        *J.n_out = 0;
+        J.passthrough = 0;
+        if (J.n == 0) {
+            CK(J.out->reserve(16));
+            continue;
+        }
+        if (!(J.leaf > 0.f)) return fail(h, LVREG_ERR_INVALID, "leaf size must be positive");
+        uint32_t* mm = L.small.as<uint32_t>() + SM_MM;
+        CK(cudaMemsetAsync(mm, 0xff, 3 * sizeof(uint32_t), L.st));
+        CK(cudaMemsetAsync(mm + 3, 0, 3 * sizeof(uint32_t), L.st));
+        if (J.from_segments) {
+            CK(L.segs.reserve(L.seg_host.size() * sizeof(Segment)));
+            CK(cudaMemcpyAsync(L.segs.p, L.seg_host.data(), L.seg_host.size() * sizeof(Segment), cudaMemcpyHostToDevice, L.st));
+            CK(L.concat.reserve((size_t)J.n * 16));
+            transform_concat_kernel<<<min(nblk(J.n, 256), (uint32_t)h->num_sms * 16), 256, 0, L.st>>>(
+                L.segs.as<Segment>(), (uint32_t)L.seg_host.size(), J.n, L.concat.as<float4>(), mm);
+            J.pts = L.concat.as<float4>();
+        } else {
+            minmax_kernel<<<min(nblk(J.n, 256), (uint32_t)h->num_sms * 8), 256, 0, L.st>>>(J.pts, J.n, mm);
+        }
         launched(h);
+        CK(cudaMemcpyAsync(L.pinned, mm, 6 * sizeof(uint32_t), cudaMemcpyDeviceToHost, L.st));
     }
-    float mn[3], mx[3];
-    CKS(read_minmax(h, mn, mx));
-    // PCL voxel_grid.hpp: leaf-size overflow rule and bounds, fp32 exactly as PCL computes them
-    const float inv = 1.0f / leaf;
-    int64_t d[3];
-    for (int a = 0; a < 3; ++a) d[a] = (int64_t)((mx[a] - mn[a]) * inv) + 1;
-    if (d[0] * d[1] * d[2] > (int64_t)INT32_MAX) {
-        CK(out.reserve((size_t)n * 16));
-        CK(cudaMemcpyAsync(out.p, pts, (size_t)n * 16, cudaMemcpyDeviceToDevice, h->st));
-        if (d_point_keys) CK(cudaMemsetAsync(d_point_keys, 0, (size_t)n * 4, h->st));
-        *n_out = n;
-        if (passthrough) *passthrough = 1;
-        return LVREG_OK;
+    CK(lanes_sync(h, mask));
+    // ---- phase 2: keys, stable sort, run heads ----
+    for (int j = 0; j < nj; ++j) {
+        VgJob& J = jobs[j];
+        if (J.n == 0) continue;
+        Lane& L = h->lane[J.lane];
+        for (int a = 0; a < 3; ++a) {
+            J.mn[a] = ordered_to_float(L.pinned[a]);
+            J.mx[a] = ordered_to_float(L.pinned[3 + a]);
+        }
+        // PCL voxel_grid.hpp: leaf-size overflow rule and bounds, fp32 exactly as PCL computes them
+        const float inv = 1.0f / J.leaf;
+        int64_t d[3];
+        for (int a = 0; a < 3; ++a) d[a] = (int64_t)((J.mx[a] - J.mn[a]) * inv) + 1;
+        if (d[0] * d[1] * d[2] > (int64_t)INT32_MAX) {
+            CK(J.out->reserve((size_t)J.n * 16));
+            CK(cudaMemcpyAsync(J.out->p, J.pts, (size_t)J.n * 16, cudaMemcpyDeviceToDevice, L.st));
+            if (J.d_point_keys) CK(cudaMemsetAsync(J.d_point_keys, 0, (size_t)J.n * 4, L.st));
+            *J.n_out = J.n;
+            J.passthrough = 1;
+            continue;
+        }
+        VoxelSpec& vs = J.vs;
+        vs.inv = inv;
+        int div_b[3];
+        for (int a = 0; a < 3; ++a) {
+            vs.min_b[a] = (int)floorf(J.mn[a] * inv);
+            int max_b = (int)floorf(J.mx[a] * inv);
+            div_b[a] = max_b - vs.min_b[a] + 1;
+        }
+        vs.mul[0] = 1;
+        vs.mul[1] = div_b[0];
+        vs.mul[2] = div_b[0] * div_b[1];
+        vs.key_bits = bits_for((uint64_t)div_b[0] * div_b[1] * div_b[2] - 1);
+        CKS(ensure_sort_buffers(h, L, J.n));
+        voxel_keys_kernel<<<nblk(J.n, 256), 256, 0, L.st>>>(J.pts, J.n, vs, L.keys[0].as<uint32_t>(), L.vals[0].as<uint32_t>());
+        launched(h);
+        if (J.d_point_keys)
+            CK(cudaMemcpyAsync(J.d_point_keys, L.keys[0].p, (size_t)J.n * 4, cudaMemcpyDeviceToDevice, L.st));
+        J.cur = radix_sort_pairs(L.keys[0].as<uint32_t>(), L.vals[0].as<uint32_t>(), L.keys[1].as<uint32_t>(),
+                                 L.vals[1].as<uint32_t>(), J.n, vs.key_bits, L.sort_scratch.as<uint32_t>(), L.st,
+                                 &h->call_launches);
+        CK(L.vox_start.reserve((size_t)J.n * 4));
+        uint32_t* d_nvox = L.small.as<uint32_t>() + SM_NVOX;
+        exclusive_scan(HeadFlagIn{L.keys[J.cur].as<uint32_t>()}, VoxelStartOut{L.vox_start.as<uint32_t>()}, J.n,
+                       L.scan_temp.as<uint32_t>(), d_nvox, L.st, &h->call_launches);
+        CK(cudaMemcpyAsync(L.pinned + 8, d_nvox, 4, cudaMemcpyDeviceToHost, L.st));
     }
-    VoxelSpec vs;
-    vs.inv = inv;
-    int div_b[3];
-    for (int a = 0; a < 3; ++a) {
-        vs.min_b[a] = (int)floorf(mn[a] * inv);
-        int max_b = (int)floorf(mx[a] * inv);
-        div_b[a] = max_b - vs.min_b[a] + 1;
+    CK(lanes_sync(h, mask));
+    // ---- phase 3: centroids (left running on the lane streams) ----
+    for (int j = 0; j < nj; ++j) {
+        VgJob& J = jobs[j];
+        if (J.n == 0 || J.passthrough) continue;
+        Lane& L = h->lane[J.lane];
+        const uint32_t nvox = L.pinned[8];
+        CK(J.out->reserve((size_t)(nvox ? nvox : 1) * 16));
+        uint32_t* okeys = nullptr;
+        if (J.want_out_keys) {
+            CK(L.vox_keys.reserve((size_t)(nvox ? nvox : 1) * 4));
+            okeys = L.vox_keys.as<uint32_t>();
+        }
+        centroid_kernel<<<nblk(nvox, 128), 128, 0, L.st>>>(J.pts, L.keys[J.cur].as<uint32_t>(), L.vals[J.cur].as<uint32_t>(),
+                                                           L.vox_start.as<uint32_t>(), L.small.as<uint32_t>() + SM_NVOX,
+                                                           J.n, J.out->as<float4>(), okeys);
+        launched(h);
+        *J.n_out = nvox;
     }
-    vs.mul[0] = 1;
-    vs.mul[1] = div_b[0];
-    vs.mul[2] = div_b[0] * div_b[1];
-    vs.key_bits = bits_for((uint64_t)div_b[0] * div_b[1] * div_b[2] - 1);
-
-    CKS(ensure_sort_buffers(h, n));
-    voxel_keys_kernel<<<nblk(n, 256), 256, 0, h->st>>>(pts, n, vs, h->keys[0].as<uint32_t>(), h->vals[0].as<uint32_t>());
-    launched(h);
-    if (d_point_keys)
-        CK(cudaMemcpyAsync(d_point_keys, h->keys[0].p, (size_t)n * 4, cudaMemcpyDeviceToDevice, h->st));
-    int cur = radix_sort_pairs(h->keys[0].as<uint32_t>(), h->vals[0].as<uint32_t>(), h->keys[1].as<uint32_t>(),
-                               h->vals[1].as<uint32_t>(), n, vs.key_bits, h->sort_scratch.as<uint32_t>(), h->st,
-                               &h->call_launches);
-    const uint32_t* skeys = h->keys[cur].as<uint32_t>();
-    const uint32_t* svals = h->vals[cur].as<uint32_t>();
-    CK(h->vox_start.reserve((size_t)n * 4));
-    uint32_t* d_nvox = h->small.as<uint32_t>() + SM_NVOX;
-    exclusive_scan(HeadFlagIn{skeys}, VoxelStartOut{h->vox_start.as<uint32_t>()}, n, h->scan_temp.as<uint32_t>(),
-                   d_nvox, h->st, &h->call_launches);
-    uint32_t* host = (uint32_t*)h->pinned;
-    CK(cudaMemcpyAsync(host, d_nvox, 4, cudaMemcpyDeviceToHost, h->st));
-    CK(cudaStreamSynchronize(h->st));
-    const uint32_t nvox = host[0];
-    CK(out.reserve((size_t)nvox * 16));
-    uint32_t* okeys = nullptr;
-    if (want_out_keys) {
-        CK(h->vox_keys.reserve((size_t)nvox * 4));
-        okeys = h->vox_keys.as<uint32_t>();
-    }
-    centroid_kernel<<<nblk(nvox, 128), 128, 0, h->st>>>(pts, skeys, svals, h->vox_start.as<uint32_t>(), d_nvox, n,
-                                                        out.as<float4>(), okeys);
-    launched(h);
     CK(cudaGetLastError());
-    *n_out = nvox;
     return LVREG_OK;
 }
 
-// ---- search-grid build -----------------------------------------------------------------------------
-int build_grid(lvreg_handle* h, MapSide& ms) {
+// ---- search-grid build (on a lane stream; no host synchronisation when the bbox is known) --------
+int build_grid(lvreg_handle* h, Lane& L, MapSide& ms, const float* bb_min, const float* bb_max) {
     const uint32_t m = ms.m;
     GridSpec gs;
     const float gate_r = sqrtf(h->prm.knn_gate_sq);
@@ -331,16 +391,29 @@ int build_grid(lvreg_handle* h, MapSide& ms) {
         gs.inv = 1.0f / cell;
         gs.dx = gs.dy = gs.dz = 1;
         CK(ms.cell_start.reserve(2 * 4));
-        CK(cudaMemsetAsync(ms.cell_start.p, 0, 8, h->st));
+        CK(cudaMemsetAsync(ms.cell_start.p, 0, 8, L.st));
         CK(ms.cell_pts.reserve(16));
         ms.gs = gs;
         return LVREG_OK;
     }
-    CKS(reset_minmax(h));
-    minmax_kernel<<<min(nblk(m, 256), (uint32_t)h->num_sms * 8), 256, 0, h->st>>>(ms.ds.as<float4>(), m, h->small.as<uint32_t>() + SM_MM);
-    launched(h);
     float mn[3], mx[3];
-    CKS(read_minmax(h, mn, mx));
+    if (bb_min && bb_max) {
+        // bounding box of the cloud the map was down-sampled from: every centroid lies inside it
+        // (cell coordinates are clamped, so a last-bit excursion is harmless)
+        for (int a = 0; a < 3; ++a) { mn[a] = bb_min[a]; mx[a] = bb_max[a]; }
+    } else {
+        uint32_t* mm = L.small.as<uint32_t>() + SM_MM;
+        CK(cudaMemsetAsync(mm, 0xff, 3 * sizeof(uint32_t), L.st));
+        CK(cudaMemsetAsync(mm + 3, 0, 3 * sizeof(uint32_t), L.st));
+        minmax_kernel<<<min(nblk(m, 256), (uint32_t)h->num_sms * 8), 256, 0, L.st>>>(ms.ds.as<float4>(), m, mm);
+        launched(h);
+        CK(cudaMemcpyAsync(L.pinned, mm, 6 * sizeof(uint32_t), cudaMemcpyDeviceToHost, L.st));
+        CK(cudaStreamSynchronize(L.st));
+        for (int a = 0; a < 3; ++a) {
+            mn[a] = ordered_to_float(L.pinned[a]);
+            mx[a] = ordered_to_float(L.pinned[3 + a]);
+        }
+    }
     for (;;) {
         const float inv = 1.0f / cell;
         int64_t dims[3];
@@ -360,22 +433,22 @@ int build_grid(lvreg_handle* h, MapSide& ms) {
         if (!(cell < 1e30f)) return fail(h, LVREG_ERR_INVALID, "map extent is not finite");
     }
     const uint32_t ncells = (uint32_t)gs.dx * gs.dy * gs.dz;
-    CKS(ensure_sort_buffers(h, m));
-    CK(h->scan_in.reserve((size_t)(ncells + 1) * 4));
-    CK(ms.cell_start.reserve((size_t)(ncells + 1) * 4));
+    CKS(ensure_sort_buffers(h, L, m));
+    CK(L.scan_in.reserve((size_t)(ncells + 9) * 4));
+    CK(ms.cell_start.reserve((size_t)(ncells + 9) * 4));
     CK(ms.cell_pts.reserve((size_t)m * 16));
-    CK(h->scan_temp.reserve((size_t)(scan_num_tiles(ncells + 1) + 2) * 4));
-    CK(cudaMemsetAsync(h->scan_in.p, 0, (size_t)(ncells + 1) * 4, h->st));
-    cell_keys_kernel<<<nblk(m, 256), 256, 0, h->st>>>(ms.ds.as<float4>(), m, gs, h->keys[0].as<uint32_t>(),
-                                                      h->vals[0].as<uint32_t>(), h->scan_in.as<uint32_t>());
+    CK(L.scan_temp.reserve((size_t)(scan_num_tiles(ncells + 1) + 2) * 4));
+    CK(cudaMemsetAsync(L.scan_in.p, 0, (size_t)(ncells + 1) * 4, L.st));
+    cell_keys_kernel<<<nblk(m, 256), 256, 0, L.st>>>(ms.ds.as<float4>(), m, gs, L.keys[0].as<uint32_t>(),
+                                                     L.vals[0].as<uint32_t>(), L.scan_in.as<uint32_t>());
     launched(h);
-    exclusive_scan(CountIn{h->scan_in.as<uint32_t>()}, StartOut{ms.cell_start.as<uint32_t>()}, ncells + 1,
-                   h->scan_temp.as<uint32_t>(), h->small.as<uint32_t>() + SM_TOTAL, h->st, &h->call_launches);
-    int cur = radix_sort_pairs(h->keys[0].as<uint32_t>(), h->vals[0].as<uint32_t>(), h->keys[1].as<uint32_t>(),
-                               h->vals[1].as<uint32_t>(), m, bits_for(ncells - 1), h->sort_scratch.as<uint32_t>(),
-                               h->st, &h->call_launches);
-    cell_gather_kernel<<<nblk(m, 256), 256, 0, h->st>>>(ms.ds.as<float4>(), h->vals[cur].as<uint32_t>(), m,
-                                                        ms.cell_pts.as<float4>());
+    exclusive_scan(CountIn{L.scan_in.as<uint32_t>()}, StartOut{ms.cell_start.as<uint32_t>()}, ncells + 1,
+                   L.scan_temp.as<uint32_t>(), L.small.as<uint32_t>() + SM_TOTAL, L.st, &h->call_launches);
+    int cur = radix_sort_pairs(L.keys[0].as<uint32_t>(), L.vals[0].as<uint32_t>(), L.keys[1].as<uint32_t>(),
+                               L.vals[1].as<uint32_t>(), m, bits_for(ncells - 1), L.sort_scratch.as<uint32_t>(),
+                               L.st, &h->call_launches);
+    cell_gather_kernel<<<nblk(m, 256), 256, 0, L.st>>>(ms.ds.as<float4>(), L.vals[cur].as<uint32_t>(), m,
+                                                       ms.cell_pts.as<float4>());
     launched(h);
     CK(cudaGetLastError());
     ms.gs = gs;
@@ -435,65 +508,67 @@ void pose_to_affine_host(const float pose[6], float T[12]) {
     T[8] = -D;     T[9] = C * F;           T[10] = C * E;           T[11] = pose[5];
 }
 
-int build_local_map_impl(lvreg_handle* h, const int32_t* ids, size_t n_ids) {
+// fills the two local-map jobs (lanes 0/1) from the keyframe id list (extractCloud MO:931-957)
+int prepare_map_jobs(lvreg_handle* h, const int32_t* ids, size_t n_ids, VgJob* jobs) {
     if (h->kfs.empty()) return fail(h, LVREG_ERR_NO_KEYFRAMES, "no keyframes");
     for (size_t i = 0; i < n_ids; ++i)
         if (ids[i] < 0 || (size_t)ids[i] >= h->kfs.size()) return fail(h, LVREG_ERR_INVALID, "keyframe id out of range");
-    std::vector<Segment> segs(n_ids ? n_ids : 1);
     for (int s = 0; s < 2; ++s) {
+        Lane& L = h->lane[s];
         MapSide& ms = h->map[s];
+        L.seg_host.clear();
         uint64_t total = 0;
         for (size_t i = 0; i < n_ids; ++i) {
             const Keyframe* kf = h->kfs[ids[i]];
-            segs[i].src = kf->cloud[s].as<float4>();
-            segs[i].begin = (uint32_t)total;
-            segs[i].n = kf->n[s];
-            pose_to_affine_host(kf->pose, segs[i].T.m);
+            if (kf->n[s] == 0) continue;          // empty clouds contribute nothing
+            Segment sg;
+            sg.src = kf->cloud[s].as<float4>();
+            sg.begin = (uint32_t)total;
+            sg.n = kf->n[s];
+            pose_to_affine_host(kf->pose, sg.T.m);        // pclPointToAffine3f(cloudKeyPoses6D[id])
+            L.seg_host.push_back(sg);
             total += kf->n[s];
         }
         if (total > 0x7fffffffull) return fail(h, LVREG_ERR_INVALID, "local map too large");
         ms.n_in = total;
-        uint32_t m = 0;
-        if (total > 0) {
-            // drop empty segments so that the binary search over `begin` is well defined
-            std::vector<Segment> live;
-            live.reserve(n_ids);
-            for (size_t i = 0; i < n_ids; ++i)
-                if (segs[i].n) live.push_back(segs[i]);
-            CK(h->segs.reserve(live.size() * sizeof(Segment)));
-            CK(cudaMemcpyAsync(h->segs.p, live.data(), live.size() * sizeof(Segment), cudaMemcpyHostToDevice, h->st));
-            CK(h->concat.reserve((size_t)total * 16));
-            CKS(reset_minmax(h));
-            transform_concat_kernel<<<min(nblk((uint32_t)total, 256), (uint32_t)h->num_sms * 16), 256, 0, h->st>>>(
-                h->segs.as<Segment>(), (uint32_t)live.size(), (uint32_t)total, h->concat.as<float4>(),
-                h->small.as<uint32_t>() + SM_MM);
-            launched(h);
-            CK(cudaStreamSynchronize(h->st));    // `live` must outlive the async copy
-            CKS(voxelgrid_dev(h, h->concat.as<float4>(), (uint32_t)total, s == 0 ? h->prm.corner_leaf : h->prm.surf_leaf,
-                              true, ms.ds, &m, false, nullptr, nullptr));
-        } else {
-            CK(ms.ds.reserve(16));
-        }
-        ms.m = m;
+        ms.valid = false;
+        VgJob& J = jobs[s];
+        J = VgJob();
+        J.lane = s;
+        J.n = (uint32_t)total;
+        J.from_segments = true;
+        J.leaf = s == 0 ? h->prm.corner_leaf : h->prm.surf_leaf;
+        J.out = &ms.ds;
+        J.n_out = &ms.m;
     }
-    mark(h, EV_MAP);
-    for (int s = 0; s < 2; ++s) {
-        CKS(build_grid(h, h->map[s]));
-        h->map[s].valid = true;
-    }
-    mark(h, EV_GRID);
     return LVREG_OK;
 }
 
-int downsample_impl(lvreg_handle* h, const lvreg_cloud* corner_raw, const lvreg_cloud* surf_raw) {
-    CKS(upload_cloud(h, corner_raw, h->raw[0], 0));
-    CKS(upload_cloud(h, surf_raw, h->raw[1], 1));
-    mark(h, EV_UPLOAD);
-    CKS(voxelgrid_dev(h, h->raw[0].as<float4>(), (uint32_t)corner_raw->n, h->prm.corner_leaf, false, h->scan_ds[0],
-                      &h->n_scan[0], false, nullptr, nullptr));
-    CKS(voxelgrid_dev(h, h->raw[1].as<float4>(), (uint32_t)surf_raw->n, h->prm.surf_leaf, false, h->scan_ds[1],
-                      &h->n_scan[1], false, nullptr, nullptr));
-    mark(h, EV_DS);
+// uploads the raw scan clouds on lanes 2/3 and fills their jobs (downsampleCurrentScan MO:987-999)
+int prepare_scan_jobs(lvreg_handle* h, const lvreg_cloud* corner_raw, const lvreg_cloud* surf_raw, VgJob* jobs) {
+    const lvreg_cloud* c[2] = {corner_raw, surf_raw};
+    for (int s = 0; s < 2; ++s) {
+        Lane& L = h->lane[LANE_SCAN_CORNER + s];
+        CKS(upload_cloud(h, c[s], L.raw, L.stage, L.st));
+        VgJob& J = jobs[s];
+        J = VgJob();
+        J.lane = LANE_SCAN_CORNER + s;
+        J.pts = L.raw.as<float4>();
+        J.n = (uint32_t)c[s]->n;
+        J.leaf = s == 0 ? h->prm.corner_leaf : h->prm.surf_leaf;
+        J.out = &h->scan_ds[s];
+        J.n_out = &h->n_scan[s];
+    }
+    return LVREG_OK;
+}
+
+// search grids of both maps on lanes 0/1, from the bounding boxes the VoxelGrid jobs measured
+int build_map_grids(lvreg_handle* h, VgJob* map_jobs) {
+    for (int s = 0; s < 2; ++s) {
+        const bool have_bb = map_jobs && map_jobs[s].n > 0;
+        CKS(build_grid(h, h->lane[s], h->map[s], have_bb ? map_jobs[s].mn : nullptr, have_bb ? map_jobs[s].mx : nullptr));
+        h->map[s].valid = true;
+    }
     return LVREG_OK;
 }
 
@@ -551,7 +626,7 @@ int scan2map_impl(lvreg_handle* h, float pose[6], lvreg_result* res) {
         }
         return fail(h, LVREG_ERR_NOT_ENOUGH_FEATURES, "not enough features");
     }
-    float* hp = (float*)h->pinned;
+    float* hp = (float*)((char*)h->pinned + 2048);
     memcpy(hp, pose, 6 * sizeof(float));
     CK(cudaMemcpyAsync(h->posebuf.p, hp, 6 * sizeof(float), cudaMemcpyHostToDevice, h->st));
 
@@ -609,7 +684,7 @@ int scan2map_impl(lvreg_handle* h, float pose[6], lvreg_result* res) {
         LVREG_REG_DISPATCH(launch_register, h, args, grid);
     }
     launched(h);
-    RegOut* ho = (RegOut*)((char*)h->pinned + 256);
+    RegOut* ho = (RegOut*)((char*)h->pinned + 4096);
     CK(cudaMemcpyAsync(ho, h->regout.p, sizeof(RegOut), cudaMemcpyDeviceToHost, h->st));
     mark(h, EV_REG);
     CK(cudaStreamSynchronize(h->st));
@@ -722,12 +797,21 @@ int lvreg_create(const lvreg_params* p, int device, void* cuda_stream, lvreg_han
         h->ev_set[i] = false;
     }
     if (cudaMallocHost(&h->pinned, 65536) != cudaSuccess) return bail(LVREG_ERR_CUDA);
-    if (h->small.reserve(SM_WORDS * 4) != cudaSuccess || h->regout.reserve(sizeof(RegOut)) != cudaSuccess ||
+    if (cudaEventCreateWithFlags(&h->ev_main, cudaEventDisableTiming) != cudaSuccess) return bail(LVREG_ERR_CUDA);
+    for (int l = 0; l < kLanes; ++l) {
+        Lane& L = h->lane[l];
+        if (cudaStreamCreateWithFlags(&L.st, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&L.ev, cudaEventDisableTiming) != cudaSuccess ||
+            L.small.reserve(SM_WORDS * 4) != cudaSuccess)
+            return bail(LVREG_ERR_CUDA);
+        L.pinned = (uint32_t*)h->pinned + 64 * l;
+        cudaMemsetAsync(L.small.p, 0, SM_WORDS * 4, h->st);
+    }
+    if (h->regout.reserve(sizeof(RegOut)) != cudaSuccess ||
         h->lmstate.reserve(sizeof(LmState)) != cudaSuccess || h->posebuf.reserve(256) != cudaSuccess ||
         h->tilectr.reserve(LVREG_MAX_ITERS * sizeof(uint32_t)) != cudaSuccess)
         return bail(LVREG_ERR_CUDA);
     cudaMemsetAsync(h->lmstate.p, 0, sizeof(LmState), h->st);
-    cudaMemsetAsync(h->small.p, 0, SM_WORDS * 4, h->st);
     // the sort pass keeps 42 KB of staging per block: ask for the large shared-memory carveout
     cudaFuncSetAttribute(rs_onesweep_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     const char* e = getenv("LVREG_LPQ");
@@ -758,15 +842,23 @@ void lvreg_destroy(lvreg_handle* h) {
         kf->cloud[1].release();
         delete kf;
     }
+    for (int l = 0; l < kLanes; ++l) {
+        Lane& L = h->lane[l];
+        if (L.st) cudaStreamSynchronize(L.st);
+        DevBuf* lb[] = {&L.stage, &L.raw, &L.concat, &L.keys[0], &L.keys[1], &L.vals[0], &L.vals[1], &L.sort_scratch,
+                        &L.scan_temp, &L.scan_in, &L.vox_start, &L.vox_keys, &L.segs, &L.small};
+        for (DevBuf* b : lb) b->release();
+        if (L.ev) cudaEventDestroy(L.ev);
+        if (L.st) cudaStreamDestroy(L.st);
+    }
     for (int s = 0; s < 2; ++s) {
         h->map[s].ds.release(); h->map[s].cell_pts.release(); h->map[s].cell_start.release();
-        h->scan_ds[s].release(); h->stage[s].release(); h->raw[s].release();
-        h->keys[s].release(); h->vals[s].release();
+        h->scan_ds[s].release();
     }
-    DevBuf* bufs[] = {&h->concat, &h->sort_scratch, &h->scan_temp, &h->scan_in, &h->vox_start, &h->vox_keys,
-                      &h->segs, &h->small, &h->partials, &h->regout, &h->lmstate, &h->posebuf, &h->tilectr, &h->tilens, &h->qbuf,
+    DevBuf* bufs[] = {&h->vgout, &h->partials, &h->regout, &h->lmstate, &h->posebuf, &h->tilectr, &h->tilens, &h->qbuf,
                       &h->idxbuf, &h->d2buf, &h->brute_partial, &h->coeffbuf, &h->flagbuf};
     for (DevBuf* b : bufs) b->release();
+    if (h->ev_main) cudaEventDestroy(h->ev_main);
     if (h->pinned) cudaFreeHost(h->pinned);
     for (int i = 0; i < EV_COUNT; ++i)
         if (h->ev[i]) cudaEventDestroy(h->ev[i]);
@@ -781,8 +873,8 @@ int lvreg_add_keyframe(lvreg_handle* h, const lvreg_cloud* corner, const lvreg_c
     CK(cudaSetDevice(h->device));
     begin_call(h);
     Keyframe* kf = new Keyframe();
-    int s0 = upload_cloud(h, corner, kf->cloud[0], 0);
-    int s1 = s0 == LVREG_OK ? upload_cloud(h, surf, kf->cloud[1], 1) : s0;
+    int s0 = upload_cloud(h, corner, kf->cloud[0], h->lane[LANE_SCAN_CORNER].stage, h->st);
+    int s1 = s0 == LVREG_OK ? upload_cloud(h, surf, kf->cloud[1], h->lane[LANE_SCAN_SURF].stage, h->st) : s0;
     if (s1 != LVREG_OK || cudaStreamSynchronize(h->st) != cudaSuccess) {
         kf->cloud[0].release();
         kf->cloud[1].release();
@@ -859,7 +951,15 @@ int lvreg_build_local_map(lvreg_handle* h, const int32_t* ids, size_t n, lvreg_m
     CK(cudaSetDevice(h->device));
     begin_call(h);
     mark(h, EV_BEGIN);
-    CKS(build_local_map_impl(h, ids, n));
+    VgJob jobs[2];
+    CKS(prepare_map_jobs(h, ids, n, jobs));
+    lanes_fork(h, 0x3);
+    CKS(voxelgrid_batch(h, jobs, 2));
+    lanes_join(h, 0x3);
+    mark(h, EV_MAP);
+    CKS(build_map_grids(h, jobs));
+    lanes_join(h, 0x3);
+    mark(h, EV_GRID);
     CK(cudaStreamSynchronize(h->st));
     h->last.map_build_ms = span(h, EV_BEGIN, EV_MAP);
     h->last.grid_build_ms = span(h, EV_MAP, EV_GRID);
@@ -876,16 +976,18 @@ int lvreg_set_local_map(lvreg_handle* h, const lvreg_cloud* corner_ds, const lvr
     begin_call(h);
     mark(h, EV_BEGIN);
     const lvreg_cloud* c[2] = {corner_ds, surf_ds};
+    lanes_fork(h, 0x3);
     for (int s = 0; s < 2; ++s) {
-        CKS(upload_cloud(h, c[s], h->map[s].ds, s));
+        Lane& L = h->lane[s];
+        h->map[s].valid = false;
+        CKS(upload_cloud(h, c[s], h->map[s].ds, L.stage, L.st));
         h->map[s].m = (uint32_t)c[s]->n;
         h->map[s].n_in = c[s]->n;
     }
+    lanes_join(h, 0x3);
     mark(h, EV_MAP);
-    for (int s = 0; s < 2; ++s) {
-        CKS(build_grid(h, h->map[s]));
-        h->map[s].valid = true;
-    }
+    CKS(build_map_grids(h, nullptr));
+    lanes_join(h, 0x3);
     mark(h, EV_GRID);
     CK(cudaStreamSynchronize(h->st));
     h->last.upload_ms = span(h, EV_BEGIN, EV_MAP);
@@ -912,10 +1014,14 @@ int lvreg_downsample_scan(lvreg_handle* h, const lvreg_cloud* corner_raw, const 
     CK(cudaSetDevice(h->device));
     begin_call(h);
     mark(h, EV_BEGIN);
-    CKS(downsample_impl(h, corner_raw, surf_raw));
+    VgJob jobs[2];
+    lanes_fork(h, 0xc);
+    CKS(prepare_scan_jobs(h, corner_raw, surf_raw, jobs));
+    CKS(voxelgrid_batch(h, jobs, 2));
+    lanes_join(h, 0xc);
+    mark(h, EV_DS);
     CK(cudaStreamSynchronize(h->st));
-    h->last.upload_ms = span(h, EV_BEGIN, EV_UPLOAD);
-    h->last.downsample_ms = span(h, EV_UPLOAD, EV_DS);
+    h->last.downsample_ms = span(h, EV_BEGIN, EV_DS);      // includes the H2D + pack of the two clouds
     finish_timings(h);
     end_call(h);
     if (nc) *nc = h->n_scan[0];
@@ -927,8 +1033,8 @@ int lvreg_set_scan_ds(lvreg_handle* h, const lvreg_cloud* corner_ds, const lvreg
     if (!h) return LVREG_ERR_INVALID;
     CK(cudaSetDevice(h->device));
     begin_call(h);
-    CKS(upload_cloud(h, corner_ds, h->scan_ds[0], 0));
-    CKS(upload_cloud(h, surf_ds, h->scan_ds[1], 1));
+    CKS(upload_cloud(h, corner_ds, h->scan_ds[0], h->lane[LANE_SCAN_CORNER].stage, h->st));
+    CKS(upload_cloud(h, surf_ds, h->scan_ds[1], h->lane[LANE_SCAN_SURF].stage, h->st));
     CK(cudaStreamSynchronize(h->st));
     h->n_scan[0] = (uint32_t)corner_ds->n;
     h->n_scan[1] = (uint32_t)surf_ds->n;
@@ -965,19 +1071,35 @@ int lvreg_register_scan(lvreg_handle* h, const lvreg_cloud* corner_raw, const lv
     CK(cudaSetDevice(h->device));
     begin_call(h);
     mark(h, EV_BEGIN);
-    if (ids) CKS(build_local_map_impl(h, ids, n_ids));      // extractSurroundingKeyFrames MO:318
-    CKS(downsample_impl(h, corner_raw, surf_raw));            // downsampleCurrentScan MO:320
+    // extractSurroundingKeyFrames (MO:318) and downsampleCurrentScan (MO:320) are independent: all
+    // four VoxelGrid filters run concurrently on the lanes and share two host synchronisations
+    VgJob jobs[4];
+    int nj = 0;
+    unsigned mask = 0xc;
+    if (ids) {
+        CKS(prepare_map_jobs(h, ids, n_ids, jobs));
+        nj = 2;
+        mask = 0xf;
+    }
+    lanes_fork(h, mask);
+    CKS(prepare_scan_jobs(h, corner_raw, surf_raw, jobs + nj));
+    nj += 2;
+    CKS(voxelgrid_batch(h, jobs, nj));
+    lanes_join(h, mask);
+    mark(h, EV_MAP);
+    if (ids) {
+        CKS(build_map_grids(h, jobs));
+        lanes_join(h, 0x3);
+    }
+    mark(h, EV_GRID);
     int s = scan2map_impl(h, pose, res);                      // scan2MapOptimization MO:322
     if (s == LVREG_OK || s == LVREG_ERR_NOT_ENOUGH_FEATURES) {
         CK(cudaStreamSynchronize(h->st));
-        const int pre = ids ? EV_GRID : EV_BEGIN;
-        if (ids) {
-            h->last.map_build_ms = span(h, EV_BEGIN, EV_MAP);
-            h->last.grid_build_ms = span(h, EV_MAP, EV_GRID);
-        }
-        h->last.upload_ms = span(h, pre, EV_UPLOAD);
-        h->last.downsample_ms = span(h, EV_UPLOAD, EV_DS);
-        h->last.register_ms = span(h, EV_DS, EV_REG);
+        // the four filters overlap, so they are reported together: map_build_ms covers H2D + pack +
+        // local-map VoxelGrid + scan down-sampling; downsample_ms stays 0 in this fused call
+        h->last.map_build_ms = span(h, EV_BEGIN, EV_MAP);
+        h->last.grid_build_ms = span(h, EV_MAP, EV_GRID);
+        h->last.register_ms = span(h, EV_GRID, EV_REG);
         finish_timings(h);
     }
     end_call(h);
@@ -1029,16 +1151,17 @@ int lvreg_transform_cloud(lvreg_handle* h, const lvreg_cloud* in, const float po
     if (!h || !in || !pose || !out) return LVREG_ERR_INVALID;
     CK(cudaSetDevice(h->device));
     begin_call(h);
-    CKS(upload_cloud(h, in, h->raw[0], 0));
+    Lane& L = h->lane[LANE_SCAN_CORNER];
+    CKS(upload_cloud(h, in, L.raw, L.stage, h->st));
     const uint32_t n = (uint32_t)in->n;
-    CK(h->concat.reserve((size_t)(n ? n : 1) * 16));
+    CK(h->vgout.reserve((size_t)(n ? n : 1) * 16));
     Affine T;
     pose_to_affine_host(pose, T.m);
     if (n) {
-        transform_kernel<<<nblk(n, 256), 256, 0, h->st>>>(h->raw[0].as<float4>(), n, T, h->concat.as<float4>());
+        transform_kernel<<<nblk(n, 256), 256, 0, h->st>>>(L.raw.as<float4>(), n, T, h->vgout.as<float4>());
         launched(h);
     }
-    int s = download_cloud(h, h->concat.as<float4>(), n, out);
+    int s = download_cloud(h, h->vgout.as<float4>(), n, out);
     end_call(h);
     return s;
 }
@@ -1049,24 +1172,31 @@ int lvreg_voxelgrid(lvreg_handle* h, const lvreg_cloud* in, float leaf, lvreg_cl
     CK(cudaSetDevice(h->device));
     begin_call(h);
     mark(h, EV_BEGIN);
-    CKS(upload_cloud(h, in, h->raw[0], 0));
-    mark(h, EV_UPLOAD);
+    Lane& L = h->lane[LANE_SCAN_CORNER];
+    lanes_fork(h, 0x4);
+    CKS(upload_cloud(h, in, L.raw, L.stage, L.st));
     uint32_t m = 0;
-    int pt = 0;
-    CKS(voxelgrid_dev(h, h->raw[0].as<float4>(), (uint32_t)in->n, leaf, false, h->concat, &m,
-                      voxel_keys_out != nullptr, nullptr, &pt));
+    VgJob J;
+    J.lane = LANE_SCAN_CORNER;
+    J.pts = L.raw.as<float4>();
+    J.n = (uint32_t)in->n;
+    J.leaf = leaf;
+    J.out = &h->vgout;
+    J.n_out = &m;
+    J.want_out_keys = voxel_keys_out != nullptr;
+    CKS(voxelgrid_batch(h, &J, 1));
+    lanes_join(h, 0x4);
     mark(h, EV_DS);
-    if (passthrough) *passthrough = pt;
+    if (passthrough) *passthrough = J.passthrough;
     if (n_out) *n_out = m;
-    if (voxel_keys_out && m && !pt) {
-        CK(cudaMemcpyAsync(voxel_keys_out, h->vox_keys.p, (size_t)m * 4, cudaMemcpyDeviceToHost, h->st));
+    if (voxel_keys_out && m && !J.passthrough) {
+        CK(cudaMemcpyAsync(voxel_keys_out, L.vox_keys.p, (size_t)m * 4, cudaMemcpyDeviceToHost, h->st));
     } else if (voxel_keys_out && m) {
         memset(voxel_keys_out, 0, (size_t)m * 4);
     }
-    int s = download_cloud(h, h->concat.as<float4>(), m, out);
+    int s = download_cloud(h, h->vgout.as<float4>(), m, out);
     CK(cudaStreamSynchronize(h->st));
-    h->last.upload_ms = span(h, EV_BEGIN, EV_UPLOAD);
-    h->last.downsample_ms = span(h, EV_UPLOAD, EV_DS);
+    h->last.downsample_ms = span(h, EV_BEGIN, EV_DS);
     finish_timings(h);
     end_call(h);
     return s;
@@ -1076,12 +1206,23 @@ int lvreg_voxel_keys(lvreg_handle* h, const lvreg_cloud* in, float leaf, uint32_
     if (!h || !in || (!keys_out && in->n)) return LVREG_ERR_INVALID;
     CK(cudaSetDevice(h->device));
     begin_call(h);
-    CKS(upload_cloud(h, in, h->raw[0], 0));
+    Lane& L = h->lane[LANE_SCAN_CORNER];
     const uint32_t n = (uint32_t)in->n;
     if (n == 0) return LVREG_OK;
     CK(h->idxbuf.reserve((size_t)n * 4));
+    lanes_fork(h, 0x4);
+    CKS(upload_cloud(h, in, L.raw, L.stage, L.st));
     uint32_t m = 0;
-    CKS(voxelgrid_dev(h, h->raw[0].as<float4>(), n, leaf, false, h->concat, &m, false, h->idxbuf.as<uint32_t>(), nullptr));
+    VgJob J;
+    J.lane = LANE_SCAN_CORNER;
+    J.pts = L.raw.as<float4>();
+    J.n = n;
+    J.leaf = leaf;
+    J.out = &h->vgout;
+    J.n_out = &m;
+    J.d_point_keys = h->idxbuf.as<uint32_t>();
+    CKS(voxelgrid_batch(h, &J, 1));
+    lanes_join(h, 0x4);
     CK(cudaMemcpyAsync(keys_out, h->idxbuf.p, (size_t)n * 4, cudaMemcpyDeviceToHost, h->st));
     CK(cudaStreamSynchronize(h->st));
     end_call(h);
@@ -1127,7 +1268,7 @@ int lvreg_knn5(lvreg_handle* h, int which, const lvreg_cloud* queries, int varia
     CK(cudaSetDevice(h->device));
     if (!h->map[which].valid) return fail(h, LVREG_ERR_NO_MAP, "no local map");
     begin_call(h);
-    CKS(upload_cloud(h, queries, h->qbuf, 0));
+    CKS(upload_cloud(h, queries, h->qbuf, h->lane[LANE_SCAN_CORNER].stage, h->st));
     const uint32_t nq = (uint32_t)queries->n;
     if (nq == 0) return LVREG_OK;
     CK(h->idxbuf.reserve((size_t)nq * 5 * 4));
@@ -1149,7 +1290,7 @@ int lvreg_bench_knn5(lvreg_handle* h, int which, const lvreg_cloud* queries, int
     CK(cudaSetDevice(h->device));
     if (!h->map[which].valid) return fail(h, LVREG_ERR_NO_MAP, "no local map");
     begin_call(h);
-    CKS(upload_cloud(h, queries, h->qbuf, 0));
+    CKS(upload_cloud(h, queries, h->qbuf, h->lane[LANE_SCAN_CORNER].stage, h->st));
     const uint32_t nq = (uint32_t)queries->n;
     if (nq == 0) return fail(h, LVREG_ERR_INVALID, "no queries");
     CK(h->idxbuf.reserve((size_t)nq * 5 * 4));
@@ -1172,7 +1313,7 @@ static int residuals_api(lvreg_handle* h, int cls, const lvreg_cloud* pts, const
     CK(cudaSetDevice(h->device));
     if (!h->map[cls].valid) return fail(h, LVREG_ERR_NO_MAP, "no local map");
     begin_call(h);
-    CKS(upload_cloud(h, pts, h->qbuf, 0));
+    CKS(upload_cloud(h, pts, h->qbuf, h->lane[LANE_SCAN_CORNER].stage, h->st));
     const uint32_t n = (uint32_t)pts->n;
     if (n == 0) return LVREG_OK;
     CK(h->coeffbuf.reserve((size_t)n * 16));
@@ -1259,7 +1400,7 @@ int lvreg_get_timings(const lvreg_handle* h, lvreg_timings* t) {
 
 int lvreg_get_iteration_profile(const lvreg_handle* h, float* us, int* iterations) {
     if (!h || !us) return LVREG_ERR_INVALID;
-    const RegOut* ho = (const RegOut*)((const char*)h->pinned + 256);    // last D2H copy of RegOut
+    const RegOut* ho = (const RegOut*)((const char*)h->pinned + 4096);    // last D2H copy of RegOut
     int n = ho->iterations;
     if (n < 0) n = 0;
     if (n > h->prm.max_iters) n = h->prm.max_iters;
