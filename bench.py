@@ -257,7 +257,7 @@ def main():
         ts = torch.from_numpy(s).cuda()
         keep.append((tc, ts))
         dev_scans.append((device_cloud(tc.data_ptr(), len(c)), device_cloud(ts.data_ptr(), len(s))))
-    d2h_bytes = 24 + int(np.dtype(np.int32).itemsize) * 0 + 1192       # pose + RegOut
+    d2h_bytes = 2344 + 6 * 4 * 0                                        # the RegOut block (pose, per-iteration log, phase stamps)
 
     def run_steps(n, first, on_device):
         out = []
@@ -329,7 +329,7 @@ def main():
                 gpu_launches=int(launches),
                 knn_queries_per_s=float(np.sum([it * nq for it in iters]) * world / (ms_dev * 1e-3)),
                 stages_ms=stage,
-                roofline=dict(kernel="register_kernel", bound="hbm", achieved=achieved, peak=hbm_peak, unit="GB/s",
+                roofline=dict(kernel="register_tpq_kernel (one cooperative launch per registration)", bound="hbm", achieved=achieved, peak=hbm_peak, unit="GB/s",
                               frac=achieved / hbm_peak, traffic=traffic, peak_source=peak_src,
                               algorithmic_bytes_per_launch=reg_bytes, launch_ms=stage["register_ms"]),
                 clocks=clocks, wall_s=dict(resident=wall_dev, e2e=wall_e2e))
