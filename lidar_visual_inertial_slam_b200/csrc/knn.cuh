@@ -228,21 +228,32 @@ __device__ __forceinline__ void thread_knn5_gated(const GridView& g, float qx, f
     // (dy, dz) visiting order: centre, faces, diagonals
     const int ody[9] = {0, -1, 1, 0, 0, -1, 1, -1, 1};
     const int odz[9] = {0, 0, 0, -1, 1, -1, -1, 1, 1};
+    // all 9 rows' cell boundaries are fetched up front (independent loads, one latency)
+    uint32_t b0[9], b1[9], b2[9], b3[9];
+    const int xl = cx > 0 ? cx - 1 : cx, xh = cx + 1 < g.dx ? cx + 2 : cx + 1;
+#pragma unroll
+    for (int r = 0; r < 9; ++r) {
+        const int yy = cy + ody[r], zz = cz + odz[r];
+        b0[r] = b1[r] = b2[r] = b3[r] = 0;
+        if (yy >= 0 && yy < g.dy && zz >= 0 && zz < g.dz) {
+            const uint32_t* row = g.cell_start + ((uint32_t)zz * g.dy + yy) * g.dx;
+            b0[r] = __ldg(row + xl);
+            b1[r] = __ldg(row + cx);
+            b2[r] = __ldg(row + cx + 1);
+            b3[r] = __ldg(row + xh);
+        }
+    }
 #pragma unroll
     for (int r = 0; r < 9; ++r) {
         const int dyy = ody[r], dzz = odz[r];
-        const int yy = cy + dyy, zz = cz + dzz;
-        if (yy < 0 || yy >= g.dy || zz < 0 || zz >= g.dz) continue;
         const float gy = dyy == 0 ? 0.f : (dyy < 0 ? gym : gyp);
         const float gz = dzz == 0 ? 0.f : (dzz < 0 ? gzm : gzp);
         const float rb = gy * gy + gz * gz;
         // tau: only points with d2 <= tau can still enter the list (strictly below the gate)
         const float tau = t[4] == kKeyNone ? gate_sq : key_d2(t[4]);
         if (rb > tau) continue;
-        const int xa = (cx > 0 && !(rb + gxm2 > tau)) ? cx - 1 : cx;
-        const int xb = (cx + 1 < g.dx && !(rb + gxp2 > tau)) ? cx + 1 : cx;
-        const uint32_t* row = g.cell_start + ((uint32_t)zz * g.dy + yy) * g.dx;
-        const uint32_t s = __ldg(row + xa), e = __ldg(row + xb + 1);
+        const uint32_t s = (rb + gxm2 > tau) ? b1[r] : b0[r];
+        const uint32_t e = (rb + gxp2 > tau) ? b2[r] : b3[r];
         thread_scan(g, s, e, qx, qy, qz, gate_sq, t);
     }
 }

@@ -347,3 +347,72 @@ def test_transform_update(lv, h):
     a = h.transform_update(p, True, 0.5, 0.1)
     b = O.transform_update(p, True, 0.5, 0.1, 0.01)
     assert np.allclose(a, b, atol=1e-6)
+
+
+# ---- ragged / degenerate inputs ---------------------------------------------------------------------
+def test_ragged_inputs_through_the_scan_path(lv, room):
+    hd = lv.Lvreg()
+    empty = np.zeros((0, 4), np.float32)
+    # keyframes with an empty corner / surf cloud, and a selection that repeats an id
+    hd.add_keyframe(room["cm"], empty, np.zeros(6, np.float32))
+    hd.add_keyframe(empty, room["sm"], np.zeros(6, np.float32))
+    hd.add_keyframe(room["cm"], room["sm"], np.array([0, 0, 0, 0.05, 0, 0], np.float32))
+    mo = O.MapOptimization()
+    mo.add_keyframe(room["cm"], empty, np.zeros(6, np.float32), 0.0)
+    mo.add_keyframe(empty, room["sm"], np.zeros(6, np.float32), 1.0)
+    mo.add_keyframe(room["cm"], room["sm"], np.array([0, 0, 0, 0.05, 0, 0], np.float32), 2.0)
+    ids = np.array([2, 0, 1, 2], np.int32)            # duplicates are concatenated twice (MO:919-926)
+    info = hd.build_local_map(ids)
+    mo.build_local_map(ids)
+    assert info.n_corner_in == 3 * len(room["cm"]) and info.n_surf_in == 3 * len(room["sm"])
+    for which in (lv.CORNER, lv.SURF):
+        assert np.array_equal(hd.get_local_map(which), mo.get_map(which))
+    # empty incoming scan: "not enough features", pose untouched, nothing crashes
+    pose, res, st = hd.register_scan(empty, empty, None, room["guess"])
+    assert st == lv.ERR_NOT_ENOUGH_FEATURES and np.array_equal(pose, room["guess"])
+    assert (res.n_corner_ds, res.n_surf_ds) == (0, 0)
+    # an empty selection gives empty maps; registration then finds no correspondences
+    hd.build_local_map(np.zeros(0, np.int32))
+    assert len(hd.get_local_map(lv.SURF)) == 0
+    pose, res, st = hd.register_scan(room["c"], room["s"], None, room["guess"])
+    assert st == lv.OK and res.converged == 0 and res.iterations == 20 and np.array_equal(pose, room["guess"])
+    # invalid ids are rejected
+    with pytest.raises(lv.LvregError):
+        hd.build_local_map(np.array([7], np.int32))
+    hd.close()
+
+
+def test_far_from_origin_coordinates(lv, room):
+    """maps a few km from the origin: voxel keys / neighbour sets stay bit-exact (fp32 rounding of large coordinates)"""
+    off = np.array([4321.5, -2876.25, 37.0, 0], np.float32)
+    cm = (room["cm"] + off).astype(np.float32)
+    sm = (room["sm"] + off).astype(np.float32)
+    hd = lv.Lvreg()
+    out, okeys, _ = hd.voxelgrid(sm, 0.4)
+    ref, _, rkeys, _ = O.voxelgrid(sm, 0.4)
+    assert np.array_equal(out, ref) and np.array_equal(okeys, rkeys)
+    hd.set_local_map(cm, sm)
+    guess = room["guess"].copy()
+    guess[3:] += off[:3]
+    coeff, flag, nn = hd.surf_residuals(room["sds"], guess)
+    rcoeff, rflag, rnn = O.surf_residuals(sm, room["sds"], guess)
+    assert np.array_equal(flag, rflag) and rflag.sum() > 1000
+    assert np.array_equal(nn[rflag == 1], rnn[rflag == 1]) and np.array_equal(coeff, rcoeff)
+    hd.close()
+
+
+def test_two_handles_are_independent(lv, room):
+    a, b = lv.Lvreg(), lv.Lvreg()
+    a.set_local_map(room["cm"], room["sm"])
+    b.set_local_map(room["cm"][:100], room["sm"][:100])
+    a.set_scan_ds(room["cds"], room["sds"])
+    b.set_scan_ds(room["cds"], room["sds"])
+    pa, ra, sa = a.scan2map(room["guess"])
+    pb, rb, sb = b.scan2map(room["guess"])
+    pa2, ra2, _ = a.scan2map(room["guess"])
+    assert ra.converged == 1 and np.array_equal(pa, pa2)             # b's work did not disturb a
+    rpb, rrb, _ = O.scan2map(room["cm"][:100], room["sm"][:100], room["cds"], room["sds"], room["guess"])
+    assert rb.iterations == rrb.iterations and rb.converged == rrb.converged
+    assert np.abs(pb - rpb).max() <= 1e-4 and not np.array_equal(pa, pb)
+    a.close()
+    b.close()
