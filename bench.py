@@ -313,6 +313,12 @@ def main():
         with open(tp) as f:
             traffic = json.load(f).get("dram_bytes_per_launch")
 
+    # second-largest consumer: the radix-sort passes of the VoxelGrid replacement (they overlap on
+    # the lanes inside a step, so they are timed on their own here, same size as the surf-map sort)
+    n_sort = int(sum(len(b) for b in ds["kf_surf"]))
+    sort_ms, sort_passes = h.bench_sort(n_sort, 28, 5)
+    sort_gbs = 16.0 * n_sort * sort_passes / (sort_ms * 1e-3) / 1e9
+
     n_total_steps = args.steps * world
     value = n_total_steps / (ms_dev * 1e-3)
     e2e = n_total_steps / (ms_e2e * 1e-3)
@@ -332,6 +338,9 @@ def main():
                 roofline=dict(kernel="register_tpq_kernel (one cooperative launch per registration)", bound="hbm", achieved=achieved, peak=hbm_peak, unit="GB/s",
                               frac=achieved / hbm_peak, traffic=traffic, peak_source=peak_src,
                               algorithmic_bytes_per_launch=reg_bytes, launch_ms=stage["register_ms"]),
+                roofline_sort=dict(kernel="rs_onesweep_kernel (%d passes over %d pairs, timed alone)" % (sort_passes, n_sort),
+                                   bound="hbm", achieved=sort_gbs, peak=hbm_peak, unit="GB/s", frac=sort_gbs / hbm_peak,
+                                   ms_per_sort=sort_ms, algorithmic_bytes_per_pair_per_pass=16),
                 clocks=clocks, wall_s=dict(resident=wall_dev, e2e=wall_e2e))
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -232,6 +232,11 @@ int lvreg_get_launch_count(const lvreg_handle* h, uint64_t* n);
 int lvreg_bench_knn5(lvreg_handle* h, int which_map, const lvreg_cloud* queries, int variant,
                      int repeats, float* ms_per_launch);
 
+/* Radix-sort micro-benchmark: sorts n pseudo-random (key, index) pairs with `key_bits` significant
+ * bits `repeats` times on the handle's stream; returns the mean device time of one whole sort and the
+ * number of 8-bit passes it took.  Algorithmic traffic per pass = 16 B per pair. */
+int lvreg_bench_sort(lvreg_handle* h, size_t n, int key_bits, int repeats, float* ms_per_sort, int* passes);
+
 #ifdef __cplusplus
 }
 #endif

@@ -330,6 +330,12 @@ class Lvreg:
         self._ck(self.L.lvreg_bench_knn5(self.h, which, C.byref(c), variant, repeats, C.byref(ms)))
         return ms.value
 
+    def bench_sort(self, n, key_bits=28, repeats=5):
+        """(ms per whole sort, number of 8-bit passes) for n random (key, index) pairs"""
+        ms, passes = C.c_float(0), C.c_int(0)
+        self._ck(self.L.lvreg_bench_sort(self.h, C.c_size_t(n), int(key_bits), int(repeats), C.byref(ms), C.byref(passes)))
+        return ms.value, passes.value
+
     def _residuals(self, fn, pts, pose):
         c, keep = _cloud(pts)
         pose = np.ascontiguousarray(pose, np.float32)

@@ -1391,6 +1391,39 @@ int lvreg_lm_step(lvreg_handle* h, const float* ori, const float* coeff, size_t 
     return LVREG_OK;
 }
 
+__global__ void __launch_bounds__(256) bench_fill_kernel(uint32_t* keys, uint32_t* vals, uint32_t n, uint32_t mask) {
+    uint32_t i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    uint32_t x = i * 2654435761u + 0x9e3779b9u;      // cheap integer hash
+    x ^= x >> 16; x *= 0x85ebca6bu; x ^= x >> 13; x *= 0xc2b2ae35u; x ^= x >> 16;
+    keys[i] = x & mask;
+    vals[i] = i;
+}
+
+int lvreg_bench_sort(lvreg_handle* h, size_t n_, int key_bits, int repeats, float* ms_per_sort, int* passes) {
+    if (!h || n_ == 0 || n_ > 0x7fffffffull || key_bits < 1 || key_bits > 32 || repeats < 1) return LVREG_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    begin_call(h);
+    const uint32_t n = (uint32_t)n_;
+    Lane& L = h->lane[LANE_MAP_SURF];
+    CKS(ensure_sort_buffers(h, L, n));
+    const uint32_t mask = key_bits >= 32 ? 0xffffffffu : ((1u << key_bits) - 1u);
+    float total = 0.f;
+    for (int r = 0; r < repeats + 2; ++r) {           // 2 warm-up rounds
+        bench_fill_kernel<<<nblk(n, 256), 256, 0, h->st>>>(L.keys[0].as<uint32_t>(), L.vals[0].as<uint32_t>(), n, mask);
+        mark(h, EV_BEGIN);
+        radix_sort_pairs(L.keys[0].as<uint32_t>(), L.vals[0].as<uint32_t>(), L.keys[1].as<uint32_t>(),
+                         L.vals[1].as<uint32_t>(), n, key_bits, L.sort_scratch.as<uint32_t>(), h->st, &h->call_launches);
+        mark(h, EV_REG);
+        CK(cudaStreamSynchronize(h->st));
+        if (r >= 2) total += span(h, EV_BEGIN, EV_REG);
+    }
+    if (ms_per_sort) *ms_per_sort = total / (float)repeats;
+    if (passes) *passes = (key_bits + 7) / 8;
+    end_call(h);
+    return LVREG_OK;
+}
+
 // ---- measurement ---------------------------------------------------------------------------------
 int lvreg_get_timings(const lvreg_handle* h, lvreg_timings* t) {
     if (!h || !t) return LVREG_ERR_INVALID;

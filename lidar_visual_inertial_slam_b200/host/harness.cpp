@@ -12,7 +12,9 @@ void truth_pose(const SequenceSpec& s, int k, float pose[6]) {
     pose[0] = (float)(0.01 * std::sin(0.7 * t));
     pose[1] = (float)(0.01 * std::cos(0.5 * t));
     pose[2] = (float)(0.15 * std::sin(0.1 * 6.283185307179586 * t / 10.0));
-    pose[3] = (float)(s.speed * t);
+    // forward along the street at `speed`, turning back smoothly before the end of the world
+    const double R = s.sensor == 1 ? 200.0 : 30.0;
+    pose[3] = (float)(R * std::sin(s.speed * t / R));
     pose[4] = (float)(0.8 * std::sin(0.05 * t * 6.283185307179586));
     pose[5] = (float)(0.02 * std::sin(0.3 * t));
 }
