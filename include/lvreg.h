@@ -215,6 +215,33 @@ int lvreg_lm_step(lvreg_handle* h, const float* ori_xyzi, const float* coeff_xyz
                   int iter_count, float pose_rpyxyz[6], float AtA_out[36], float Atb_out[6],
                   float x_out[6], int* converged);
 
+/* ---- "next" row: FeatureExtraction on the device ----------------------------- */
+/* The per-point side channels of lidar_odometry/msg/CloudInfo.msg that FeatureExtraction consumes
+ * (imageProjection.cpp:624-647); host arrays. */
+typedef struct lvreg_scan_info {
+    const int32_t* start_ring_index;   /* n_scan entries */
+    const int32_t* end_ring_index;     /* n_scan entries */
+    int32_t        n_scan;             /* N_SCAN, <= 256 */
+    int32_t        reserved;
+    const int32_t* point_col_ind;      /* one per point of the deskewed cloud */
+    const float*   point_range;        /* one per point */
+} lvreg_scan_info;
+/* calculateSmoothness + markOccludedPoints + extractFeatures (featureExtraction.cpp:87-245) on the
+ * deskewed, ring-ordered cloud: corner cloud (<= 40 per ring sector, ring / sector / pick order) and
+ * surface cloud (per-ring VoxelGrid with `surf_leaf` = odometrySurfLeafSize, rings in order).
+ * Unspecified reference behaviour is pinned: std::sort ties break on the point index; entries the
+ * reference never initialises read as zero.  corner / surf (optional) receive host or device
+ * copies; label_out (optional, host, one int32 per point) receives cloudLabel.  The two clouds also
+ * stay on the device as laserCloudCornerLast / laserCloudSurfLast -- see lvreg_get_feature_clouds. */
+int lvreg_extract_features(lvreg_handle* h, const lvreg_cloud* deskewed, const lvreg_scan_info* info,
+                           float edge_threshold, float surf_threshold, float surf_leaf,
+                           lvreg_cloud_out* corner, size_t* n_corner, lvreg_cloud_out* surf, size_t* n_surf,
+                           int32_t* label_out);
+/* Device-resident descriptors of the last extracted feature clouds; pass them to
+ * lvreg_register_scan / lvreg_downsample_scan to go from the raw scan to the pose without a host
+ * round trip of the features. */
+int lvreg_get_feature_clouds(const lvreg_handle* h, lvreg_cloud* corner, lvreg_cloud* surf);
+
 /* ---- measurement -------------------------------------------------------------------------- */
 int lvreg_get_timings(const lvreg_handle* h, lvreg_timings* t);
 /* Phase profile of the last lvreg_scan2map / lvreg_register_scan launch, from block 0's

@@ -149,6 +149,11 @@ def to_pcl_layout(a):
     return out
 
 
+class ScanInfo(C.Structure):
+    _fields_ = [("start_ring_index", C.c_void_p), ("end_ring_index", C.c_void_p), ("n_scan", C.c_int32),
+                ("reserved", C.c_int32), ("point_col_ind", C.c_void_p), ("point_range", C.c_void_p)]
+
+
 class Lvreg:
     """One registration handle = one mapOptimization instance on one GPU / stream."""
 
@@ -329,6 +334,37 @@ class Lvreg:
         ms = C.c_float(0)
         self._ck(self.L.lvreg_bench_knn5(self.h, which, C.byref(c), variant, repeats, C.byref(ms)))
         return ms.value
+
+    def extract_features(self, pts, point_range, point_col_ind, start_ring, end_ring, edge_threshold=1.0,
+                         surf_threshold=0.1, surf_leaf=0.4):
+        """FeatureExtraction (featureExtraction.cpp:87-245) -> (corner, surf, label)"""
+        c, keep = _cloud(pts)
+        rng = np.ascontiguousarray(point_range, np.float32)
+        col = np.ascontiguousarray(point_col_ind, np.int32)
+        sr = np.ascontiguousarray(start_ring, np.int32)
+        er = np.ascontiguousarray(end_ring, np.int32)
+        info = ScanInfo(sr.ctypes.data, er.ctypes.data, len(sr), 0, col.ctypes.data, rng.ctypes.data)
+        n = c.n
+        corner = np.zeros((max(len(sr) * 240, 1), 4), np.float32)
+        surf = np.zeros((max(n, 1), 4), np.float32)
+        label = np.zeros(max(n, 1), np.int32)
+        co, so = CloudOut(), CloudOut()
+        for o, a in ((co, corner), (so, surf)):
+            o.data = a.ctypes.data
+            o.capacity = len(a)
+            o.stride = 16
+            o.intensity_offset = 12
+        nc, ns = C.c_size_t(0), C.c_size_t(0)
+        self._ck(self.L.lvreg_extract_features(self.h, C.byref(c), C.byref(info), C.c_float(edge_threshold),
+                                               C.c_float(surf_threshold), C.c_float(surf_leaf), C.byref(co), C.byref(nc),
+                                               C.byref(so), C.byref(ns), label.ctypes.data_as(C.c_void_p)))
+        return corner[:nc.value].copy(), surf[:ns.value].copy(), label[:n].copy()
+
+    def feature_clouds(self):
+        """device-resident (corner, surf) descriptors of the last extract_features call"""
+        c, s = Cloud(), Cloud()
+        self._ck(self.L.lvreg_get_feature_clouds(self.h, C.byref(c), C.byref(s)))
+        return c, s
 
     def bench_sort(self, n, key_bits=28, repeats=5):
         """(ms per whole sort, number of 8-bit passes) for n random (key, index) pairs"""

@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "feature.cuh"
 #include "fit.cuh"
 #include "knn.cuh"
 #include "prims.cuh"
@@ -97,6 +98,9 @@ struct lvreg_handle {
     DevBuf scan_ds[2];
     uint32_t n_scan[2] = {0, 0};
     // scratch of the main stream
+    DevBuf feat_pts, feat_range, feat_col, feat_rings, feat_curv, feat_picked, feat_label, feat_flag, feat_ringof,
+        feat_cidx, feat_ccnt, feat_pos, feat_cand, feat_spec, feat_idx, feat_pidx, feat_corner, feat_surf;
+    uint32_t n_feat[2] = {0, 0};
     DevBuf vgout, partials, regout, lmstate, posebuf, tilectr, tilens, qbuf, idxbuf, d2buf, brute_partial, coeffbuf, flagbuf;
     void* pinned = nullptr;       // 64 KB page-locked scratch: lanes use [0, 1 KB), RegOut lives at +4 KB
     cudaEvent_t ev[EV_COUNT];
@@ -855,7 +859,10 @@ void lvreg_destroy(lvreg_handle* h) {
         h->map[s].ds.release(); h->map[s].cell_pts.release(); h->map[s].cell_start.release();
         h->scan_ds[s].release();
     }
-    DevBuf* bufs[] = {&h->vgout, &h->partials, &h->regout, &h->lmstate, &h->posebuf, &h->tilectr, &h->tilens, &h->qbuf,
+    DevBuf* bufs[] = {&h->feat_pts, &h->feat_range, &h->feat_col, &h->feat_rings, &h->feat_curv, &h->feat_picked,
+                      &h->feat_label, &h->feat_flag, &h->feat_ringof, &h->feat_cidx, &h->feat_ccnt, &h->feat_pos,
+                      &h->feat_cand, &h->feat_spec, &h->feat_idx, &h->feat_pidx, &h->feat_corner, &h->feat_surf,
+                      &h->vgout, &h->partials, &h->regout, &h->lmstate, &h->posebuf, &h->tilectr, &h->tilens, &h->qbuf,
                       &h->idxbuf, &h->d2buf, &h->brute_partial, &h->coeffbuf, &h->flagbuf};
     for (DevBuf* b : bufs) b->release();
     if (h->ev_main) cudaEventDestroy(h->ev_main);
@@ -1388,6 +1395,166 @@ int lvreg_lm_step(lvreg_handle* h, const float* ori, const float* coeff, size_t 
     if (x_out) memcpy(x_out, hp + 50, 6 * sizeof(float));
     if (converged) *converged = *(int*)(hp + 56);
     end_call(h);
+    return LVREG_OK;
+}
+
+// ---- "next" row: FeatureExtraction --------------------------------------------------------------
+int lvreg_extract_features(lvreg_handle* h, const lvreg_cloud* deskewed, const lvreg_scan_info* info, float edge_th,
+                           float surf_th, float surf_leaf, lvreg_cloud_out* corner, size_t* n_corner,
+                           lvreg_cloud_out* surf, size_t* n_surf, int32_t* label_out) {
+    if (!h || !deskewed || !info || !info->start_ring_index || !info->end_ring_index) return LVREG_ERR_INVALID;
+    if (info->n_scan < 1 || info->n_scan > 256) return fail(h, LVREG_ERR_INVALID, "n_scan must be in [1, 256]");
+    if (deskewed->n && (!info->point_col_ind || !info->point_range)) return LVREG_ERR_INVALID;
+    if (!(surf_leaf > 0.f)) return fail(h, LVREG_ERR_INVALID, "leaf size must be positive");
+    CK(cudaSetDevice(h->device));
+    begin_call(h);
+    mark(h, EV_BEGIN);
+    Lane& L = h->lane[LANE_SCAN_SURF];
+    const uint32_t n = (uint32_t)deskewed->n;
+    const int ns = info->n_scan;
+    h->n_feat[0] = h->n_feat[1] = 0;
+    if (n_corner) *n_corner = 0;
+    if (n_surf) *n_surf = 0;
+    CKS(upload_cloud(h, deskewed, h->feat_pts, L.stage, h->st));
+    CK(h->feat_corner.reserve((size_t)ns * kFeCornerStride * 16));
+    if (n == 0) return LVREG_OK;
+    // shared-memory budget of the per-ring kernel from the ring / sector lengths
+    int cap = 16, max_sector = 1;
+    for (int r = 0; r < ns; ++r) {
+        const int a = info->start_ring_index[r], b = info->end_ring_index[r];
+        if (a < -1000000 || b > (int)n + 1000000) return fail(h, LVREG_ERR_INVALID, "ring index out of range");
+        int lo = a - 5, hi = b + 4;
+        if (lo < 0) lo = 0;
+        if (hi > (int)n - 1) hi = (int)n - 1;
+        if (hi - lo + 1 > cap) cap = hi - lo + 1;
+        if ((b - a) / 6 + 2 > max_sector) max_sector = (b - a) / 6 + 2;
+    }
+    int sort_cap = 2;
+    while (sort_cap < max_sector) sort_cap <<= 1;
+    const size_t smem = fe_ring_smem_bytes(cap, sort_cap);
+    if (smem > 220 * 1024) return fail(h, LVREG_ERR_INVALID, "a ring is too long for the feature-extraction kernel");
+    CK(cudaFuncSetAttribute(fe_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+
+    CK(h->feat_range.reserve((size_t)n * 4));
+    CK(h->feat_col.reserve((size_t)n * 4));
+    CK(h->feat_rings.reserve((size_t)ns * 8));
+    CK(h->feat_curv.reserve((size_t)n * 4));
+    CK(h->feat_picked.reserve(n));
+    CK(h->feat_label.reserve(n));
+    CK(h->feat_flag.reserve((size_t)(n + 8) * 4));
+    CK(h->feat_ringof.reserve(n));
+    CK(h->feat_cidx.reserve((size_t)ns * kFeCornerStride * 4));
+    CK(h->feat_ccnt.reserve((size_t)ns * 4 + 16));
+    CK(h->feat_pos.reserve((size_t)(n + 8) * 4));
+    CK(h->feat_cand.reserve((size_t)(n + 8) * 4));
+    CK(h->feat_spec.reserve((size_t)ns * sizeof(RingSpec)));
+    CKS(ensure_sort_buffers(h, L, n));
+    CK(cudaMemcpyAsync(h->feat_range.p, info->point_range, (size_t)n * 4, cudaMemcpyHostToDevice, h->st));
+    CK(cudaMemcpyAsync(h->feat_col.p, info->point_col_ind, (size_t)n * 4, cudaMemcpyHostToDevice, h->st));
+    int32_t* d_start = h->feat_rings.as<int32_t>();
+    int32_t* d_end = d_start + ns;
+    CK(cudaMemcpyAsync(d_start, info->start_ring_index, (size_t)ns * 4, cudaMemcpyHostToDevice, h->st));
+    CK(cudaMemcpyAsync(d_end, info->end_ring_index, (size_t)ns * 4, cudaMemcpyHostToDevice, h->st));
+    CK(cudaMemsetAsync(h->feat_picked.p, 0, n, h->st));
+    CK(cudaMemsetAsync(h->feat_label.p, 0, n, h->st));
+    CK(cudaMemsetAsync(h->feat_flag.p, 0, (size_t)(n + 8) * 4, h->st));
+    CK(cudaMemsetAsync(h->feat_ringof.p, 0, n, h->st));
+    int32_t* d_err = h->feat_ccnt.as<int32_t>() + ns;
+    CK(cudaMemsetAsync(d_err, 0, 4, h->st));
+    uint32_t* d_small = L.small.as<uint32_t>();
+
+    fe_smooth_kernel<<<nblk(n, 256), 256, 0, h->st>>>(h->feat_range.as<float>(), h->feat_col.as<int32_t>(), (int)n,
+                                                      h->feat_curv.as<float>(), h->feat_picked.as<uint8_t>());
+    fe_ring_kernel<<<ns, 256, smem, h->st>>>(h->feat_curv.as<float>(), h->feat_picked.as<uint8_t>(), h->feat_col.as<int32_t>(),
+                                             (int)n, d_start, d_end, edge_th, surf_th, cap, sort_cap,
+                                             h->feat_label.as<int8_t>(), h->feat_flag.as<uint32_t>(),
+                                             h->feat_ringof.as<uint8_t>(), h->feat_cidx.as<int32_t>(),
+                                             h->feat_ccnt.as<int32_t>(), d_err);
+    fe_corner_gather_kernel<<<1, 256, 0, h->st>>>(h->feat_pts.as<float4>(), h->feat_cidx.as<int32_t>(),
+                                                  h->feat_ccnt.as<int32_t>(), ns, h->feat_corner.as<float4>(), d_small + SM_TOTAL);
+    launched(h, 3);
+    exclusive_scan(FlagIn{h->feat_flag.as<uint32_t>()}, CompactOut{h->feat_pos.as<uint32_t>(), h->feat_cand.as<uint32_t>()}, n,
+                   L.scan_temp.as<uint32_t>(), d_small + SM_NVOX, h->st, &h->call_launches);
+    uint32_t* host = L.pinned;
+    CK(cudaMemcpyAsync(host, d_small + SM_TOTAL, 4, cudaMemcpyDeviceToHost, h->st));
+    CK(cudaMemcpyAsync(host + 1, d_small + SM_NVOX, 4, cudaMemcpyDeviceToHost, h->st));
+    CK(cudaMemcpyAsync(host + 2, d_err, 4, cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    if (host[2]) return fail(h, LVREG_ERR_INVALID, "ring layout exceeds the feature-extraction kernel's limits");
+    const uint32_t nc = host[0], n_cand = host[1];
+    uint32_t nsurf = 0;
+    if (n_cand) {
+        CK(h->feat_idx.reserve((size_t)n_cand * 4));
+        CK(h->feat_pidx.reserve((size_t)n_cand * 4));
+        CK(L.vox_start.reserve((size_t)n_cand * 4));
+        fe_ring_bbox_kernel<<<ns, 256, 0, h->st>>>(h->feat_pts.as<float4>(), h->feat_flag.as<uint32_t>(), h->feat_pos.as<uint32_t>(),
+                                                   d_start, d_end, (int)n, surf_leaf, h->feat_spec.as<RingSpec>());
+        fe_surf_keys_kernel<<<nblk(n_cand, 256), 256, 0, h->st>>>(h->feat_pts.as<float4>(), h->feat_cand.as<uint32_t>(), n_cand,
+                                                                  h->feat_ringof.as<uint8_t>(), h->feat_spec.as<RingSpec>(),
+                                                                  L.keys[0].as<uint32_t>(), L.vals[0].as<uint32_t>(),
+                                                                  h->feat_idx.as<uint32_t>());
+        launched(h, 2);
+        int cur = radix_sort_pairs(L.keys[0].as<uint32_t>(), L.vals[0].as<uint32_t>(), L.keys[1].as<uint32_t>(),
+                                   L.vals[1].as<uint32_t>(), n_cand, 32, L.sort_scratch.as<uint32_t>(), h->st, &h->call_launches);
+        // second, stable sort by ring: (ring, idx, input order)
+        uint32_t* k_a = L.keys[cur].as<uint32_t>();
+        uint32_t* v_a = L.vals[cur].as<uint32_t>();
+        uint32_t* k_b = L.keys[cur ^ 1].as<uint32_t>();
+        uint32_t* v_b = L.vals[cur ^ 1].as<uint32_t>();
+        fe_ring_keys_kernel<<<nblk(n_cand, 256), 256, 0, h->st>>>(v_a, n_cand, h->feat_cand.as<uint32_t>(),
+                                                                  h->feat_ringof.as<uint8_t>(), k_a);
+        launched(h);
+        int cur2 = radix_sort_pairs(k_a, v_a, k_b, v_b, n_cand, bits_for((uint64_t)(ns > 1 ? ns - 1 : 1)),
+                                    L.sort_scratch.as<uint32_t>(), h->st, &h->call_launches);
+        const uint32_t* rk = cur2 ? k_b : k_a;
+        const uint32_t* rv = cur2 ? v_b : v_a;
+        exclusive_scan(RingVoxelHeadIn{rk, rv, h->feat_idx.as<uint32_t>()}, VoxelStartOut{L.vox_start.as<uint32_t>()}, n_cand,
+                       L.scan_temp.as<uint32_t>(), d_small + SM_NVOX, h->st, &h->call_launches);
+        CK(cudaMemcpyAsync(host, d_small + SM_NVOX, 4, cudaMemcpyDeviceToHost, h->st));
+        CK(cudaStreamSynchronize(h->st));
+        nsurf = host[0];
+        CK(h->feat_surf.reserve((size_t)(nsurf ? nsurf : 1) * 16));
+        fe_point_index_kernel<<<nblk(n_cand, 256), 256, 0, h->st>>>(rv, n_cand, h->feat_cand.as<uint32_t>(), h->feat_pidx.as<uint32_t>());
+        centroid_kernel<<<nblk(nsurf, 128), 128, 0, h->st>>>(h->feat_pts.as<float4>(), rk, h->feat_pidx.as<uint32_t>(),
+                                                             L.vox_start.as<uint32_t>(), d_small + SM_NVOX, n_cand,
+                                                             h->feat_surf.as<float4>(), nullptr);
+        launched(h, 2);
+    } else {
+        CK(h->feat_surf.reserve(16));
+    }
+    CK(cudaGetLastError());
+    mark(h, EV_DS);
+    h->n_feat[0] = nc;
+    h->n_feat[1] = nsurf;
+    if (n_corner) *n_corner = nc;
+    if (n_surf) *n_surf = nsurf;
+    if (label_out) {
+        std::vector<int8_t> tmp(n);
+        CK(cudaMemcpyAsync(tmp.data(), h->feat_label.p, n, cudaMemcpyDeviceToHost, h->st));
+        CK(cudaStreamSynchronize(h->st));
+        for (uint32_t i = 0; i < n; ++i) label_out[i] = tmp[i];
+    }
+    if (corner) CKS(download_cloud(h, h->feat_corner.as<float4>(), nc, corner));
+    if (surf) CKS(download_cloud(h, h->feat_surf.as<float4>(), nsurf, surf));
+    CK(cudaStreamSynchronize(h->st));
+    h->last.downsample_ms = span(h, EV_BEGIN, EV_DS);
+    finish_timings(h);
+    end_call(h);
+    return LVREG_OK;
+}
+
+int lvreg_get_feature_clouds(const lvreg_handle* h, lvreg_cloud* corner, lvreg_cloud* surf) {
+    if (!h || !corner || !surf) return LVREG_ERR_INVALID;
+    lvreg_cloud* c[2] = {corner, surf};
+    const DevBuf* b[2] = {&h->feat_corner, &h->feat_surf};
+    for (int s = 0; s < 2; ++s) {
+        c[s]->data = b[s]->p;
+        c[s]->n = h->n_feat[s];
+        c[s]->stride = 16;
+        c[s]->intensity_offset = 12;
+        c[s]->on_device = 1;
+        c[s]->reserved = 0;
+    }
     return LVREG_OK;
 }
 

@@ -162,6 +162,20 @@ void    orc_mo_register_scan(orc_mo* mo, const float* corner_raw, size_t nc_raw,
                              const float* surf_raw, size_t ns_raw, float pose[6], orc_result* res,
                              size_t* nc_ds, size_t* ns_ds);
 
+/* ---- "next" row: FeatureExtraction, oracle_feature.cpp --------------------------
+ * calculateSmoothness + markOccludedPoints + extractFeatures of
+ * lidar_odometry/src/featureExtraction.cpp:87-245 on one deskewed, ring-ordered cloud
+ * (imageProjection.cpp:624-647 layout: start/end_ring_index, point_col_ind, point_range).
+ * Pinned choices for what the reference leaves unspecified: std::sort ties -> by index;
+ * cloudNeighborPicked / cloudLabel / cloudSmoothness entries the reference never initialises
+ * (i < 5, i >= n-5) read as 0 / {0, i}.  corner_out / surf_out have room for n rows.
+ * label_out (optional, n): cloudLabel.  Returns 0. */
+int orc_extract_features(const float* pts, size_t n, const float* point_range, const int32_t* point_col_ind,
+                         const int32_t* start_ring_index, const int32_t* end_ring_index, int n_scan,
+                         float edge_threshold, float surf_threshold, float surf_leaf,
+                         float* corner_out, size_t* n_corner, float* surf_out, size_t* n_surf,
+                         int32_t* label_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -269,6 +269,25 @@ def transform_update(pose, imu_available=False, imu_roll=0.0, imu_pitch=0.0, imu
     return pose
 
 
+def extract_features(pts, point_range, point_col_ind, start_ring, end_ring, edge_threshold=1.0,
+                     surf_threshold=0.1, surf_leaf=0.4):
+    """FeatureExtraction (featureExtraction.cpp:87-245): returns (corner, surf, label)"""
+    pts = _f32(pts)
+    rng = _f32(point_range)
+    col = np.ascontiguousarray(point_col_ind, np.int32)
+    sr = np.ascontiguousarray(start_ring, np.int32)
+    er = np.ascontiguousarray(end_ring, np.int32)
+    n = len(pts)
+    corner = np.zeros((max(n, 1), 4), np.float32)
+    surf = np.zeros((max(n, 1), 4), np.float32)
+    label = np.zeros(max(n, 1), np.int32)
+    nc, ns = C.c_size_t(0), C.c_size_t(0)
+    lib().orc_extract_features(_p(pts), C.c_size_t(n), _p(rng), _p(col), _p(sr), _p(er), len(sr),
+                               C.c_float(edge_threshold), C.c_float(surf_threshold), C.c_float(surf_leaf),
+                               _p(corner), C.byref(nc), _p(surf), C.byref(ns), _p(label))
+    return corner[:nc.value].copy(), surf[:ns.value].copy(), label[:n].copy()
+
+
 class MapOptimization:
     """mapOptimization-like object: keyframes, local map, per-scan registration."""
 

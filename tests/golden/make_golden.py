@@ -15,7 +15,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from oracle import pyoracle as O                    # noqa: E402
-from tests.synth import room_world, scan_from_world  # noqa: E402
+from tests.synth import room_world, scan_from_world, ring_scan  # noqa: E402
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 
@@ -52,6 +52,13 @@ def main():
                         final_pose=pose, iterations=np.int32(res.iterations), converged=np.int32(res.converged),
                         n_sel=np.array(res.n_sel[:res.iterations], np.int32),
                         pose_iter=np.array([list(res.pose_iter[i]) for i in range(res.iterations)], np.float32))
+    # 3. FeatureExtraction ("next" row 8f-1)
+    frng = np.random.default_rng(77)
+    fpts, frg, fcol, fsr, fer = ring_scan(frng, 8, 600)
+    fc, fs, fl = O.extract_features(fpts, frg, fcol, fsr, fer, edge_threshold=0.5)
+    np.savez_compressed(os.path.join(HERE, "features.npz"), pts=fpts, point_range=frg, point_col_ind=fcol,
+                        start_ring_index=fsr, end_ring_index=fer, edge_threshold=np.float32(0.5), corner=fc, surf=fs,
+                        label=fl.astype(np.int8))
     print("golden vectors written to", HERE)
 
 

@@ -85,3 +85,42 @@ def corridor_world(rng, n_surf=40000, n_corner=6000, length=30.0, half_w=2.0, he
     def with_i(p):
         return np.concatenate([p, rng.uniform(0, 255, (len(p), 1))], axis=1).astype(np.float32)
     return with_i(corner), with_i(surf)
+
+
+def ring_scan(rng, n_scan=16, horizon=1800, drop=0.03, noise=0.01, elev=(-15.0, 15.0), n_pillars=14):
+    """A deskewed, ring-ordered cloud with the CloudInfo side channels of imageProjection.cpp:624-647:
+    returns (pts [n,4], point_range, point_col_ind, start_ring_index, end_ring_index).  Scene: a box
+    room with square pillars, so that there are depth discontinuities (edge features)."""
+    pillars = [(rng.uniform(-4, 4), rng.uniform(-3, 3), rng.uniform(0.15, 0.4)) for _ in range(n_pillars)]
+    pts, rg, col, sr, er = [], [], [], [], []
+    count = 0
+    for r in range(n_scan):
+        sr.append(count - 1 + 5)
+        el = np.deg2rad(elev[0] + (elev[1] - elev[0]) * r / max(1, n_scan - 1))
+        for c in range(horizon):
+            if rng.uniform() < drop:
+                continue
+            az = 2 * np.pi * c / horizon
+            d = np.array([np.cos(el) * np.cos(az), np.cos(el) * np.sin(az), np.sin(el)])
+            ts = []
+            for ax, half in ((0, 5.0), (1, 4.0), (2, 1.5)):
+                if abs(d[ax]) > 1e-9:
+                    ts.append(half / abs(d[ax]))
+            t = min(ts)
+            for (px, py, hw) in pillars:          # axis-aligned square pillars, full height
+                for ax, ctr, oth, octr in ((0, px, 1, py), (1, py, 0, px)):
+                    if abs(d[ax]) < 1e-9:
+                        continue
+                    for face in (ctr - hw, ctr + hw):
+                        tt = face / d[ax]
+                        if 0.3 < tt < t and abs(d[oth] * tt - octr) <= hw:
+                            t = tt
+            t += rng.normal(0, noise)
+            p = d * t
+            pts.append([p[0], p[1], p[2], float(r) + c / 10000.0])
+            rg.append(t)
+            col.append(c)
+            count += 1
+        er.append(count - 1 - 5)
+    return (np.array(pts, np.float32), np.array(rg, np.float32), np.array(col, np.int32),
+            np.array(sr, np.int32), np.array(er, np.int32))

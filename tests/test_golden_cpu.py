@@ -36,6 +36,18 @@ def test_oracle_matches_golden_registration():
     assert np.abs(pose - z["truth"])[3:].max() < 0.02 and np.abs(pose - z["truth"])[:3].max() < 0.005
 
 
+def test_oracle_matches_golden_features():
+    z = np.load(os.path.join(G, "features.npz"))
+    c, s, l = O.extract_features(z["pts"], z["point_range"], z["point_col_ind"], z["start_ring_index"],
+                                 z["end_ring_index"], edge_threshold=float(z["edge_threshold"]))
+    assert np.array_equal(c, z["corner"]) and np.array_equal(s, z["surf"]) and np.array_equal(l, z["label"])
+    assert len(c) > 10 and len(s) > 100
+    # every corner is an input point with label 1, in ring order
+    lab1 = np.flatnonzero(l == 1)
+    assert len(lab1) == len(c)
+    assert {tuple(r) for r in c} == {tuple(r) for r in z["pts"][lab1]}
+
+
 def _declared_symbols():
     text = open(os.path.join(ROOT, "include", "lvreg.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
