@@ -150,9 +150,13 @@ __global__ void __launch_bounds__(256) fe_ring_kernel(const float* __restrict__ 
                     picked[ind + l - lo] = 1;
                 }
             };
+            // [sp, ep) is sorted ascending and position ep is unsorted, so both greedy loops can stop
+            // as soon as the sorted part can no longer satisfy their threshold (same result as the
+            // reference's full sweeps, which only test and skip from there on)
             int largest = 0;
             for (int k = ep; k >= sp; --k) {
                 const int ind = sorted_ind(k);
+                if (k < ep && !(curv[ind - lo] > edge_th)) break;
                 if (picked[ind - lo] == 0 && curv[ind - lo] > edge_th) {
                     ++largest;
                     if (largest <= kFeMaxCorner) {
@@ -167,7 +171,8 @@ __global__ void __launch_bounds__(256) fe_ring_kernel(const float* __restrict__ 
             }
             for (int k = sp; k <= ep; ++k) {
                 const int ind = sorted_ind(k);
-                if (picked[ind - lo] == 0 && curv[ind - lo] < surf_th) {
+                if (k < ep && !(curv[ind - lo] < surf_th)) k = ep - 1;      // jump to the unsorted tail element
+                else if (picked[ind - lo] == 0 && curv[ind - lo] < surf_th) {
                     label[ind - lo] = -1;
                     picked[ind - lo] = 1;
                     mark_neighbours(ind);
@@ -191,18 +196,17 @@ __global__ void __launch_bounds__(256) fe_corner_gather_kernel(const float4* __r
                                                                const int32_t* __restrict__ corner_idx,
                                                                const int32_t* __restrict__ corner_cnt, int n_scan,
                                                                float4* __restrict__ out, uint32_t* __restrict__ total) {
-    __shared__ int offs[257];
+    __shared__ int off_s;
+    const int r = blockIdx.x;                     // one block per ring
     if (threadIdx.x == 0) {
         int s = 0;
-        for (int r = 0; r < n_scan; ++r) { offs[r] = s; s += corner_cnt[r]; }
-        offs[n_scan] = s;
-        *total = (uint32_t)s;
+        for (int q = 0; q < r; ++q) s += corner_cnt[q];
+        off_s = s;
+        if (r == n_scan - 1) *total = (uint32_t)(s + corner_cnt[r]);
     }
     __syncthreads();
-    for (int r = 0; r < n_scan; ++r) {
-        const int c = corner_cnt[r];
-        for (int t = threadIdx.x; t < c; t += blockDim.x) out[offs[r] + t] = pts[corner_idx[r * kFeCornerStride + t]];
-    }
+    const int c = corner_cnt[r];
+    for (int t = threadIdx.x; t < c; t += blockDim.x) out[off_s + t] = pts[corner_idx[r * kFeCornerStride + t]];
 }
 
 struct FlagIn {

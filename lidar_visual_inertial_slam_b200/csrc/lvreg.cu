@@ -1470,7 +1470,7 @@ int lvreg_extract_features(lvreg_handle* h, const lvreg_cloud* deskewed, const l
                                              h->feat_label.as<int8_t>(), h->feat_flag.as<uint32_t>(),
                                              h->feat_ringof.as<uint8_t>(), h->feat_cidx.as<int32_t>(),
                                              h->feat_ccnt.as<int32_t>(), d_err);
-    fe_corner_gather_kernel<<<1, 256, 0, h->st>>>(h->feat_pts.as<float4>(), h->feat_cidx.as<int32_t>(),
+    fe_corner_gather_kernel<<<ns, 256, 0, h->st>>>(h->feat_pts.as<float4>(), h->feat_cidx.as<int32_t>(),
                                                   h->feat_ccnt.as<int32_t>(), ns, h->feat_corner.as<float4>(), d_small + SM_TOTAL);
     launched(h, 3);
     exclusive_scan(FlagIn{h->feat_flag.as<uint32_t>()}, CompactOut{h->feat_pos.as<uint32_t>(), h->feat_cand.as<uint32_t>()}, n,
