@@ -285,9 +285,14 @@ struct VgJob {
 int voxelgrid_batch(lvreg_handle* h, VgJob* jobs, int nj) {
     unsigned mask = 0;
     for (int j = 0; j < nj; ++j) mask |= 1u << jobs[j].lane;
+    // the largest cloud is the critical path: enqueue its work first in every phase
+    int order[kLanes] = {0, 1, 2, 3};
+    for (int a2 = 0; a2 < nj; ++a2)
+        for (int b2 = a2 + 1; b2 < nj; ++b2)
+            if (jobs[order[b2]].n > jobs[order[a2]].n) { int t2 = order[a2]; order[a2] = order[b2]; order[b2] = t2; }
     // ---- phase 1: (transform + concatenate +) bounding box ----
-    for (int j = 0; j < nj; ++j) {
-        VgJob& J = jobs[j];
+    for (int jo = 0; jo < nj; ++jo) {
+        VgJob& J = jobs[order[jo]];
         Lane& L = h->lane[J.lane];
         *J.n_out = 0;
         J.passthrough = 0;
@@ -314,8 +319,8 @@ int voxelgrid_batch(lvreg_handle* h, VgJob* jobs, int nj) {
     }
     CK(lanes_sync(h, mask));
     // ---- phase 2: keys, stable sort, run heads ----
-    for (int j = 0; j < nj; ++j) {
-        VgJob& J = jobs[j];
+    for (int jo = 0; jo < nj; ++jo) {
+        VgJob& J = jobs[order[jo]];
         if (J.n == 0) continue;
         Lane& L = h->lane[J.lane];
         for (int a = 0; a < 3; ++a) {
@@ -347,13 +352,16 @@ int voxelgrid_batch(lvreg_handle* h, VgJob* jobs, int nj) {
         vs.mul[2] = div_b[0] * div_b[1];
         vs.key_bits = bits_for((uint64_t)div_b[0] * div_b[1] * div_b[2] - 1);
         CKS(ensure_sort_buffers(h, L, J.n));
-        voxel_keys_kernel<<<nblk(J.n, 256), 256, 0, L.st>>>(J.pts, J.n, vs, L.keys[0].as<uint32_t>(), L.vals[0].as<uint32_t>());
+        radix_sort_prepare(L.sort_scratch.as<uint32_t>(), J.n, vs.key_bits, L.st);
+        voxel_keys_kernel<<<min(nblk(J.n, 256 * 8), (uint32_t)h->num_sms * 8), 256, 0, L.st>>>(
+            J.pts, J.n, vs, L.keys[0].as<uint32_t>(), L.vals[0].as<uint32_t>(),
+            sort_ghist_ptr(L.sort_scratch.as<uint32_t>(), J.n), sort_num_passes(vs.key_bits));
         launched(h);
         if (J.d_point_keys)
             CK(cudaMemcpyAsync(J.d_point_keys, L.keys[0].p, (size_t)J.n * 4, cudaMemcpyDeviceToDevice, L.st));
-        J.cur = radix_sort_pairs(L.keys[0].as<uint32_t>(), L.vals[0].as<uint32_t>(), L.keys[1].as<uint32_t>(),
-                                 L.vals[1].as<uint32_t>(), J.n, vs.key_bits, L.sort_scratch.as<uint32_t>(), L.st,
-                                 &h->call_launches);
+        J.cur = radix_sort_run(L.keys[0].as<uint32_t>(), L.vals[0].as<uint32_t>(), L.keys[1].as<uint32_t>(),
+                               L.vals[1].as<uint32_t>(), J.n, vs.key_bits, L.sort_scratch.as<uint32_t>(), true, L.st,
+                               &h->call_launches);
         CK(L.vox_start.reserve((size_t)J.n * 4));
         uint32_t* d_nvox = L.small.as<uint32_t>() + SM_NVOX;
         exclusive_scan(HeadFlagIn{L.keys[J.cur].as<uint32_t>()}, VoxelStartOut{L.vox_start.as<uint32_t>()}, J.n,
@@ -362,8 +370,8 @@ int voxelgrid_batch(lvreg_handle* h, VgJob* jobs, int nj) {
     }
     CK(lanes_sync(h, mask));
     // ---- phase 3: centroids (left running on the lane streams) ----
-    for (int j = 0; j < nj; ++j) {
-        VgJob& J = jobs[j];
+    for (int jo = 0; jo < nj; ++jo) {
+        VgJob& J = jobs[order[jo]];
         if (J.n == 0 || J.passthrough) continue;
         Lane& L = h->lane[J.lane];
         const uint32_t nvox = L.pinned[8];

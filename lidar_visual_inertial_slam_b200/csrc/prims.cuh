@@ -332,23 +332,65 @@ inline size_t sort_scratch_words(uint32_t n) {
     return (size_t)kSortMaxPasses * 256 * sort_num_blocks(n) + kSortMaxPasses * 256 + 8;
 }
 
-// Sorts (keys, vals) by the low `key_bits` bits of key, stable.  Ping-pongs between the two
-// buffer pairs; returns 0 when the result is in (keys0, vals0), 1 when in (keys1, vals1).
-inline int radix_sort_pairs(uint32_t* keys0, uint32_t* vals0, uint32_t* keys1, uint32_t* vals1,
-                            uint32_t n, int key_bits, uint32_t* scratch, cudaStream_t st,
-                            int* launches) {
+inline int sort_num_passes(int key_bits) {
+    int passes = key_bits <= 0 ? 1 : (key_bits + 7) / 8;
+    return passes > kSortMaxPasses ? kSortMaxPasses : passes;
+}
+inline uint32_t* sort_ghist_ptr(uint32_t* scratch, uint32_t n) {
+    return scratch + (size_t)kSortMaxPasses * 256 * sort_num_blocks(n);
+}
+
+// zeroes the look-back status words, the digit histograms and the tickets; must precede the
+// histogram producer (rs_global_hist_kernel, or a key-generating kernel that accumulates the
+// histograms itself through HistAccumulator)
+inline void radix_sort_prepare(uint32_t* scratch, uint32_t n, int key_bits, cudaStream_t st) {
+    const uint32_t nblocks = sort_num_blocks(n);
+    const int passes = sort_num_passes(key_bits);
+    cudaMemsetAsync(scratch, 0, ((size_t)passes * 256 * nblocks) * sizeof(uint32_t), st);
+    cudaMemsetAsync(sort_ghist_ptr(scratch, n), 0, (kSortMaxPasses * 256 + 8) * sizeof(uint32_t), st);
+}
+
+// per-block digit histograms of all passes, accumulated by a kernel that already has the keys in
+// registers (saves the separate histogram read of the keys)
+struct HistAccumulator {
+    uint32_t (*hist)[kSortMaxPasses][256];     // shared memory, one copy per warp
+    __device__ __forceinline__ void init(uint32_t (*smem)[kSortMaxPasses][256]) {
+        hist = smem;
+        for (int i = threadIdx.x; i < 8 * kSortMaxPasses * 256; i += blockDim.x) (&hist[0][0][0])[i] = 0;
+        __syncthreads();
+    }
+    __device__ __forceinline__ void add(uint32_t key, int passes) {
+        const int warp = threadIdx.x >> 5;
+#pragma unroll
+        for (int p = 0; p < kSortMaxPasses; ++p)
+            if (p < passes) atomicAdd(&hist[warp][p][(key >> (8 * p)) & 255u], 1u);
+    }
+    __device__ __forceinline__ void flush(uint32_t* ghist, int passes) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < passes * 256; i += blockDim.x) {
+            uint32_t s = 0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) s += (&hist[w][0][0])[i];
+            if (s) atomicAdd(&ghist[i], s);
+        }
+    }
+};
+
+// the passes proper; `hist_ready` = the histograms were accumulated by the key producer
+inline int radix_sort_run(uint32_t* keys0, uint32_t* vals0, uint32_t* keys1, uint32_t* vals1, uint32_t n,
+                          int key_bits, uint32_t* scratch, bool hist_ready, cudaStream_t st, int* launches) {
     if (n == 0) return 0;
     const uint32_t nblocks = sort_num_blocks(n);
-    int passes = key_bits <= 0 ? 1 : (key_bits + 7) / 8;
-    if (passes > kSortMaxPasses) passes = kSortMaxPasses;
+    const int passes = sort_num_passes(key_bits);
     uint32_t* status = scratch;
-    uint32_t* ghist = scratch + (size_t)kSortMaxPasses * 256 * nblocks;
+    uint32_t* ghist = sort_ghist_ptr(scratch, n);
     uint32_t* tickets = ghist + kSortMaxPasses * 256;
-    cudaMemsetAsync(scratch, 0, ((size_t)passes * 256 * nblocks) * sizeof(uint32_t), st);
-    cudaMemsetAsync(ghist, 0, (kSortMaxPasses * 256 + 8) * sizeof(uint32_t), st);
-    uint32_t hb = (n + 256 * 16 - 1) / (256 * 16);
-    if (hb > (uint32_t)kNumSMs * 8) hb = kNumSMs * 8;
-    rs_global_hist_kernel<<<hb, 256, 0, st>>>(keys0, n, passes, ghist);
+    if (!hist_ready) {
+        uint32_t hb = (n + 256 * 16 - 1) / (256 * 16);
+        if (hb > (uint32_t)kNumSMs * 8) hb = kNumSMs * 8;
+        rs_global_hist_kernel<<<hb, 256, 0, st>>>(keys0, n, passes, ghist);
+        if (launches) *launches += 1;
+    }
     int cur = 0;
     for (int p = 0; p < passes; ++p) {
         const uint32_t* kin = cur ? keys1 : keys0;
@@ -359,8 +401,18 @@ inline int radix_sort_pairs(uint32_t* keys0, uint32_t* vals0, uint32_t* keys1, u
                                                              status + (size_t)p * 256 * nblocks, tickets + p);
         cur ^= 1;
     }
-    if (launches) *launches += 1 + passes;
+    if (launches) *launches += passes;
     return cur;
+}
+
+// Sorts (keys, vals) by the low `key_bits` bits of key, stable.  Ping-pongs between the two
+// buffer pairs; returns 0 when the result is in (keys0, vals0), 1 when in (keys1, vals1).
+inline int radix_sort_pairs(uint32_t* keys0, uint32_t* vals0, uint32_t* keys1, uint32_t* vals1,
+                            uint32_t n, int key_bits, uint32_t* scratch, cudaStream_t st,
+                            int* launches) {
+    if (n == 0) return 0;
+    radix_sort_prepare(scratch, n, key_bits, st);
+    return radix_sort_run(keys0, vals0, keys1, vals1, n, key_bits, scratch, false, st, launches);
 }
 
 }  // namespace lvreg

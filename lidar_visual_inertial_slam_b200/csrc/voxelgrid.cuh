@@ -140,17 +140,25 @@ struct VoxelSpec {
     int key_bits;        // bits needed for the largest idx
 };
 
+// grid-stride; also accumulates the radix-sort digit histograms of the keys it produces
 __global__ void __launch_bounds__(256) voxel_keys_kernel(const float4* __restrict__ pts, uint32_t n,
                                                          VoxelSpec vs, uint32_t* __restrict__ keys,
-                                                         uint32_t* __restrict__ vals) {
-    uint32_t i = blockIdx.x * 256 + threadIdx.x;
-    if (i >= n) return;
-    float4 p = ld_stream(pts + i);
-    int ix = (int)(floorf(p.x * vs.inv) - (float)vs.min_b[0]);
-    int iy = (int)(floorf(p.y * vs.inv) - (float)vs.min_b[1]);
-    int iz = (int)(floorf(p.z * vs.inv) - (float)vs.min_b[2]);
-    keys[i] = (uint32_t)(ix * vs.mul[0] + iy * vs.mul[1] + iz * vs.mul[2]);
-    vals[i] = i;
+                                                         uint32_t* __restrict__ vals, uint32_t* __restrict__ ghist,
+                                                         int passes) {
+    __shared__ uint32_t hist_s[8][kSortMaxPasses][256];
+    HistAccumulator acc;
+    acc.init(hist_s);
+    for (uint32_t i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+        float4 p = ld_stream(pts + i);
+        int ix = (int)(floorf(p.x * vs.inv) - (float)vs.min_b[0]);
+        int iy = (int)(floorf(p.y * vs.inv) - (float)vs.min_b[1]);
+        int iz = (int)(floorf(p.z * vs.inv) - (float)vs.min_b[2]);
+        const uint32_t key = (uint32_t)(ix * vs.mul[0] + iy * vs.mul[1] + iz * vs.mul[2]);
+        keys[i] = key;
+        vals[i] = i;
+        acc.add(key, passes);
+    }
+    acc.flush(ghist, passes);
 }
 
 // ---- run heads -> voxel starts -----------------------------------------------------------------
