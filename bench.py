@@ -232,8 +232,11 @@ def main():
     use_dist = world > 1
     multi.init(backend="nccl", device=torch.device("cuda", local_rank))     # barrier + timing reduce only
 
-    stream = torch.cuda.current_stream().cuda_stream
-    h = lv.Lvreg(device=local_rank, stream=stream)
+    # the library launches on THIS stream (its four lanes fork from / join into it), and the
+    # torch.cuda.Event pairs below are recorded on it
+    tstream = torch.cuda.Stream(device=local_rank)
+    torch.cuda.set_stream(tstream)
+    h = lv.Lvreg(device=local_rank, stream=tstream.cuda_stream)
     seed = multi.sequence_seed(SEED, rank)                            # independent sequence per GPU
     ds = make_dataset(args.workload, seed, lambda p, leaf: h.voxelgrid(p, leaf)[0], log)
     for i in range(len(ds["kf_pose"])):
