@@ -197,8 +197,7 @@ __global__ void __launch_bounds__(kSortThreads, 4) rs_onesweep_kernel(
     uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, uint32_t n, int shift,
     const uint32_t* __restrict__ ghist /*256, this pass*/, volatile uint32_t* status /*[tiles][256]*/,
     uint32_t* ticket) {
-    __shared__ uint32_t sk[kSortTile];
-    __shared__ uint32_t sv[kSortTile];
+    __shared__ uint2 skv[kSortTile];         // (key, payload) staged together: one 64-bit access each way
     __shared__ uint32_t wcnt[kSortWarps][256];
     __shared__ uint32_t gofs[256];          // global offset of a digit run minus its tile-local start
     __shared__ uint32_t scan_ws[8];
@@ -309,8 +308,7 @@ __global__ void __launch_bounds__(kSortThreads, 4) rs_onesweep_kernel(
     for (int r = 0; r < kSortItems; ++r) {
         const uint32_t dd = (k[r] >> shift) & 255u;
         const uint32_t pos = wcnt[warp][dd] + rank[r];
-        sk[pos] = k[r];
-        sv[pos] = v[r];
+        skv[pos] = make_uint2(k[r], v[r]);
     }
     __syncthreads();
     const uint32_t tile_n = min((uint32_t)kSortTile, n - tile * kSortTile);
@@ -318,10 +316,10 @@ __global__ void __launch_bounds__(kSortThreads, 4) rs_onesweep_kernel(
     for (int r = 0; r < kSortItems; ++r) {
         const uint32_t e = r * kSortThreads + threadIdx.x;
         if (e < tile_n) {
-            const uint32_t key = sk[e];
-            const uint32_t dst = gofs[(key >> shift) & 255u] + e;
-            keys_out[dst] = key;
-            vals_out[dst] = sv[e];
+            const uint2 kv = skv[e];
+            const uint32_t dst = gofs[(kv.x >> shift) & 255u] + e;
+            keys_out[dst] = kv.x;
+            vals_out[dst] = kv.y;
         }
     }
 }
