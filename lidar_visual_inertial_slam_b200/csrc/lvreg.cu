@@ -1599,6 +1599,15 @@ int lvreg_bench_sort(lvreg_handle* h, size_t n_, int key_bits, int repeats, floa
     return LVREG_OK;
 }
 
+#ifdef LVREG_SORT_PROF
+extern "C" int lvreg_debug_sort_prof(unsigned long long* out, int reset) {
+    if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(g_sort_prof, z, sizeof(z)); return 0; }
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, g_sort_prof, 16 * sizeof(unsigned long long));
+    return 0;
+}
+#endif
+
 // ---- measurement ---------------------------------------------------------------------------------
 int lvreg_get_timings(const lvreg_handle* h, lvreg_timings* t) {
     if (!h || !t) return LVREG_ERR_INVALID;

@@ -192,6 +192,14 @@ __global__ void __launch_bounds__(256) rs_global_hist_kernel(const uint32_t* __r
     }
 }
 
+#ifdef LVREG_SORT_PROF
+// debug build only: per-phase clock cycles summed over tiles (thread 0 of every block)
+__device__ unsigned long long g_sort_prof[16];
+#define SORT_STAMP(k) do { if (threadIdx.x == 0) { long long t_ = clock64(); atomicAdd(&g_sort_prof[k], (unsigned long long)(t_ - t_prev_)); t_prev_ = t_; } } while (0)
+#else
+#define SORT_STAMP(k) do {} while (0)
+#endif
+
 __global__ void __launch_bounds__(kSortThreads, 4) rs_onesweep_kernel(
     const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
     uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, uint32_t n, int shift,
@@ -200,39 +208,58 @@ __global__ void __launch_bounds__(kSortThreads, 4) rs_onesweep_kernel(
     __shared__ uint2 skv[kSortTile];         // (key, payload) staged together: one 64-bit access each way
     __shared__ uint32_t wcnt[kSortWarps][256];
     __shared__ uint32_t gofs[256];          // global offset of a digit run minus its tile-local start
-    __shared__ uint32_t scan_ws[8];
+    __shared__ uint32_t scan_ws[2][8];
     __shared__ uint32_t tile_s;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#ifdef LVREG_SORT_PROF
+    long long t_prev_ = clock64();
+#endif
     if (threadIdx.x == 0) tile_s = atomicAdd(ticket, 1u);
     for (int i = threadIdx.x; i < kSortWarps * 256; i += kSortThreads) (&wcnt[0][0])[i] = 0;
     __syncthreads();
     const uint32_t tile = tile_s;
+    SORT_STAMP(0);
 
     // ---- rank the tile's elements (stable) ----
     const uint32_t base = tile * kSortTile + warp * (32 * kSortItems);
-    uint32_t k[kSortItems], v[kSortItems];
+    uint32_t k[kSortItems];
     uint16_t rank[kSortItems];
 #pragma unroll
     for (int r = 0; r < kSortItems; ++r) {
         const uint32_t i = base + r * 32 + lane;
-        const bool valid = i < n;
-        k[r] = valid ? keys_in[i] : 0xffffffffu;     // padding sorts last inside the (final) tile
-        v[r] = valid ? vals_in[i] : 0u;
+        k[r] = i < n ? keys_in[i] : 0xffffffffu;        // padding sorts last inside the (final) tile
     }
-    // all matches first (independent, pipelined), then the short serial chain of counter updates
-    uint32_t peers[kSortItems];
-#pragma unroll
-    for (int r = 0; r < kSortItems; ++r) peers[r] = __match_any_sync(0xffffffffu, (k[r] >> shift) & 255u);
+#ifdef LVREG_SORT_PROF
+    if (k[0] == 0x12345678u && k[kSortItems - 1] == 0x9abcdef0u) t_prev_ += 1;   // wait for the loads
+    SORT_STAMP(1);
+#endif
 #pragma unroll
     for (int r = 0; r < kSortItems; ++r) {
+        // lanes with the same digit, from 8 ballots: the hardware match.any iterates over the
+        // distinct values in the warp (~30 here) and measured ~2x slower under load
         const uint32_t d = (k[r] >> shift) & 255u;
-        const int leader = __ffs(peers[r]) - 1;
+        uint32_t peers = 0xffffffffu;
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            const bool bit = (d >> b) & 1u;
+            const uint32_t bal = __ballot_sync(0xffffffffu, bit);
+            peers &= bit ? bal : ~bal;
+        }
+        // the counters are private to the warp and each digit has one leader: a plain
+        // read-modify-write is enough (a shared-memory atomic with a result is slower)
+        const int leader = __ffs(peers) - 1;
         uint32_t old = 0;
-        if (lane == leader) old = atomicAdd(&wcnt[warp][d], (uint32_t)__popc(peers[r]));
+        if (lane == leader) {
+            old = wcnt[warp][d];
+            wcnt[warp][d] = old + (uint32_t)__popc(peers);
+        }
+        __syncwarp();
         old = __shfl_sync(0xffffffffu, old, leader);
-        rank[r] = (uint16_t)(old + __popc(peers[r] & ((1u << lane) - 1u)));
+        rank[r] = (uint16_t)(old + __popc(peers & ((1u << lane) - 1u)));
     }
+    SORT_STAMP(2);
     __syncthreads();
+    SORT_STAMP(3);
 
     // ---- per digit: tile count, exclusive prefix over warps, publish, look back ----
     const int d = threadIdx.x;               // one thread per digit
@@ -252,27 +279,32 @@ __global__ void __launch_bounds__(kSortThreads, 4) rs_onesweep_kernel(
     const uint32_t real_cnt = cnt - pad;
     status[(size_t)tile * 256 + d] = (tile == 0 ? kFlagIncl : kFlagAgg) | real_cnt;
 
+    // the payloads are not needed before the staging: load them now, off the ranking's registers
+    uint32_t v[kSortItems];
+#pragma unroll
+    for (int r = 0; r < kSortItems; ++r) {
+        const uint32_t i = base + r * 32 + lane;
+        v[r] = i < n ? vals_in[i] : 0u;
+    }
+
     // exclusive scan of the global histogram (digit bases) and of the tile counts (tile-local starts)
     uint32_t gb, tl;
     {
         const uint32_t gh = ghist[d];
-        uint32_t a = warp_inclusive_scan(gh, lane);
-        if (lane == 31) scan_ws[warp] = a;
+        const uint32_t a = warp_inclusive_scan(gh, lane);
+        const uint32_t b = warp_inclusive_scan(cnt, lane);
+        if (lane == 31) { scan_ws[0][warp] = a; scan_ws[1][warp] = b; }
         __syncthreads();
-        uint32_t wp = 0;
-        for (int w = 0; w < warp; ++w) wp += scan_ws[w];
-        gb = a - gh + wp;
-        __syncthreads();
-        uint32_t b = warp_inclusive_scan(cnt, lane);
-        if (lane == 31) scan_ws[warp] = b;
-        __syncthreads();
-        wp = 0;
-        for (int w = 0; w < warp; ++w) wp += scan_ws[w];
-        tl = b - cnt + wp;
+        uint32_t wa = 0, wb = 0;
+        for (int w = 0; w < warp; ++w) { wa += scan_ws[0][w]; wb += scan_ws[1][w]; }
+        gb = a - gh + wa;
+        tl = b - cnt + wb;
     }
+    SORT_STAMP(4);
     uint32_t excl = 0;
     if (tile > 0) {
-        // decoupled look-back, 16 predecessors per round trip (independent loads in flight)
+        // decoupled look-back, 16 predecessors per round trip (independent loads in flight).
+        // Measured: ~4 round trips + ~9 polls of a predecessor that has not ranked yet per tile.
         constexpr int LB = 16;
         int pred = (int)tile - 1;
         bool done = false;
@@ -287,16 +319,17 @@ __global__ void __launch_bounds__(kSortThreads, 4) rs_onesweep_kernel(
 #pragma unroll
             for (int j = 0; j < LB; ++j) {
                 if (!done) {
-                    uint32_t v = s[j];
-                    while ((v & kFlagMask) == 0) v = status[(size_t)(pred - j) * 256 + d];
-                    excl += v & ~kFlagMask;
-                    if (v & kFlagIncl) done = true;
+                    uint32_t sv = s[j];
+                    while ((sv & kFlagMask) == 0) sv = status[(size_t)(pred - j) * 256 + d];
+                    excl += sv & ~kFlagMask;
+                    if (sv & kFlagIncl) done = true;
                 }
             }
             pred -= LB;
         }
         status[(size_t)tile * 256 + d] = kFlagIncl | (excl + real_cnt);
     }
+    SORT_STAMP(5);
     gofs[d] = gb + excl - tl;
     // tile-local start of each (warp, digit) run
 #pragma unroll
@@ -311,6 +344,7 @@ __global__ void __launch_bounds__(kSortThreads, 4) rs_onesweep_kernel(
         skv[pos] = make_uint2(k[r], v[r]);
     }
     __syncthreads();
+    SORT_STAMP(6);
     const uint32_t tile_n = min((uint32_t)kSortTile, n - tile * kSortTile);
 #pragma unroll
     for (int r = 0; r < kSortItems; ++r) {
@@ -322,6 +356,7 @@ __global__ void __launch_bounds__(kSortThreads, 4) rs_onesweep_kernel(
             vals_out[dst] = kv.y;
         }
     }
+    SORT_STAMP(7);
 }
 
 inline uint32_t sort_num_blocks(uint32_t n) { return (n + kSortTile - 1) / kSortTile; }
