@@ -242,6 +242,68 @@ int lvreg_extract_features(lvreg_handle* h, const lvreg_cloud* deskewed, const l
  * round trip of the features. */
 int lvreg_get_feature_clouds(const lvreg_handle* h, lvreg_cloud* corner, lvreg_cloud* surf);
 
+/* ---- "next" row: loop-closure registration --------------------------------------
+ * Replaces, for the loop-closure thread (MO:523-535 -> performLoopClosure MO:549-628), everything
+ * between the candidate pair and the pose constraint:
+ *   loopFindNearKeyframes  MO:719-741   keyframes [key-n, key+n] (corner then surf of each, under
+ *                                       the stored poses) concatenated + downSizeFilterICP
+ *   pcl::IterativeClosestPoint MO:578-590  point-to-point, 1-NN correspondences within
+ *                                       max_corr_dist, Umeyama/SVD estimate, PCL's
+ *                                       DefaultConvergenceCriteria; align() with identity guess
+ *   getFitnessScore / gates MO:572,592  submap sizes >= 300 / 1000, converged, fitness <= gate
+ *   pose correction        MO:600-609   tCorrect = icp.getFinalTransformation() * tWrong
+ * The gtsam::Pose3 algebra of MO:610-619 (poseFrom.between(poseTo), the noise model) and the
+ * candidate search (MO:630-661, a radius search over a few hundred key poses) stay on the host:
+ * see host/map_optimization.cpp.  The 3x3 cross-covariance is accumulated in double and decomposed
+ * by a one-sided Jacobi SVD in double (Eigen::umeyama works in float; the difference is float
+ * rounding -- stated in DESIGN.md). */
+enum { LVREG_ICP_NOT_CONVERGED = 0, LVREG_ICP_ITERATIONS = 1, LVREG_ICP_TRANSFORM = 2, LVREG_ICP_ABS_MSE = 3,
+       LVREG_ICP_REL_MSE = 4, LVREG_ICP_NO_CORRESPONDENCES = 5, LVREG_ICP_NO_INPUT = 6 };
+enum { LVREG_LOOP_OK = 0, LVREG_LOOP_SUBMAP_TOO_SMALL = 1, LVREG_LOOP_NOT_CONVERGED = 2,
+       LVREG_LOOP_FITNESS_TOO_HIGH = 3 };
+typedef struct lvreg_icp_params {
+    float max_corr_dist;               /* setMaxCorrespondenceDistance, historyKeyframeSearchRadius * 2 */
+    int32_t max_iterations;            /* setMaximumIterations */
+    double transformation_epsilon;     /* setTransformationEpsilon */
+    double euclidean_fitness_epsilon;  /* setEuclideanFitnessEpsilon */
+    float reserved[4];
+} lvreg_icp_params;
+typedef struct lvreg_icp_result {
+    int32_t converged;                 /* hasConverged() */
+    int32_t iterations;                /* nr_iterations_ */
+    int32_t state;                     /* LVREG_ICP_*: which criterion ended the loop */
+    int32_t n_correspondences;         /* kept pairs in the last iteration */
+    double fitness;                    /* getFitnessScore() */
+    double mse;                        /* mean squared correspondence distance of the last iteration */
+    float final_transformation[16];    /* getFinalTransformation(), row-major 4x4 */
+} lvreg_icp_result;
+typedef struct lvreg_loop_result {
+    int32_t status;                    /* LVREG_LOOP_* */
+    int32_t n_source, n_target;        /* cureKeyframeCloud / prevKeyframeCloud sizes */
+    int32_t reserved;
+    lvreg_icp_result icp;
+    float pose_from[6];                /* corrected pose of key_cur {roll,pitch,yaw,x,y,z}: Pose3(RzRyRx, Point3) of MO:606 */
+    float pose_to[6];                  /* stored pose of key_pre, MO:611 */
+    float noise;                       /* (float)getFitnessScore(), the diagonal of the constraint noise, MO:613 */
+    float reserved2;
+} lvreg_loop_result;
+void lvreg_icp_default_params(lvreg_icp_params* p);
+/* loopFindNearKeyframes into slot 0 (ICP source) or 1 (ICP target, also builds its search grid) */
+int lvreg_loop_find_near_keyframes(lvreg_handle* h, int key, int search_num, int slot, size_t* n_out);
+/* setInputSource (slot 0) / setInputTarget (slot 1) from a caller-provided cloud */
+int lvreg_icp_set_cloud(lvreg_handle* h, int slot, const lvreg_cloud* cloud);
+int lvreg_icp_get_cloud(lvreg_handle* h, int slot, lvreg_cloud_out* out, size_t* n);
+/* exact 1-NN of every query in the ICP target ((d2, index) tie-break); idx -1 / d2 +inf when the
+ * target is empty or nothing lies within max_dist (<= 0: unbounded).  Stage-level parity entry. */
+int lvreg_nn1(lvreg_handle* h, const lvreg_cloud* queries, float max_dist, int32_t* idx_out, float* d2_out);
+/* icp.align() + icp.getFitnessScore() on the two slots */
+int lvreg_icp_align(lvreg_handle* h, const lvreg_icp_params* prm, lvreg_icp_result* res);
+/* tCorrect = correction * pclPointToAffine3f(pose) -> {roll,pitch,yaw,x,y,z}; host arithmetic */
+int lvreg_correct_pose(const float* correction4x4, const float pose[6], float out[6]);
+/* performLoopClosure from the submaps on (MO:566-613) for a given candidate pair */
+int lvreg_perform_loop_closure(lvreg_handle* h, int key_cur, int key_pre, int search_num,
+                               const lvreg_icp_params* prm, float fitness_gate, lvreg_loop_result* out);
+
 /* ---- measurement -------------------------------------------------------------------------- */
 int lvreg_get_timings(const lvreg_handle* h, lvreg_timings* t);
 /* Phase profile of the last lvreg_scan2map / lvreg_register_scan launch, from block 0's

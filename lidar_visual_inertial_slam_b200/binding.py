@@ -59,6 +59,31 @@ class Timings(C.Structure):
                 ("kernel_launches", C.c_int32), ("reserved", C.c_int32)]
 
 
+class IcpParams(C.Structure):
+    _fields_ = [("max_corr_dist", C.c_float), ("max_iterations", C.c_int32),
+                ("transformation_epsilon", C.c_double), ("euclidean_fitness_epsilon", C.c_double),
+                ("reserved", C.c_float * 4)]
+
+
+class IcpResult(C.Structure):
+    _fields_ = [("converged", C.c_int32), ("iterations", C.c_int32), ("state", C.c_int32),
+                ("n_correspondences", C.c_int32), ("fitness", C.c_double), ("mse", C.c_double),
+                ("final_transformation", C.c_float * 16)]
+
+    @property
+    def T(self):
+        return np.array(self.final_transformation[:], np.float32).reshape(4, 4)
+
+
+class LoopResult(C.Structure):
+    _fields_ = [("status", C.c_int32), ("n_source", C.c_int32), ("n_target", C.c_int32), ("reserved", C.c_int32),
+                ("icp", IcpResult), ("pose_from", C.c_float * 6), ("pose_to", C.c_float * 6),
+                ("noise", C.c_float), ("reserved2", C.c_float)]
+
+
+ICP_NOT_CONVERGED, ICP_ITERATIONS, ICP_TRANSFORM, ICP_ABS_MSE, ICP_REL_MSE, ICP_NO_CORRESPONDENCES, ICP_NO_INPUT = range(7)
+LOOP_OK, LOOP_SUBMAP_TOO_SMALL, LOOP_NOT_CONVERGED, LOOP_FITNESS_TOO_HIGH = range(4)
+
 _lib = None
 
 
@@ -91,6 +116,23 @@ def default_params(**kw):
     for k, v in kw.items():
         setattr(p, k, v)
     return p
+
+
+def icp_default_params(**kw):
+    p = IcpParams()
+    lib().lvreg_icp_default_params(C.byref(p))
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+def correct_pose(correction4x4, pose):
+    T = np.ascontiguousarray(correction4x4, np.float32).reshape(16)
+    pose = np.ascontiguousarray(pose, np.float32)
+    out = np.zeros(6, np.float32)
+    lib().lvreg_correct_pose(T.ctypes.data_as(C.c_void_p), pose.ctypes.data_as(C.c_void_p),
+                             out.ctypes.data_as(C.c_void_p))
+    return out
 
 
 def pose_to_affine(pose):
@@ -284,6 +326,40 @@ class Lvreg:
 
     def reset_lm_state(self):
         self._ck(self.L.lvreg_reset_lm_state(self.h))
+
+    # ---- loop closure ----
+    def loop_find_near_keyframes(self, key, search_num, slot):
+        n = C.c_size_t(0)
+        self._ck(self.L.lvreg_loop_find_near_keyframes(self.h, int(key), int(search_num), int(slot), C.byref(n)))
+        return n.value
+
+    def icp_set_cloud(self, slot, cloud):
+        c, _keep = _cloud(cloud)
+        self._ck(self.L.lvreg_icp_set_cloud(self.h, int(slot), C.byref(c)))
+
+    def icp_get_cloud(self, slot, pcl_layout=False):
+        return self._get_cloud(self.L.lvreg_icp_get_cloud, slot, pcl_layout)
+
+    def nn1(self, queries, max_dist=0.0):
+        c, _keep = _cloud(queries)
+        idx = np.zeros(c.n, np.int32)
+        d2 = np.zeros(c.n, np.float32)
+        self._ck(self.L.lvreg_nn1(self.h, C.byref(c), C.c_float(max_dist), idx.ctypes.data_as(C.c_void_p),
+                                  d2.ctypes.data_as(C.c_void_p)))
+        return idx, d2
+
+    def icp_align(self, params=None):
+        params = params or icp_default_params()
+        res = IcpResult()
+        self._ck(self.L.lvreg_icp_align(self.h, C.byref(params), C.byref(res)))
+        return res
+
+    def perform_loop_closure(self, key_cur, key_pre, search_num=25, params=None, fitness_gate=0.3):
+        params = params or icp_default_params()
+        out = LoopResult()
+        self._ck(self.L.lvreg_perform_loop_closure(self.h, int(key_cur), int(key_pre), int(search_num),
+                                                   C.byref(params), C.c_float(fitness_gate), C.byref(out)))
+        return out
 
     # ---- stage level ----
     def transform_cloud(self, pts, pose):

@@ -15,6 +15,7 @@
 #include "common.cuh"
 #include "feature.cuh"
 #include "fit.cuh"
+#include "icp.cuh"
 #include "knn.cuh"
 #include "prims.cuh"
 #include "register.cuh"
@@ -97,6 +98,9 @@ struct lvreg_handle {
     MapSide map[2];
     DevBuf scan_ds[2];
     uint32_t n_scan[2] = {0, 0};
+    // loop closure: [0] source (cureKeyframeCloud), [1] target (prevKeyframeCloud) + its search grid
+    MapSide icp_cloud[2];
+    DevBuf icp_cur, icp_partials, icp_state, icp_idx, icp_d2;
     // scratch of the main stream
     DevBuf feat_pts, feat_range, feat_col, feat_rings, feat_curv, feat_picked, feat_label, feat_flag, feat_ringof,
         feat_cidx, feat_ccnt, feat_pos, feat_cand, feat_spec, feat_idx, feat_pidx, feat_corner, feat_surf;
@@ -392,11 +396,12 @@ int voxelgrid_batch(lvreg_handle* h, VgJob* jobs, int nj) {
 }
 
 // ---- search-grid build (on a lane stream; no host synchronisation when the bbox is known) --------
-int build_grid(lvreg_handle* h, Lane& L, MapSide& ms, const float* bb_min, const float* bb_max) {
+int build_grid(lvreg_handle* h, Lane& L, MapSide& ms, const float* bb_min, const float* bb_max,
+               float cell_override = 0.f) {
     const uint32_t m = ms.m;
     GridSpec gs;
     const float gate_r = sqrtf(h->prm.knn_gate_sq);
-    float cell = gate_r * (1.0f + 1.0f / 128.0f);
+    float cell = cell_override > 0.f ? cell_override : gate_r * (1.0f + 1.0f / 128.0f);
     if (m == 0) {
         gs.ox = gs.oy = gs.oz = 0.f;
         gs.cell = cell;
@@ -866,8 +871,9 @@ void lvreg_destroy(lvreg_handle* h) {
     for (int s = 0; s < 2; ++s) {
         h->map[s].ds.release(); h->map[s].cell_pts.release(); h->map[s].cell_start.release();
         h->scan_ds[s].release();
+        h->icp_cloud[s].ds.release(); h->icp_cloud[s].cell_pts.release(); h->icp_cloud[s].cell_start.release();
     }
-    DevBuf* bufs[] = {&h->feat_pts, &h->feat_range, &h->feat_col, &h->feat_rings, &h->feat_curv, &h->feat_picked,
+    DevBuf* bufs[] = {&h->icp_cur, &h->icp_partials, &h->icp_state, &h->icp_idx, &h->icp_d2, &h->feat_pts, &h->feat_range, &h->feat_col, &h->feat_rings, &h->feat_curv, &h->feat_picked,
                       &h->feat_label, &h->feat_flag, &h->feat_ringof, &h->feat_cidx, &h->feat_ccnt, &h->feat_pos,
                       &h->feat_cand, &h->feat_spec, &h->feat_idx, &h->feat_pidx, &h->feat_corner, &h->feat_surf,
                       &h->vgout, &h->partials, &h->regout, &h->lmstate, &h->posebuf, &h->tilectr, &h->tilens, &h->qbuf,
@@ -1607,6 +1613,292 @@ extern "C" int lvreg_debug_sort_prof(unsigned long long* out, int reset) {
     return 0;
 }
 #endif
+
+
+// ---- loop closure ---------------------------------------------------------------------
+namespace {
+
+constexpr float kIcpCell = 1.0f;          // search-grid cell of the ICP target, metres
+constexpr size_t kPinnedIcpState = 48 * 1024;
+
+// loopFindNearKeyframes for one slot: fills the lane's segment list and the VoxelGrid job
+int prepare_loop_job(lvreg_handle* h, int key, int search_num, int slot, VgJob& J) {
+    Lane& L = h->lane[slot];
+    MapSide& ms = h->icp_cloud[slot];
+    L.seg_host.clear();
+    uint64_t total = 0;
+    const int K = (int)h->kfs.size();
+    for (int i = -search_num; i <= search_num; ++i) {
+        const int k = key + i;
+        if (k < 0 || k >= K) continue;
+        const Keyframe* kf = h->kfs[k];
+        for (int s = 0; s < 2; ++s) {              // corner, then surf, of every keyframe (MO:730-731)
+            if (kf->n[s] == 0) continue;
+            Segment sg;
+            sg.src = kf->cloud[s].as<float4>();
+            sg.begin = (uint32_t)total;
+            sg.n = kf->n[s];
+            pose_to_affine_host(kf->pose, sg.T.m);
+            L.seg_host.push_back(sg);
+            total += kf->n[s];
+        }
+    }
+    if (total > 0x7fffffffull) return fail(h, LVREG_ERR_INVALID, "loop-closure submap too large");
+    ms.n_in = total;
+    ms.valid = false;
+    J = VgJob();
+    J.lane = slot;
+    J.n = (uint32_t)total;
+    J.from_segments = true;
+    J.leaf = h->prm.surf_leaf;                     // downSizeFilterICP, MO:249
+    J.out = &ms.ds;
+    J.n_out = &ms.m;
+    return LVREG_OK;
+}
+
+IcpParams icp_params_dev(const lvreg_icp_params* p) {
+    IcpParams P;
+    P.max_d2 = (double)p->max_corr_dist * (double)p->max_corr_dist;
+    P.rot_thr = 1.0 - p->transformation_epsilon;
+    P.trans_thr = p->transformation_epsilon;
+    P.rel_mse = p->euclidean_fitness_epsilon;
+    P.abs_mse = 1e-12;
+    P.max_iterations = p->max_iterations;
+    return P;
+}
+
+int icp_align_impl(lvreg_handle* h, const lvreg_icp_params* prm, lvreg_icp_result* res) {
+    memset(res, 0, sizeof(*res));
+    for (int i = 0; i < 4; ++i) res->final_transformation[i * 5] = 1.f;
+    res->fitness = 1.7976931348623157e308;
+    const uint32_t ns = h->icp_cloud[0].m, nt = h->icp_cloud[1].m;
+    if (!h->icp_cloud[0].valid || !h->icp_cloud[1].valid) return fail(h, LVREG_ERR_NO_MAP, "ICP source / target not set");
+    if (ns == 0 || nt == 0) { res->state = ICP_NO_INPUT; return LVREG_OK; }
+    if (prm->max_iterations < 1) return fail(h, LVREG_ERR_INVALID, "max_iterations < 1");
+    const IcpParams P = icp_params_dev(prm);
+    const uint32_t nb = nblk(ns, kIcpThreads);
+    CK(h->icp_cur.reserve((size_t)ns * 16));
+    CK(h->icp_partials.reserve((size_t)nb * kIcpMoments * 8));
+    CK(h->icp_state.reserve(sizeof(IcpState)));
+    IcpState* hs = (IcpState*)((char*)h->pinned + kPinnedIcpState);
+    memset(hs, 0, sizeof(*hs));
+    hs->mse_prev = 1.7976931348623157e308;
+    for (int i = 0; i < 4; ++i) hs->T_final[i * 5] = hs->T_inc[i * 5] = 1.f;
+    CK(cudaMemcpyAsync(h->icp_state.p, hs, sizeof(IcpState), cudaMemcpyHostToDevice, h->st));
+    CK(cudaMemcpyAsync(h->icp_cur.p, h->icp_cloud[0].ds.p, (size_t)ns * 16, cudaMemcpyDeviceToDevice, h->st));
+    const GridView g = grid_view(h->icp_cloud[1]);
+    IcpState* ds = h->icp_state.as<IcpState>();
+    // the per-iteration decision is taken on the device; the host polls every few iterations
+    const int batch = 4;
+    for (int it = 0; it < prm->max_iterations;) {
+        for (int b = 0; b < batch && it < prm->max_iterations; ++b, ++it) {
+            icp_correspond_kernel<<<nb, kIcpThreads, 0, h->st>>>(h->icp_cur.as<float4>(), ns, g, P, ds,
+                                                               h->icp_partials.as<double>());
+            icp_update_kernel<<<1, kIcpThreads, 0, h->st>>>(h->icp_partials.as<double>(), nb, P, ds);
+            icp_transform_kernel<<<nb, kIcpThreads, 0, h->st>>>(h->icp_cur.as<float4>(), ns, ds);
+            launched(h, 3);
+        }
+        CK(cudaMemcpyAsync(hs, ds, sizeof(IcpState), cudaMemcpyDeviceToHost, h->st));
+        CK(cudaStreamSynchronize(h->st));
+        if (hs->done) break;
+    }
+    // getFitnessScore: the original source under the final transformation, no range cap
+    icp_fitness_kernel<<<nb, kIcpThreads, 0, h->st>>>(h->icp_cloud[0].ds.as<float4>(), ns, g, ds,
+                                                    h->icp_partials.as<double>());
+    icp_fitness_reduce_kernel<<<1, kIcpThreads, 0, h->st>>>(h->icp_partials.as<double>(), nb, ds);
+    launched(h, 2);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(hs, ds, sizeof(IcpState), cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    res->iterations = hs->iterations;
+    res->state = hs->state;
+    res->converged = (hs->state == ICP_ITERATIONS || hs->state == ICP_TRANSFORM || hs->state == ICP_ABS_MSE ||
+                      hs->state == ICP_REL_MSE) ? 1 : 0;
+    res->n_correspondences = hs->n_corr;
+    res->mse = hs->mse;
+    res->fitness = hs->fitness_sum / (double)ns;
+    memcpy(res->final_transformation, hs->T_final, sizeof(hs->T_final));
+    return LVREG_OK;
+}
+
+// 4x4 float product with the coefficient sums taken over k in order
+void mat4_mul_host(const float* A, const float* B, float* C) {
+    float R[16];
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) {
+            float s = A[i * 4 + 0] * B[0 * 4 + j];
+            s = s + A[i * 4 + 1] * B[1 * 4 + j];
+            s = s + A[i * 4 + 2] * B[2 * 4 + j];
+            s = s + A[i * 4 + 3] * B[3 * 4 + j];
+            R[i * 4 + j] = s;
+        }
+    memcpy(C, R, sizeof(R));
+}
+
+}  // namespace
+
+void lvreg_icp_default_params(lvreg_icp_params* p) {
+    if (!p) return;
+    memset(p, 0, sizeof(*p));
+    p->max_corr_dist = 30.0f;                 // historyKeyframeSearchRadius * 2 (MO:580, utility.h:296)
+    p->max_iterations = 100;                  // MO:581
+    p->transformation_epsilon = 1e-6;         // MO:582
+    p->euclidean_fitness_epsilon = 1e-6;      // MO:583
+}
+
+int lvreg_loop_find_near_keyframes(lvreg_handle* h, int key, int search_num, int slot, size_t* n_out) {
+    if (!h || slot < 0 || slot > 1 || search_num < 0) return LVREG_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    if (h->kfs.empty()) return fail(h, LVREG_ERR_NO_KEYFRAMES, "no keyframes");
+    begin_call(h);
+    mark(h, EV_BEGIN);
+    VgJob J;
+    CKS(prepare_loop_job(h, key, search_num, slot, J));
+    lanes_fork(h, 1u << slot);
+    CKS(voxelgrid_batch(h, &J, 1));
+    lanes_join(h, 1u << slot);
+    mark(h, EV_MAP);
+    if (slot == 1) {
+        CKS(build_grid(h, h->lane[slot], h->icp_cloud[1], J.n ? J.mn : nullptr, J.n ? J.mx : nullptr, kIcpCell));
+        lanes_join(h, 1u << slot);
+    }
+    mark(h, EV_GRID);
+    CK(cudaStreamSynchronize(h->st));
+    h->icp_cloud[slot].valid = true;
+    h->last.map_build_ms = span(h, EV_BEGIN, EV_MAP);
+    h->last.grid_build_ms = span(h, EV_MAP, EV_GRID);
+    finish_timings(h);
+    end_call(h);
+    if (n_out) *n_out = h->icp_cloud[slot].m;
+    return LVREG_OK;
+}
+
+int lvreg_icp_set_cloud(lvreg_handle* h, int slot, const lvreg_cloud* cloud) {
+    if (!h || slot < 0 || slot > 1 || !cloud) return LVREG_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    begin_call(h);
+    Lane& L = h->lane[slot];
+    MapSide& ms = h->icp_cloud[slot];
+    ms.valid = false;
+    lanes_fork(h, 1u << slot);
+    CKS(upload_cloud(h, cloud, ms.ds, L.stage, L.st));
+    ms.m = (uint32_t)cloud->n;
+    ms.n_in = cloud->n;
+    if (slot == 1) CKS(build_grid(h, L, ms, nullptr, nullptr, kIcpCell));
+    CK(lanes_sync(h, 1u << slot));
+    ms.valid = true;
+    end_call(h);
+    return LVREG_OK;
+}
+
+int lvreg_icp_get_cloud(lvreg_handle* h, int slot, lvreg_cloud_out* out, size_t* n) {
+    if (!h || slot < 0 || slot > 1) return LVREG_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    if (!h->icp_cloud[slot].valid) return fail(h, LVREG_ERR_NO_MAP, "ICP cloud not set");
+    if (n) *n = h->icp_cloud[slot].m;
+    if (!out) return LVREG_OK;
+    return download_cloud(h, h->icp_cloud[slot].ds.as<float4>(), h->icp_cloud[slot].m, out);
+}
+
+int lvreg_nn1(lvreg_handle* h, const lvreg_cloud* queries, float max_dist, int32_t* idx_out, float* d2_out) {
+    if (!h || !queries || (queries->n && (!idx_out || !d2_out))) return LVREG_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    if (!h->icp_cloud[1].valid) return fail(h, LVREG_ERR_NO_MAP, "ICP target not set");
+    begin_call(h);
+    const uint32_t n = (uint32_t)queries->n;
+    if (n == 0) { end_call(h); return LVREG_OK; }
+    CKS(upload_cloud(h, queries, h->qbuf, h->lane[LANE_SCAN_CORNER].stage, h->st));
+    CK(h->icp_idx.reserve((size_t)n * 4));
+    CK(h->icp_d2.reserve((size_t)n * 4));
+    const float max_d2 = max_dist > 0.f && max_dist < 1e18f ? max_dist * max_dist : INFINITY;
+    nn1_kernel<<<nblk(n, kIcpThreads), kIcpThreads, 0, h->st>>>(h->qbuf.as<float4>(), n, grid_view(h->icp_cloud[1]), max_d2,
+                                                             h->icp_idx.as<int32_t>(), h->icp_d2.as<float>());
+    launched(h);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(idx_out, h->icp_idx.p, (size_t)n * 4, cudaMemcpyDeviceToHost, h->st));
+    CK(cudaMemcpyAsync(d2_out, h->icp_d2.p, (size_t)n * 4, cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    end_call(h);
+    return LVREG_OK;
+}
+
+int lvreg_icp_align(lvreg_handle* h, const lvreg_icp_params* prm, lvreg_icp_result* res) {
+    if (!h || !prm || !res) return LVREG_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    begin_call(h);
+    mark(h, EV_BEGIN);
+    int s = icp_align_impl(h, prm, res);
+    mark(h, EV_REG);
+    CK(cudaStreamSynchronize(h->st));
+    h->last.register_ms = span(h, EV_BEGIN, EV_REG);
+    finish_timings(h);
+    end_call(h);
+    return s;
+}
+
+int lvreg_correct_pose(const float* correction4x4, const float pose[6], float out[6]) {
+    if (!correction4x4 || !pose || !out) return LVREG_ERR_INVALID;
+    float T12[12], W[16], C[16];
+    pose_to_affine_host(pose, T12);              // tWrong = pclPointToAffine3f(copy_cloudKeyPoses6D[loopKeyCur]), MO:602
+    memcpy(W, T12, sizeof(T12));
+    W[12] = W[13] = W[14] = 0.f; W[15] = 1.f;
+    mat4_mul_host(correction4x4, W, C);          // tCorrect = correctionLidarFrame * tWrong, MO:604
+    out[3] = C[3]; out[4] = C[7]; out[5] = C[11];   // pcl::getTranslationAndEulerAngles, MO:605
+    out[0] = atan2f(C[9], C[10]);
+    out[1] = (float)asin((double)-C[8]);
+    out[2] = atan2f(C[4], C[0]);
+    return LVREG_OK;
+}
+
+int lvreg_perform_loop_closure(lvreg_handle* h, int key_cur, int key_pre, int search_num, const lvreg_icp_params* prm,
+                               float fitness_gate, lvreg_loop_result* out) {
+    if (!h || !prm || !out || search_num < 0) return LVREG_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    const int K = (int)h->kfs.size();
+    if (K == 0) return fail(h, LVREG_ERR_NO_KEYFRAMES, "no keyframes");
+    if (key_cur < 0 || key_cur >= K || key_pre < 0 || key_pre >= K) return fail(h, LVREG_ERR_INVALID, "keyframe id out of range");
+    memset(out, 0, sizeof(*out));
+    begin_call(h);
+    mark(h, EV_BEGIN);
+    // both submaps at once, one lane each (MO:569-571)
+    VgJob jobs[2];
+    CKS(prepare_loop_job(h, key_cur, 0, 0, jobs[0]));
+    CKS(prepare_loop_job(h, key_pre, search_num, 1, jobs[1]));
+    lanes_fork(h, 0x3);
+    CKS(voxelgrid_batch(h, jobs, 2));
+    lanes_join(h, 0x3);
+    mark(h, EV_MAP);
+    CKS(build_grid(h, h->lane[1], h->icp_cloud[1], jobs[1].n ? jobs[1].mn : nullptr, jobs[1].n ? jobs[1].mx : nullptr, kIcpCell));
+    lanes_join(h, 0x2);
+    mark(h, EV_GRID);
+    h->icp_cloud[0].valid = h->icp_cloud[1].valid = true;
+    out->n_source = (int32_t)h->icp_cloud[0].m;
+    out->n_target = (int32_t)h->icp_cloud[1].m;
+    int s = LVREG_OK;
+    if (out->n_source < 300 || out->n_target < 1000) {          // MO:572
+        out->status = LVREG_LOOP_SUBMAP_TOO_SMALL;
+    } else {
+        s = icp_align_impl(h, prm, &out->icp);
+        if (s == LVREG_OK) {
+            if (!out->icp.converged) out->status = LVREG_LOOP_NOT_CONVERGED;                 // MO:592
+            else if (out->icp.fitness > (double)fitness_gate) out->status = LVREG_LOOP_FITNESS_TOO_HIGH;
+            else {
+                lvreg_correct_pose(out->icp.final_transformation, h->kfs[key_cur]->pose, out->pose_from);
+                memcpy(out->pose_to, h->kfs[key_pre]->pose, 6 * sizeof(float));              // MO:611
+                out->noise = (float)out->icp.fitness;                                        // MO:613
+                out->status = LVREG_LOOP_OK;
+            }
+        }
+    }
+    mark(h, EV_REG);
+    CK(cudaStreamSynchronize(h->st));
+    h->last.map_build_ms = span(h, EV_BEGIN, EV_MAP);
+    h->last.grid_build_ms = span(h, EV_MAP, EV_GRID);
+    h->last.register_ms = span(h, EV_GRID, EV_REG);
+    finish_timings(h);
+    end_call(h);
+    return s;
+}
 
 // ---- measurement ---------------------------------------------------------------------------------
 int lvreg_get_timings(const lvreg_handle* h, lvreg_timings* t) {

@@ -176,6 +176,48 @@ int orc_extract_features(const float* pts, size_t n, const float* point_range, c
                          float* corner_out, size_t* n_corner, float* surf_out, size_t* n_surf,
                          int32_t* label_out);
 
+/* ---- "next" row: loop-closure ICP, oracle_icp.cpp + oracle_reg.cpp ---------------
+ * pcl::IterativeClosestPoint as configured at MO:578-590, getFitnessScore MO:592, submaps MO:719-741,
+ * candidate search MO:630-661, pose correction MO:600-609.  Header of oracle_icp.cpp lists what is
+ * restated from PCL and the one deliberate deviation (double raw-moment Umeyama). */
+enum { ORC_ICP_NOT_CONVERGED = 0, ORC_ICP_ITERATIONS = 1, ORC_ICP_TRANSFORM = 2, ORC_ICP_ABS_MSE = 3,
+       ORC_ICP_REL_MSE = 4, ORC_ICP_NO_CORRESPONDENCES = 5, ORC_ICP_NO_INPUT = 6 };
+typedef struct orc_icp_params {
+    float max_corr_dist;
+    int max_iterations;
+    double transformation_epsilon;
+    double euclidean_fitness_epsilon;
+    int num_threads;
+} orc_icp_params;
+typedef struct orc_icp_result {
+    int converged, iterations, state, n_correspondences;
+    double fitness, mse;
+    float final_transformation[16];       /* row-major 4x4 */
+} orc_icp_result;
+typedef struct orc_loop_result {
+    int status;                           /* 0 constraint produced, 1 submap too small (MO:572), 2 ICP not converged,
+                                             3 fitness above the gate (MO:592) */
+    int n_source, n_target;
+    orc_icp_result icp;
+    float pose_from[6];                   /* corrected pose of key_cur {r,p,y,x,y,z}, MO:604-609 */
+    float pose_to[6];                     /* stored pose of key_pre, MO:611 */
+    float noise;                          /* (float)getFitnessScore, MO:613 */
+} orc_loop_result;
+void orc_icp_default_params(orc_icp_params* p);
+void orc_umeyama_from_moments(const double* mom17, float* T4x4);
+void orc_nn1(const float* tgt, size_t nt, const float* q, size_t nq, int32_t* idx, float* d2, int num_threads);
+void orc_icp_align(const float* src, size_t ns, const float* tgt, size_t nt, const orc_icp_params* P,
+                   orc_icp_result* res);
+void orc_correct_pose(const float* correction4x4, const float pose[6], float out[6]);
+/* loopFindNearKeyframes into slot 0 (source) or 1 (target); returns the row count */
+size_t orc_mo_loop_find_near_keyframes(orc_mo* mo, int key, int search_num, int slot);
+void   orc_mo_get_loop_cloud(const orc_mo* mo, int slot, float* out);
+/* detectLoopClosureDistance without the loopIndexContainer bookkeeping; returns 1 when a pair was found */
+int    orc_mo_detect_loop_closure_distance(orc_mo* mo, double time_cur, float radius, float time_diff,
+                                           int* key_cur, int* key_pre);
+void   orc_mo_perform_loop_closure(orc_mo* mo, int key_cur, int key_pre, int search_num,
+                                   const orc_icp_params* P, float fitness_gate, orc_loop_result* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -366,6 +366,7 @@ struct orc_mo {
     std::map<int, std::pair<std::vector<float>, std::vector<float>>> cache;   // laserCloudMapContainer
     std::vector<float> corner_map_ds, surf_map_ds;             // laserCloud{Corner,Surf}FromMapDS
     orc_lm_state lm;
+    std::vector<float> loop_cloud[2];                          // cureKeyframeCloud / prevKeyframeCloud
 };
 
 extern "C" orc_mo* orc_mo_create(const orc_params* p) {
@@ -485,4 +486,83 @@ extern "C" void orc_mo_register_scan(orc_mo* mo, const float* corner_raw, size_t
     orc_scan2map(mo->corner_map_ds.data(), mo->corner_map_ds.size() / 4, mo->surf_map_ds.data(),
                  mo->surf_map_ds.size() / 4, cds.data(), nc, sds.data(), ns, pose, &mo->lm, &mo->P, res);
     if (res->status == 0) orc_transform_update(pose, 0, 0, 0, 0, &mo->P);
+}
+
+// ---- loop closure ----------------------------------------------------------------
+// loopFindNearKeyframes, MO:719-741: corner then surf of every keyframe in [key - n, key + n], each
+// under its own stored pose, concatenated in that order, then downSizeFilterICP (leaf =
+// mappingSurfLeafSize, MO:249)
+extern "C" size_t orc_mo_loop_find_near_keyframes(orc_mo* mo, int key, int search_num, int slot) {
+    std::vector<float> cat;
+    const int K = (int)mo->times.size();
+    for (int i = -search_num; i <= search_num; ++i) {
+        const int k = key + i;
+        if (k < 0 || k >= K) continue;
+        float T[12];
+        orc_pose_to_affine(&mo->poses[6 * (size_t)k], T);
+        for (int which = 0; which < 2; ++which) {
+            const std::vector<float>& src = which == 0 ? mo->corner_kf[k] : mo->surf_kf[k];
+            const size_t at = cat.size();
+            cat.resize(at + src.size());
+            orc_transform_cloud(src.data(), src.size() / 4, T, cat.data() + at, mo->P.num_threads);
+        }
+    }
+    std::vector<float>& out = mo->loop_cloud[slot ? 1 : 0];
+    out.clear();
+    if (cat.empty()) return 0;
+    out.resize(cat.size());
+    int pass;
+    const size_t n = orc_voxelgrid(cat.data(), cat.size() / 4, mo->P.surf_leaf, out.data(), nullptr, nullptr, &pass);
+    out.resize(4 * n);
+    return n;
+}
+extern "C" void orc_mo_get_loop_cloud(const orc_mo* mo, int slot, float* out) {
+    const std::vector<float>& v = mo->loop_cloud[slot ? 1 : 0];
+    std::memcpy(out, v.data(), v.size() * sizeof(float));
+}
+
+// detectLoopClosureDistance, MO:630-661: nearest-first radius search around the last key pose, first hit
+// older than time_diff
+extern "C" int orc_mo_detect_loop_closure_distance(orc_mo* mo, double time_cur, float radius, float time_diff,
+                                                   int* key_cur, int* key_pre) {
+    const size_t K = mo->times.size();
+    if (K == 0) return 0;
+    std::vector<float> pos(4 * K);
+    for (size_t i = 0; i < K; ++i) {
+        pos[4 * i + 0] = mo->poses[6 * i + 3];
+        pos[4 * i + 1] = mo->poses[6 * i + 4];
+        pos[4 * i + 2] = mo->poses[6 * i + 5];
+        pos[4 * i + 3] = (float)i;
+    }
+    orc_kdtree* tree = orc_kdtree_build(pos.data(), K);
+    std::vector<int32_t> idx(K);
+    std::vector<float> d2(K);
+    const size_t found = orc_kdtree_radius(tree, &pos[4 * (K - 1)], radius, idx.data(), d2.data(), K);
+    orc_kdtree_free(tree);
+    int pre = -1;
+    for (size_t i = 0; i < found && i < K; ++i)
+        if (std::fabs(mo->times[(size_t)idx[i]] - time_cur) > (double)time_diff) { pre = idx[i]; break; }
+    const int cur = (int)K - 1;
+    if (pre == -1 || pre == cur) return 0;
+    *key_cur = cur;
+    *key_pre = pre;
+    return 1;
+}
+
+// performLoopClosure from the submaps on, MO:566-613
+extern "C" void orc_mo_perform_loop_closure(orc_mo* mo, int key_cur, int key_pre, int search_num,
+                                            const orc_icp_params* P, float fitness_gate, orc_loop_result* out) {
+    std::memset(out, 0, sizeof(*out));
+    const size_t ns = orc_mo_loop_find_near_keyframes(mo, key_cur, 0, 0);
+    const size_t nt = orc_mo_loop_find_near_keyframes(mo, key_pre, search_num, 1);
+    out->n_source = (int)ns;
+    out->n_target = (int)nt;
+    if (ns < 300 || nt < 1000) { out->status = 1; return; }
+    orc_icp_align(mo->loop_cloud[0].data(), ns, mo->loop_cloud[1].data(), nt, P, &out->icp);
+    if (!out->icp.converged) { out->status = 2; return; }
+    if (out->icp.fitness > (double)fitness_gate) { out->status = 3; return; }
+    orc_correct_pose(out->icp.final_transformation, &mo->poses[6 * (size_t)key_cur], out->pose_from);
+    std::memcpy(out->pose_to, &mo->poses[6 * (size_t)key_pre], 6 * sizeof(float));
+    out->noise = (float)out->icp.fitness;
+    out->status = 0;
 }

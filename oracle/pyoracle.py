@@ -59,6 +59,7 @@ def lib():
         _lib.orc_mo_num_keyframes.restype = C.c_size_t
         _lib.orc_mo_extract_nearby.restype = C.c_size_t
         _lib.orc_mo_map_size.restype = C.c_size_t
+        _lib.orc_mo_loop_find_near_keyframes.restype = C.c_size_t
     return _lib
 
 
@@ -288,6 +289,72 @@ def extract_features(pts, point_range, point_col_ind, start_ring, end_ring, edge
     return corner[:nc.value].copy(), surf[:ns.value].copy(), label[:n].copy()
 
 
+# ---- loop-closure ICP, oracle_icp.cpp ------------------------------------------
+class IcpParams(C.Structure):
+    _fields_ = [("max_corr_dist", C.c_float), ("max_iterations", C.c_int),
+                ("transformation_epsilon", C.c_double), ("euclidean_fitness_epsilon", C.c_double),
+                ("num_threads", C.c_int)]
+
+
+class IcpResult(C.Structure):
+    _fields_ = [("converged", C.c_int), ("iterations", C.c_int), ("state", C.c_int),
+                ("n_correspondences", C.c_int), ("fitness", C.c_double), ("mse", C.c_double),
+                ("final_transformation", C.c_float * 16)]
+
+    @property
+    def T(self):
+        return np.array(self.final_transformation[:], np.float32).reshape(4, 4)
+
+
+class LoopResult(C.Structure):
+    _fields_ = [("status", C.c_int), ("n_source", C.c_int), ("n_target", C.c_int), ("icp", IcpResult),
+                ("pose_from", C.c_float * 6), ("pose_to", C.c_float * 6), ("noise", C.c_float)]
+
+
+def icp_default_params(**kw):
+    p = IcpParams()
+    lib().orc_icp_default_params(C.byref(p))
+    p.num_threads = 8
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+def umeyama_from_moments(mom17):
+    mom = np.ascontiguousarray(mom17, np.float64)
+    T = np.zeros(16, np.float32)
+    lib().orc_umeyama_from_moments(_p(mom), _p(T))
+    return T.reshape(4, 4)
+
+
+def nn1(tgt, queries, num_threads=8):
+    tgt = _f32(tgt)
+    queries = _f32(queries)
+    idx = np.zeros(len(queries), np.int32)
+    d2 = np.zeros(len(queries), np.float32)
+    lib().orc_nn1(_p(tgt), C.c_size_t(len(tgt)), _p(queries), C.c_size_t(len(queries)), _p(idx), _p(d2),
+                  C.c_int(num_threads))
+    return idx, d2
+
+
+def icp_align(src, tgt, params=None):
+    src = _f32(src)
+    tgt = _f32(tgt)
+    params = params or icp_default_params()
+    res = IcpResult()
+    lib().orc_icp_align(_p(src), C.c_size_t(len(src)), _p(tgt), C.c_size_t(len(tgt)), C.byref(params),
+                        C.byref(res))
+    return res
+
+
+def correct_pose(correction4x4, pose):
+    T = _f32(correction4x4).reshape(16)
+    pose = _f32(pose)
+    out = np.zeros(6, np.float32)
+    lib().orc_correct_pose(_p(T), _p(pose), _p(out))
+    return out
+
+
 class MapOptimization:
     """mapOptimization-like object: keyframes, local map, per-scan registration."""
 
@@ -332,6 +399,27 @@ class MapOptimization:
                                    _p(surf_raw), C.c_size_t(len(surf_raw)), _p(pose),
                                    C.byref(res), C.byref(nc), C.byref(ns))
         return pose, res, nc.value, ns.value
+
+    def loop_find_near_keyframes(self, key, search_num, slot=0):
+        n = lib().orc_mo_loop_find_near_keyframes(self.h, C.c_int(key), C.c_int(search_num), C.c_int(slot))
+        out = np.zeros((n, 4), np.float32)
+        if n:
+            lib().orc_mo_get_loop_cloud(self.h, C.c_int(slot), _p(out))
+        return out
+
+    def detect_loop_closure_distance(self, time_cur, radius=15.0, time_diff=30.0):
+        cur = C.c_int(-1)
+        pre = C.c_int(-1)
+        ok = lib().orc_mo_detect_loop_closure_distance(self.h, C.c_double(time_cur), C.c_float(radius),
+                                                       C.c_float(time_diff), C.byref(cur), C.byref(pre))
+        return (cur.value, pre.value) if ok else None
+
+    def perform_loop_closure(self, key_cur, key_pre, search_num=25, params=None, fitness_gate=0.3):
+        params = params or icp_default_params()
+        out = LoopResult()
+        lib().orc_mo_perform_loop_closure(self.h, C.c_int(key_cur), C.c_int(key_pre), C.c_int(search_num),
+                                          C.byref(params), C.c_float(fitness_gate), C.byref(out))
+        return out
 
     def __del__(self):
         if getattr(self, "h", None):
