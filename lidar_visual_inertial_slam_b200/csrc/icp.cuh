@@ -43,39 +43,45 @@ struct IcpParams {
 constexpr int kIcpMoments = 17;
 constexpr int kIcpThreads = 256;
 
-// Exact nearest neighbour of q in the cell grid: Chebyshev shells around q's (clamped) cell.  Every
-// point of shell s is at least (s-1) cells away, so the search stops once the best distance is below
-// that bound (or the bound passes max_d2: such a neighbour would be rejected anyway).  Rows and cells
-// whose slab cannot beat the best distance are skipped without touching memory.  Returns the
-// (d2 bits << 32 | index) key, kKeyNone when nothing was found.
-__device__ __forceinline__ u64 nn1_search(const GridView& g, float qx, float qy, float qz, float max_d2,
-                                          uint32_t* pos_out = nullptr) {
+// Running best of a nearest-neighbour search: (d2 bits << 32 | index) key plus the matched point
+struct Nn1Best {
+    u64 key;
+    float d2, x, y, z;
+    __device__ __forceinline__ Nn1Best() : key(kKeyNone), d2(INFINITY), x(0.f), y(0.f), z(0.f) {}
+};
+
+// Chebyshev shells s = 0 .. s_limit around q's (clamped) cell of grid g.  Every point of shell s is
+// at least (s-1) cells away, so the search is complete once the best distance is below that bound
+// (returns true), or once the bound passes max_d2 (such a neighbour would be rejected anyway; also
+// true).  Returns false when s_limit was reached first.  Rows and cells whose slab cannot beat the
+// best distance are skipped without touching memory.
+__device__ __forceinline__ bool nn1_shells(const GridView& g, float qx, float qy, float qz, float max_d2,
+                                           int s_limit, Nn1Best& best) {
     float ux, uy, uz;
     const int cx = cell_coord(qx, g.ox, g.inv, g.dx, &ux);
     const int cy = cell_coord(qy, g.oy, g.inv, g.dy, &uy);
     const int cz = cell_coord(qz, g.oz, g.inv, g.dz, &uz);
     const float slack = 2e-3f * g.cell;
-    u64 best = kKeyNone;
-    uint32_t best_pos = 0;
-    float best_d2 = __int_as_float(0x7f800000);
     const int smax = max(max(max(cx, g.dx - 1 - cx), max(cy, g.dy - 1 - cy)), max(cz, g.dz - 1 - cz));
-    for (int s = 0; s <= smax; ++s) {
+    for (int s = 0;; ++s) {
         if (s > 1) {
             const float lb = (float)(s - 1) * g.cell * 0.9999f;
             const float lb2 = lb * lb;
-            if (best_d2 < lb2 || lb2 > max_d2) break;
+            if (best.d2 < lb2 || lb2 > max_d2) return true;
         }
+        if (s > smax) return true;                      // the whole grid has been visited
+        if (s > s_limit) return false;
         const int z0 = max(cz - s, 0), z1 = min(cz + s, g.dz - 1);
         const int y0 = max(cy - s, 0), y1 = min(cy + s, g.dy - 1);
         for (int z = z0; z <= z1; ++z) {
             float dzl = fmaxf(fmaxf(((float)z - uz) * g.cell, (uz - (float)(z + 1)) * g.cell) - slack, 0.f);
             const float dz2 = dzl * dzl;
-            if (dz2 > best_d2) continue;
+            if (dz2 > best.d2) continue;
             const bool zface = (z == cz - s) || (z == cz + s);
             for (int y = y0; y <= y1; ++y) {
                 float dyl = fmaxf(fmaxf(((float)y - uy) * g.cell, (uy - (float)(y + 1)) * g.cell) - slack, 0.f);
                 const float dyz2 = dz2 + dyl * dyl;
-                if (dyz2 > best_d2) continue;
+                if (dyz2 > best.d2) continue;
                 const bool face = zface || (y == cy - s) || (y == cy + s);
                 const uint32_t row = ((uint32_t)z * g.dy + y) * g.dx;
                 // a face row contributes its whole x-range, an interior row only its two end cells
@@ -86,33 +92,43 @@ __device__ __forceinline__ u64 nn1_search(const GridView& g, float qx, float qy,
                     else { xa = xb = k == 0 ? cx - s : cx + s; if (xa < 0 || xa >= g.dx) continue; }
                     if (!face) {
                         float dxl = fmaxf(fmaxf(((float)xa - ux) * g.cell, (ux - (float)(xa + 1)) * g.cell) - slack, 0.f);
-                        if (dyz2 + dxl * dxl > best_d2) continue;
+                        if (dyz2 + dxl * dxl > best.d2) continue;
                     }
                     const uint32_t b = __ldg(g.cell_start + row + xa), e = __ldg(g.cell_start + row + xb + 1);
                     for (uint32_t c = b; c < e; ++c) {
                         const float4 p = __ldg(g.pts + c);
                         const float d = sqdist(qx, qy, qz, p.x, p.y, p.z);
                         const u64 key = make_key(d, p.w);
-                        if (key < best) { best = key; best_d2 = d; best_pos = c; }
+                        if (key < best.key) { best.key = key; best.d2 = d; best.x = p.x; best.y = p.y; best.z = p.z; }
                     }
                 }
             }
         }
     }
-    if (pos_out) *pos_out = best_pos;
+}
+
+// Exact nearest neighbour with the (d2, index) tie-break over two grids of the same target: the fine
+// grid (1 m cells) resolves every query whose neighbour lies within one cell -- nearly all of them in
+// an overlapping pair of submaps -- from 27 cells; the rest (non-overlapping parts, up to
+// max_corr_dist = 30 m away) continue on the coarse grid, where 30 m are 4-5 shells instead of 30.
+__device__ __forceinline__ Nn1Best nn1_search(const GridView& fine, const GridView& coarse, float qx, float qy,
+                                              float qz, float max_d2) {
+    Nn1Best best;
+    if (nn1_shells(fine, qx, qy, qz, max_d2, 1, best)) return best;      // complete after shells 0 and 1
+    nn1_shells(coarse, qx, qy, qz, max_d2, 0x7fffffff, best);              // the fine result keeps pruning
     return best;
 }
 
 // stage-level 1-NN (parity tests): idx -1 / d2 +inf when the target is empty
 __global__ void __launch_bounds__(kIcpThreads) nn1_kernel(const float4* __restrict__ q, uint32_t n, GridView g,
-                                                          float max_d2, int32_t* __restrict__ idx,
+                                                          GridView gc, float max_d2, int32_t* __restrict__ idx,
                                                           float* __restrict__ d2) {
     const uint32_t i = blockIdx.x * kIcpThreads + threadIdx.x;
     if (i >= n) return;
     const float4 p = q[i];
-    const u64 key = nn1_search(g, p.x, p.y, p.z, max_d2);
-    idx[i] = key_idx(key);
-    d2[i] = key_d2(key);
+    const Nn1Best b = nn1_search(g, gc, p.x, p.y, p.z, max_d2);
+    idx[i] = key_idx(b.key);
+    d2[i] = key_d2(b.key);
 }
 
 // block-wide sum of NV doubles per thread, fixed order; result valid in thread 0
@@ -140,7 +156,7 @@ __device__ __forceinline__ void block_sum(double (&v)[NV], double* smem /* [8][N
 }
 
 __global__ void __launch_bounds__(kIcpThreads) icp_correspond_kernel(const float4* __restrict__ cur, uint32_t n,
-                                                                     GridView g, IcpParams P,
+                                                                     GridView g, GridView gc, IcpParams P,
                                                                      const IcpState* __restrict__ st,
                                                                      double* __restrict__ partials) {
     if (st->done) return;
@@ -152,12 +168,10 @@ __global__ void __launch_bounds__(kIcpThreads) icp_correspond_kernel(const float
     if (i < n) {
         const float4 s = cur[i];
         const float gate = P.max_d2 < 3.0e38 ? (float)P.max_d2 * 1.0001f : __int_as_float(0x7f800000);
-        uint32_t pos;
-        const u64 key = nn1_search(g, s.x, s.y, s.z, gate, &pos);
-        if (key != kKeyNone && !((double)key_d2(key) > P.max_d2)) {      // PCL: skip when d2 > max_dist^2
-            const float4 t = __ldg(g.pts + pos);
+        const Nn1Best t = nn1_search(g, gc, s.x, s.y, s.z, gate);
+        if (t.key != kKeyNone && !((double)t.d2 > P.max_d2)) {           // PCL: skip when d2 > max_dist^2
             m[0] = 1.0;
-            m[1] = (double)key_d2(key);
+            m[1] = (double)t.d2;
             m[2] = s.x; m[3] = s.y; m[4] = s.z;
             m[5] = t.x; m[6] = t.y; m[7] = t.z;
             m[8] = (double)t.x * s.x;  m[9] = (double)t.x * s.y;  m[10] = (double)t.x * s.z;
@@ -314,7 +328,8 @@ __global__ void __launch_bounds__(kIcpThreads) icp_transform_kernel(float4* __re
 
 // getFitnessScore: sum of squared 1-NN distances of T_final * src (no range cap), per block
 __global__ void __launch_bounds__(kIcpThreads) icp_fitness_kernel(const float4* __restrict__ src, uint32_t n,
-                                                                  GridView g, const IcpState* __restrict__ st,
+                                                                  GridView g, GridView gc,
+                                                                  const IcpState* __restrict__ st,
                                                                   double* __restrict__ partials) {
     __shared__ double red[8];
     double v[1] = {0.0};
@@ -325,8 +340,8 @@ __global__ void __launch_bounds__(kIcpThreads) icp_fitness_kernel(const float4* 
         const float x = T[0] * p.x + T[1] * p.y + T[2] * p.z + T[3];
         const float y = T[4] * p.x + T[5] * p.y + T[6] * p.z + T[7];
         const float z = T[8] * p.x + T[9] * p.y + T[10] * p.z + T[11];
-        const u64 key = nn1_search(g, x, y, z, __int_as_float(0x7f800000));
-        if (key != kKeyNone) v[0] = (double)key_d2(key);
+        const Nn1Best b = nn1_search(g, gc, x, y, z, __int_as_float(0x7f800000));
+        if (b.key != kKeyNone) v[0] = (double)b.d2;
     }
     block_sum<1>(v, red);
     if (threadIdx.x == 0) partials[blockIdx.x] = v[0];

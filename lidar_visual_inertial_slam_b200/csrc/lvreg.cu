@@ -100,6 +100,7 @@ struct lvreg_handle {
     uint32_t n_scan[2] = {0, 0};
     // loop closure: [0] source (cureKeyframeCloud), [1] target (prevKeyframeCloud) + its search grid
     MapSide icp_cloud[2];
+    MapSide icp_coarse;                    // second, coarse search grid over the target's points
     DevBuf icp_cur, icp_partials, icp_state, icp_idx, icp_d2;
     // scratch of the main stream
     DevBuf feat_pts, feat_range, feat_col, feat_rings, feat_curv, feat_picked, feat_label, feat_flag, feat_ringof,
@@ -397,8 +398,9 @@ int voxelgrid_batch(lvreg_handle* h, VgJob* jobs, int nj) {
 
 // ---- search-grid build (on a lane stream; no host synchronisation when the bbox is known) --------
 int build_grid(lvreg_handle* h, Lane& L, MapSide& ms, const float* bb_min, const float* bb_max,
-               float cell_override = 0.f) {
+               float cell_override = 0.f, const float4* pts_override = nullptr) {
     const uint32_t m = ms.m;
+    const float4* pts = pts_override ? pts_override : ms.ds.as<float4>();
     GridSpec gs;
     const float gate_r = sqrtf(h->prm.knn_gate_sq);
     float cell = cell_override > 0.f ? cell_override : gate_r * (1.0f + 1.0f / 128.0f);
@@ -422,7 +424,7 @@ int build_grid(lvreg_handle* h, Lane& L, MapSide& ms, const float* bb_min, const
         uint32_t* mm = L.small.as<uint32_t>() + SM_MM;
         CK(cudaMemsetAsync(mm, 0xff, 3 * sizeof(uint32_t), L.st));
         CK(cudaMemsetAsync(mm + 3, 0, 3 * sizeof(uint32_t), L.st));
-        minmax_kernel<<<min(nblk(m, 256), (uint32_t)h->num_sms * 8), 256, 0, L.st>>>(ms.ds.as<float4>(), m, mm);
+        minmax_kernel<<<min(nblk(m, 256), (uint32_t)h->num_sms * 8), 256, 0, L.st>>>(pts, m, mm);
         launched(h);
         CK(cudaMemcpyAsync(L.pinned, mm, 6 * sizeof(uint32_t), cudaMemcpyDeviceToHost, L.st));
         CK(cudaStreamSynchronize(L.st));
@@ -456,7 +458,7 @@ int build_grid(lvreg_handle* h, Lane& L, MapSide& ms, const float* bb_min, const
     CK(ms.cell_pts.reserve((size_t)m * 16));
     CK(L.scan_temp.reserve((size_t)(scan_num_tiles(ncells + 1) + 2) * 4));
     CK(cudaMemsetAsync(L.scan_in.p, 0, (size_t)(ncells + 1) * 4, L.st));
-    cell_keys_kernel<<<nblk(m, 256), 256, 0, L.st>>>(ms.ds.as<float4>(), m, gs, L.keys[0].as<uint32_t>(),
+    cell_keys_kernel<<<nblk(m, 256), 256, 0, L.st>>>(pts, m, gs, L.keys[0].as<uint32_t>(),
                                                      L.vals[0].as<uint32_t>(), L.scan_in.as<uint32_t>());
     launched(h);
     exclusive_scan(CountIn{L.scan_in.as<uint32_t>()}, StartOut{ms.cell_start.as<uint32_t>()}, ncells + 1,
@@ -464,7 +466,7 @@ int build_grid(lvreg_handle* h, Lane& L, MapSide& ms, const float* bb_min, const
     int cur = radix_sort_pairs(L.keys[0].as<uint32_t>(), L.vals[0].as<uint32_t>(), L.keys[1].as<uint32_t>(),
                                L.vals[1].as<uint32_t>(), m, bits_for(ncells - 1), L.sort_scratch.as<uint32_t>(),
                                L.st, &h->call_launches);
-    cell_gather_kernel<<<nblk(m, 256), 256, 0, L.st>>>(ms.ds.as<float4>(), L.vals[cur].as<uint32_t>(), m,
+    cell_gather_kernel<<<nblk(m, 256), 256, 0, L.st>>>(pts, L.vals[cur].as<uint32_t>(), m,
                                                        ms.cell_pts.as<float4>());
     launched(h);
     CK(cudaGetLastError());
@@ -873,6 +875,7 @@ void lvreg_destroy(lvreg_handle* h) {
         h->scan_ds[s].release();
         h->icp_cloud[s].ds.release(); h->icp_cloud[s].cell_pts.release(); h->icp_cloud[s].cell_start.release();
     }
+    h->icp_coarse.cell_pts.release(); h->icp_coarse.cell_start.release();
     DevBuf* bufs[] = {&h->icp_cur, &h->icp_partials, &h->icp_state, &h->icp_idx, &h->icp_d2, &h->feat_pts, &h->feat_range, &h->feat_col, &h->feat_rings, &h->feat_curv, &h->feat_picked,
                       &h->feat_label, &h->feat_flag, &h->feat_ringof, &h->feat_cidx, &h->feat_ccnt, &h->feat_pos,
                       &h->feat_cand, &h->feat_spec, &h->feat_idx, &h->feat_pidx, &h->feat_corner, &h->feat_surf,
@@ -1618,7 +1621,35 @@ extern "C" int lvreg_debug_sort_prof(unsigned long long* out, int reset) {
 // ---- loop closure ---------------------------------------------------------------------
 namespace {
 
-constexpr float kIcpCell = 1.0f;          // search-grid cell of the ICP target, metres
+constexpr float kIcpCell = 1.0f;          // fine search-grid cell of the ICP target, metres
+constexpr float kIcpCoarseCell = 6.0f;    // coarse grid for the queries the fine grid cannot resolve in 27 cells
+
+// both search grids of the ICP target, on lane 1, from the VoxelGrid job's bounding box when there is one
+int build_icp_grids(lvreg_handle* h, const float* mn, const float* mx) {
+    Lane& L = h->lane[1];
+    MapSide& t = h->icp_cloud[1];
+    float bmn[3], bmx[3];
+    if (!mn && t.m) {
+        // one bounding-box pass serves both grids
+        uint32_t* mm = L.small.as<uint32_t>() + SM_MM;
+        CK(cudaMemsetAsync(mm, 0xff, 3 * sizeof(uint32_t), L.st));
+        CK(cudaMemsetAsync(mm + 3, 0, 3 * sizeof(uint32_t), L.st));
+        minmax_kernel<<<min(nblk(t.m, 256), (uint32_t)h->num_sms * 8), 256, 0, L.st>>>(t.ds.as<float4>(), t.m, mm);
+        launched(h);
+        CK(cudaMemcpyAsync(L.pinned, mm, 6 * sizeof(uint32_t), cudaMemcpyDeviceToHost, L.st));
+        CK(cudaStreamSynchronize(L.st));
+        for (int a = 0; a < 3; ++a) {
+            bmn[a] = ordered_to_float(L.pinned[a]);
+            bmx[a] = ordered_to_float(L.pinned[3 + a]);
+        }
+        mn = bmn;
+        mx = bmx;
+    }
+    CKS(build_grid(h, L, t, mn, mx, kIcpCell));
+    h->icp_coarse.m = t.m;
+    CKS(build_grid(h, L, h->icp_coarse, mn, mx, kIcpCoarseCell, t.ds.as<float4>()));
+    return LVREG_OK;
+}
 constexpr size_t kPinnedIcpState = 48 * 1024;
 
 // loopFindNearKeyframes for one slot: fills the lane's segment list and the VoxelGrid job
@@ -1686,13 +1717,13 @@ int icp_align_impl(lvreg_handle* h, const lvreg_icp_params* prm, lvreg_icp_resul
     for (int i = 0; i < 4; ++i) hs->T_final[i * 5] = hs->T_inc[i * 5] = 1.f;
     CK(cudaMemcpyAsync(h->icp_state.p, hs, sizeof(IcpState), cudaMemcpyHostToDevice, h->st));
     CK(cudaMemcpyAsync(h->icp_cur.p, h->icp_cloud[0].ds.p, (size_t)ns * 16, cudaMemcpyDeviceToDevice, h->st));
-    const GridView g = grid_view(h->icp_cloud[1]);
+    const GridView g = grid_view(h->icp_cloud[1]), gc = grid_view(h->icp_coarse);
     IcpState* ds = h->icp_state.as<IcpState>();
     // the per-iteration decision is taken on the device; the host polls every few iterations
     const int batch = 4;
     for (int it = 0; it < prm->max_iterations;) {
         for (int b = 0; b < batch && it < prm->max_iterations; ++b, ++it) {
-            icp_correspond_kernel<<<nb, kIcpThreads, 0, h->st>>>(h->icp_cur.as<float4>(), ns, g, P, ds,
+            icp_correspond_kernel<<<nb, kIcpThreads, 0, h->st>>>(h->icp_cur.as<float4>(), ns, g, gc, P, ds,
                                                                h->icp_partials.as<double>());
             icp_update_kernel<<<1, kIcpThreads, 0, h->st>>>(h->icp_partials.as<double>(), nb, P, ds);
             icp_transform_kernel<<<nb, kIcpThreads, 0, h->st>>>(h->icp_cur.as<float4>(), ns, ds);
@@ -1703,7 +1734,7 @@ int icp_align_impl(lvreg_handle* h, const lvreg_icp_params* prm, lvreg_icp_resul
         if (hs->done) break;
     }
     // getFitnessScore: the original source under the final transformation, no range cap
-    icp_fitness_kernel<<<nb, kIcpThreads, 0, h->st>>>(h->icp_cloud[0].ds.as<float4>(), ns, g, ds,
+    icp_fitness_kernel<<<nb, kIcpThreads, 0, h->st>>>(h->icp_cloud[0].ds.as<float4>(), ns, g, gc, ds,
                                                     h->icp_partials.as<double>());
     icp_fitness_reduce_kernel<<<1, kIcpThreads, 0, h->st>>>(h->icp_partials.as<double>(), nb, ds);
     launched(h, 2);
@@ -1759,7 +1790,7 @@ int lvreg_loop_find_near_keyframes(lvreg_handle* h, int key, int search_num, int
     lanes_join(h, 1u << slot);
     mark(h, EV_MAP);
     if (slot == 1) {
-        CKS(build_grid(h, h->lane[slot], h->icp_cloud[1], J.n ? J.mn : nullptr, J.n ? J.mx : nullptr, kIcpCell));
+        CKS(build_icp_grids(h, J.n ? J.mn : nullptr, J.n ? J.mx : nullptr));
         lanes_join(h, 1u << slot);
     }
     mark(h, EV_GRID);
@@ -1784,7 +1815,7 @@ int lvreg_icp_set_cloud(lvreg_handle* h, int slot, const lvreg_cloud* cloud) {
     CKS(upload_cloud(h, cloud, ms.ds, L.stage, L.st));
     ms.m = (uint32_t)cloud->n;
     ms.n_in = cloud->n;
-    if (slot == 1) CKS(build_grid(h, L, ms, nullptr, nullptr, kIcpCell));
+    if (slot == 1) CKS(build_icp_grids(h, nullptr, nullptr));
     CK(lanes_sync(h, 1u << slot));
     ms.valid = true;
     end_call(h);
@@ -1811,7 +1842,8 @@ int lvreg_nn1(lvreg_handle* h, const lvreg_cloud* queries, float max_dist, int32
     CK(h->icp_idx.reserve((size_t)n * 4));
     CK(h->icp_d2.reserve((size_t)n * 4));
     const float max_d2 = max_dist > 0.f && max_dist < 1e18f ? max_dist * max_dist : INFINITY;
-    nn1_kernel<<<nblk(n, kIcpThreads), kIcpThreads, 0, h->st>>>(h->qbuf.as<float4>(), n, grid_view(h->icp_cloud[1]), max_d2,
+    nn1_kernel<<<nblk(n, kIcpThreads), kIcpThreads, 0, h->st>>>(h->qbuf.as<float4>(), n, grid_view(h->icp_cloud[1]),
+                                                             grid_view(h->icp_coarse), max_d2,
                                                              h->icp_idx.as<int32_t>(), h->icp_d2.as<float>());
     launched(h);
     CK(cudaGetLastError());
@@ -1868,7 +1900,7 @@ int lvreg_perform_loop_closure(lvreg_handle* h, int key_cur, int key_pre, int se
     CKS(voxelgrid_batch(h, jobs, 2));
     lanes_join(h, 0x3);
     mark(h, EV_MAP);
-    CKS(build_grid(h, h->lane[1], h->icp_cloud[1], jobs[1].n ? jobs[1].mn : nullptr, jobs[1].n ? jobs[1].mx : nullptr, kIcpCell));
+    CKS(build_icp_grids(h, jobs[1].n ? jobs[1].mn : nullptr, jobs[1].n ? jobs[1].mx : nullptr));
     lanes_join(h, 0x2);
     mark(h, EV_GRID);
     h->icp_cloud[0].valid = h->icp_cloud[1].valid = true;

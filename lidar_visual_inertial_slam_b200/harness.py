@@ -98,6 +98,15 @@ class MapOptimizationMirror:
             raise RuntimeError(self.L.lvh_last_error().decode())
         return st, pose, res, tim, nk.value
 
+    def perform_loop_closure(self):
+        """mapOptimization::performLoopClosure -> (queued, key_cur, key_pre, LoopResult)"""
+        from .binding import LoopResult
+        cur, pre, out = C.c_int(-1), C.c_int(-1), LoopResult()
+        st = self.L.lvh_mo_perform_loop_closure(self.mo, C.byref(cur), C.byref(pre), C.byref(out))
+        if st == -2:
+            raise RuntimeError(self.L.lvh_last_error().decode())
+        return bool(st), cur.value, pre.value, out
+
     def selection(self):
         ids = np.zeros(4096, np.int32)
         n = self.L.lvh_mo_selection(self.mo, ids.ctypes.data_as(C.c_void_p), C.c_size_t(len(ids)))

@@ -93,6 +93,24 @@ size_t lvh_mo_selection(void* p, int32_t* ids, size_t cap) {
 }
 void* lvh_mo_handle(void* p) { return ((mapOptimization*)p)->handle(); }
 
+// performLoopClosure (MO:549-628) on the mirror: 1 = constraint queued, 0 = no candidate / gated, -2 = exception.
+// cur / pre receive the candidate pair of detectLoopClosureDistance (-1 when none), out the device result.
+int lvh_mo_perform_loop_closure(void* p, int* cur, int* pre, lvreg_loop_result* out) {
+    mapOptimization* mo = (mapOptimization*)p;
+    try {
+        int c = -1, q = -1;
+        const bool have = mo->detectLoopClosureDistance(&c, &q);
+        if (cur) *cur = have ? c : -1;
+        if (pre) *pre = have ? q : -1;
+        const bool queued = mo->performLoopClosure();
+        if (out) *out = mo->lastLoop;
+        return queued ? 1 : 0;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return -2;
+    }
+}
+
 // whole-sequence replay (what lvreg_replay runs per sequence)
 int lvh_replay(int sensor, uint64_t seed, int n_scans, double period, double speed, float gt, float gr, int device,
                int gen_threads, double* out /*10 doubles*/) {

@@ -119,6 +119,62 @@ std::vector<int32_t> mapOptimization::extractNearby() {
     return ids;
 }
 
+// detectLoopClosureDistance, MO:630-661: nearest-first radius search around the newest key pose, first
+// hit whose time differs by more than historyKeyframeSearchTimeDiff
+bool mapOptimization::detectLoopClosureDistance(int* latestID, int* closestID) {
+    const int loopKeyCur = (int)cloudKeyPoses3D.size() - 1;
+    int loopKeyPre = -1;
+    if (loopKeyCur < 0) return false;
+    if (loopIndexContainer.find(loopKeyCur) != loopIndexContainer.end()) return false;   // MO:636-638
+    const PointType& last = cloudKeyPoses3D.back();
+    const float r2 = P_.historyKeyframeSearchRadius * P_.historyKeyframeSearchRadius;
+    std::vector<std::pair<float, int>> hits;
+    for (size_t i = 0; i < cloudKeyPoses3D.size(); ++i) {
+        const PointType& p = cloudKeyPoses3D[i];
+        float dx = last.x - p.x, dy = last.y - p.y, dz = last.z - p.z;
+        float d2 = dx * dx;
+        d2 += dy * dy;
+        d2 += dz * dz;
+        if (d2 < r2) hits.emplace_back(d2, (int)i);
+    }
+    std::sort(hits.begin(), hits.end());
+    for (const auto& hit : hits) {
+        if (std::fabs(cloudKeyPoses6D[hit.second].time - timeLaserInfoCur) > P_.historyKeyframeSearchTimeDiff) {
+            loopKeyPre = hit.second;
+            break;
+        }
+    }
+    if (loopKeyPre == -1 || loopKeyCur == loopKeyPre) return false;
+    *latestID = loopKeyCur;
+    *closestID = loopKeyPre;
+    return true;
+}
+
+// performLoopClosure, MO:549-628.  Submaps, ICP, gates and the pose correction run on the device
+// (lvreg_perform_loop_closure); the constraint is queued exactly like loopIndexQueue / loopPoseQueue /
+// loopNoiseQueue.
+bool mapOptimization::performLoopClosure() {
+    if (cloudKeyPoses3D.empty()) return false;
+    int loopKeyCur, loopKeyPre;
+    if (!detectLoopClosureDistance(&loopKeyCur, &loopKeyPre)) return false;
+    lvreg_icp_params icp;
+    lvreg_icp_default_params(&icp);
+    icp.max_corr_dist = P_.historyKeyframeSearchRadius * 2;          // MO:580
+    int st = lvreg_perform_loop_closure(h_, loopKeyCur, loopKeyPre, P_.historyKeyframeSearchNum, &icp,
+                                        P_.historyKeyframeFitnessScore, &lastLoop);
+    if (st != LVREG_OK) throw std::runtime_error(std::string("lvreg_perform_loop_closure: ") + lvreg_last_error(h_));
+    if (lastLoop.status != LVREG_LOOP_OK) return false;
+    LoopConstraint c;
+    c.loopKeyCur = loopKeyCur;
+    c.loopKeyPre = loopKeyPre;
+    std::memcpy(c.poseFrom, lastLoop.pose_from, sizeof(c.poseFrom));
+    std::memcpy(c.poseTo, lastLoop.pose_to, sizeof(c.poseTo));
+    c.noiseScore = lastLoop.noise;
+    loopQueue.push_back(c);
+    loopIndexContainer[loopKeyCur] = loopKeyPre;                     // MO:626
+    return true;
+}
+
 void mapOptimization::extractSurroundingKeyFrames() {
     if (cloudKeyPoses3D.empty()) return;                     // MO:974-975
     std::vector<int32_t> ids = extractNearby();

@@ -3,11 +3,14 @@
 // functions and data members keep the reference's names and meaning so that a maintainer can
 // swap the bodies one for one; every data-parallel step goes through the C ABI
 // of liblvreg (include/lvreg.h).  Not mirrored (out of scope): iSAM2 factors,
-// loop closure, GPS, ROS publishing -- saveKeyFramesAndFactor takes the LM pose as the keyframe
-// pose, which is what the replay harness needs.
+// GPS, ROS publishing -- saveKeyFramesAndFactor takes the LM pose as the keyframe pose, which is
+// what the replay harness needs.  Loop closure is mirrored up to the pose constraint:
+// detectLoopClosureDistance + performLoopClosure queue {poseFrom, poseTo, noise}; the gtsam
+// BetweenFactor built from them (MO:610-619, 1488-1527) stays with the caller.
 #pragma once
 
 #include <cstdint>
+#include <map>
 #include <vector>
 
 #include "../../include/lvreg.h"
@@ -41,6 +44,10 @@ struct ParamServer {
     float surroundingkeyframeAddingAngleThreshold = 0.2f;   // utility.h:281
     bool  sensorIsLivox = true;                             // MO:1392-1396: keyframe every > 1.0 s
     double mappingProcessInterval = 0.15;                   // utility.h:283, MO:311-314
+    float historyKeyframeSearchRadius = 15.0f;              // utility.h:296
+    float historyKeyframeSearchTimeDiff = 30.0f;            // utility.h:298
+    int   historyKeyframeSearchNum = 25;                    // utility.h:300
+    float historyKeyframeFitnessScore = 0.3f;               // utility.h:302
     ParamServer() { lvreg_default_params(&lv); }
 };
 
@@ -79,6 +86,18 @@ class mapOptimization {
     // laserCloudInfoHandler body MO:316-326 for one incoming scan; `guess` replaces
     // updateInitialGuess (MO:806-877, out of scope).  Returns false when throttled (MO:311-314).
     bool laserCloudInfoHandler(const Cloud& corner, const Cloud& surf, double stamp, const float* guess);
+
+    // ---- loop closure (MO:549-661), same names as the reference ----
+    struct LoopConstraint {                  // one entry of loopIndexQueue / loopPoseQueue / loopNoiseQueue
+        int loopKeyCur, loopKeyPre;
+        float poseFrom[6], poseTo[6];        // {roll,pitch,yaw,x,y,z}; the factor is poseFrom.between(poseTo)
+        float noiseScore;
+    };
+    std::map<int, int> loopIndexContainer;                           // MO:107
+    std::vector<LoopConstraint> loopQueue;                           // MO:108-110
+    lvreg_loop_result lastLoop;
+    bool detectLoopClosureDistance(int* latestID, int* closestID);   // MO:630-661
+    bool performLoopClosure();                                       // MO:549-628; true when a constraint was queued
 
     // read-backs of device-resident clouds (laserCloud*LastDS / *FromMapDS)
     Cloud getLaserCloudLastDS(int which);

@@ -59,8 +59,38 @@ def main():
     np.savez_compressed(os.path.join(HERE, "features.npz"), pts=fpts, point_range=frg, point_col_ind=fcol,
                         start_ring_index=fsr, end_ring_index=fer, edge_threshold=np.float32(0.5), corner=fc, surf=fs,
                         label=fl.astype(np.int8))
+    icp_golden()
     print("golden vectors written to", HERE)
 
 
+def icp_golden():
+    """4. loop-closure ICP ("next" row 8f-2): 1-NN, one Umeyama step, the full align() and the pose correction"""
+    rng = np.random.default_rng(20261019)
+    cw, sw = room_world(rng, n_surf=9000, n_corner=2400, half=6.0, height=4.0)
+    tgt = O.voxelgrid(np.concatenate([cw, sw]), 0.4)[0]
+    pose = np.array([0.02, -0.015, 0.06, 0.35, -0.3, 0.1])
+    from tests.synth import rot_rpy
+    R = rot_rpy(*pose[:3])
+    sel = tgt[rng.choice(len(tgt), 1200, replace=False)]
+    src = sel.copy()
+    src[:, :3] = ((sel[:, :3].astype(np.float64) - pose[3:]) @ R + rng.normal(0, 0.01, (1200, 3))).astype(np.float32)
+    idx, d2 = O.nn1(tgt, src)
+    s, t = src[:, :3].astype(np.float64), tgt[idx, :3].astype(np.float64)
+    mom = np.zeros(17)
+    mom[0], mom[1] = len(s), d2.astype(np.float64).sum()
+    mom[2:5], mom[5:8], mom[8:17] = s.sum(0), t.sum(0), (t.T @ s).reshape(9)
+    T1 = O.umeyama_from_moments(mom)
+    res = O.icp_align(src, tgt)
+    stored = np.array([0.01, 0.02, -0.4, 3.0, -1.0, 0.2], np.float32)
+    np.savez_compressed(os.path.join(HERE, "icp.npz"), src=src, tgt=tgt, pose=pose, nn_idx=idx, nn_d2=d2, moments=mom,
+                        first_T=T1, final_T=res.T, iterations=np.int32(res.iterations), state=np.int32(res.state),
+                        converged=np.int32(res.converged), fitness=np.float64(res.fitness),
+                        n_corr=np.int32(res.n_correspondences), stored_pose=stored,
+                        corrected_pose=O.correct_pose(res.T, stored))
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "icp":
+        icp_golden()
+    else:
+        main()

@@ -48,6 +48,23 @@ def test_oracle_matches_golden_features():
     assert {tuple(r) for r in c} == {tuple(r) for r in z["pts"][lab1]}
 
 
+def test_oracle_matches_golden_icp():
+    z = np.load(os.path.join(G, "icp.npz"))
+    idx, d2 = O.nn1(z["tgt"], z["src"])
+    assert np.array_equal(idx, z["nn_idx"]) and np.array_equal(d2, z["nn_d2"])
+    assert np.array_equal(O.umeyama_from_moments(z["moments"]), z["first_T"])
+    res = O.icp_align(z["src"], z["tgt"])
+    assert np.array_equal(res.T, z["final_T"])
+    assert (res.iterations, res.state, res.converged, res.n_correspondences) == \
+        (int(z["iterations"]), int(z["state"]), int(z["converged"]), int(z["n_corr"]))
+    assert res.fitness == float(z["fitness"])
+    assert np.array_equal(O.correct_pose(res.T, z["stored_pose"]), z["corrected_pose"])
+    # the alignment recovers the displacement the source was generated with
+    from tests.synth import rot_rpy
+    assert np.abs(res.T[:3, :3] - rot_rpy(*z["pose"][:3])).max() < 5e-3
+    assert np.abs(res.T[:3, 3] - z["pose"][3:]).max() < 3e-2
+
+
 def _declared_symbols():
     text = open(os.path.join(ROOT, "include", "lvreg.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)

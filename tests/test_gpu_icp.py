@@ -153,6 +153,22 @@ def test_icp_no_correspondences_and_empty(lv, h, world):
     assert g.converged == 0 and g.state == lv.ICP_NO_INPUT
 
 
+def test_icp_golden_vectors(lv, h):
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "icp.npz"))
+    h.icp_set_cloud(0, z["src"])
+    h.icp_set_cloud(1, z["tgt"])
+    gi, gd = h.nn1(z["src"])
+    assert np.array_equal(gi, z["nn_idx"]) and np.array_equal(gd, z["nn_d2"])
+    g = h.icp_align()
+    assert (g.iterations, g.state, g.converged, g.n_correspondences) == \
+        (int(z["iterations"]), int(z["state"]), int(z["converged"]), int(z["n_corr"]))
+    assert np.max(np.abs(g.T[:3, 3] - z["final_T"][:3, 3])) <= POS_TOL
+    assert np.max(np.abs(g.T[:3, :3] - z["final_T"][:3, :3])) <= ROT_TOL
+    assert abs(g.fitness - float(z["fitness"])) <= 1e-9
+    assert np.array_equal(lv.correct_pose(z["final_T"], z["stored_pose"]), z["corrected_pose"])
+
+
 # ---- submaps + performLoopClosure ----------------------------------------------------------------
 @pytest.fixture(scope="module")
 def loop_sequence(lv, world):

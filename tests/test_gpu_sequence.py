@@ -116,6 +116,45 @@ def test_mirror_sequence_replay_vs_oracle(lv):
     mo.close()
 
 
+def test_mirror_loop_closure_vs_oracle(lv):
+    """A trajectory that returns to its start after > 30 s: the mirror's performLoopClosure (candidate
+    search on the host, submaps + ICP + pose correction on the device) against the oracle."""
+    from lidar_visual_inertial_slam_b200 import harness as H
+    gen = H.Generator(H.MID360, 0x5EED0007)
+    mo = H.MapOptimizationMirror()
+    omo = O.MapOptimization()
+    period, speed = 1.2, 2.5
+    n_kf = 0
+    t = 0.0
+    for k in range(32):
+        truth = gen.truth_pose(k, period, speed)
+        corner, surf = gen.scan(truth, 500 + k, 4)
+        guess = truth if k == 0 else gen.guess_pose(k, truth, 0.05, 0.01)
+        t = k * period
+        st, pose, res, tim, nkf = mo.handle_scan(corner, surf, t, guess)
+        if nkf > n_kf:
+            omo.add_keyframe(O.voxelgrid(corner, 0.2)[0], O.voxelgrid(surf, 0.4)[0], pose, t)
+            n_kf = nkf
+    assert n_kf >= 25
+    queued, cur, pre, g = mo.perform_loop_closure()
+    pair = omo.detect_loop_closure_distance(t)
+    assert pair == (cur, pre) and cur == n_kf - 1 and pre < 8
+    o = omo.perform_loop_closure(cur, pre, 25)
+    assert g.status == o.status
+    assert queued == (o.status == 0)
+    assert (g.n_source, g.n_target) == (o.n_source, o.n_target)
+    if o.n_source >= 300 and o.n_target >= 1000:
+        assert (g.icp.iterations, g.icp.state, g.icp.converged) == (o.icp.iterations, o.icp.state, o.icp.converged)
+        assert np.abs(g.icp.T[:3, 3] - o.icp.T[:3, 3]).max() <= POS_TOL
+        assert np.abs(g.icp.T[:3, :3] - o.icp.T[:3, :3]).max() <= ROT_TOL
+    if o.status == 0:
+        assert np.abs(np.array(g.pose_from[:]) - np.array(o.pose_from[:])).max() <= POS_TOL
+    # the same pair is not closed twice (loopIndexContainer, MO:636-638)
+    if queued:
+        assert mo.perform_loop_closure()[0] is False
+    mo.close()
+
+
 def test_whole_sequence_replay_binary_path(lv):
     from lidar_visual_inertial_slam_b200 import harness as H
     r = H.replay(H.MID360, 0x5EED0001, 25, device=0, period=0.2, gen_threads=4)

@@ -250,3 +250,110 @@ def test_radius_search_sorted_strict():
     ref = np.flatnonzero(dd < np.float32(2500.0))
     ref = ref[np.lexsort((ref, dd[ref]))]
     assert np.array_equal(idx, ref) and idx[0] == 499
+
+
+# ---- loop-closure ICP ---------------------------------------------------------------
+def _moments(s, t, d2=None):
+    s = np.asarray(s, np.float64)
+    t = np.asarray(t, np.float64)
+    mom = np.zeros(17)
+    mom[0] = len(s)
+    mom[1] = 0.0 if d2 is None else float(np.sum(d2))
+    mom[2:5], mom[5:8], mom[8:17] = s.sum(0), t.sum(0), (t.T @ s).reshape(9)
+    return mom
+
+
+def _umeyama_numpy(s, t):
+    # Eigen::umeyama(src, dst, with_scaling=false), in float64
+    ms, mt = s.mean(0), t.mean(0)
+    sig = (t - mt).T @ (s - ms) / len(s)
+    U, S, Vt = np.linalg.svd(sig)
+    D = np.eye(3)
+    if np.linalg.det(U) * np.linalg.det(Vt) < 0:
+        D[2, 2] = -1
+    R = U @ D @ Vt
+    return R, mt - R @ ms
+
+
+def test_umeyama_matches_numpy_svd():
+    from tests.synth import rot_rpy
+    rng = np.random.default_rng(5)
+    for k in range(300):
+        n = int(rng.integers(3, 400))
+        s = rng.normal(0, rng.choice([0.1, 5.0, 60.0]), (n, 3)) + rng.uniform(-100, 100, 3)
+        R0 = rot_rpy(*rng.uniform(-3, 3, 3))
+        t = s @ R0.T + rng.uniform(-20, 20, 3) + rng.normal(0, 0.01, (n, 3))
+        if k % 5 == 0:
+            t[:, 2] = t[:, 2].mean()                  # coplanar target: rank-2 covariance
+        T = O.umeyama_from_moments(_moments(s, t))
+        R, tr = _umeyama_numpy(s, t)
+        assert np.abs(T[:3, :3] - R).max() < 2e-6
+        assert np.abs(T[:3, 3] - tr).max() < 2e-5 * max(1.0, np.abs(tr).max())
+        assert abs(np.linalg.det(T[:3, :3].astype(np.float64)) - 1.0) < 1e-5
+        assert np.array_equal(T[3], [0, 0, 0, 1])
+
+
+def test_umeyama_reflection_case_gives_a_rotation():
+    # a mirrored copy: the best orthogonal map is a reflection, Umeyama must return det = +1
+    rng = np.random.default_rng(6)
+    s = rng.normal(0, 1, (200, 3))
+    t = s * np.array([1, 1, -1])
+    T = O.umeyama_from_moments(_moments(s, t))
+    R, tr = _umeyama_numpy(s, t)
+    assert np.linalg.det(T[:3, :3].astype(np.float64)) > 0.999
+    assert np.abs(T[:3, :3] - R).max() < 2e-6
+
+
+def test_nn1_matches_numpy_brute_force():
+    rng = np.random.default_rng(8)
+    tgt = rng.uniform(-20, 20, (3000, 4)).astype(np.float32)
+    q = rng.uniform(-25, 25, (400, 4)).astype(np.float32)
+    idx, d2 = O.nn1(tgt, q)
+    dx = q[:, None, 0] - tgt[None, :, 0]
+    dy = q[:, None, 1] - tgt[None, :, 1]
+    dz = q[:, None, 2] - tgt[None, :, 2]
+    D = (dx * dx + dy * dy).astype(np.float32) + dz * dz            # the fp32 operation order of the path
+    assert np.array_equal(idx, D.argmin(1).astype(np.int32))
+    assert np.array_equal(d2, D.min(1))
+
+
+def test_icp_align_recovers_a_known_motion_and_reports_pcl_states():
+    from tests.synth import rot_rpy, room_world
+    rng = np.random.default_rng(9)
+    cw, sw = room_world(rng, n_surf=9000, n_corner=2400, half=6.0, height=4.0)
+    tgt = O.voxelgrid(np.concatenate([cw, sw]), 0.4)[0]
+    pose = np.array([0.01, -0.02, 0.08, 0.3, -0.25, 0.1])
+    R = rot_rpy(*pose[:3])
+    sel = tgt[rng.choice(len(tgt), 1500, replace=False)]
+    src = sel.copy()
+    src[:, :3] = ((sel[:, :3].astype(np.float64) - pose[3:]) @ R).astype(np.float32)
+    res = O.icp_align(src, tgt)
+    assert res.converged == 1 and res.state in (2, 3, 4)        # TRANSFORM / ABS_MSE / REL_MSE
+    assert np.abs(res.T[:3, :3] - R).max() < 1e-3 and np.abs(res.T[:3, 3] - pose[3:]).max() < 1e-2
+    assert res.fitness < 1e-4
+    # iteration cap -> PCL reports convergence with state ITERATIONS
+    capped = O.icp_align(src, tgt, O.icp_default_params(max_iterations=2))
+    assert capped.converged == 1 and capped.state == 1 and capped.iterations == 2
+    # nothing within the correspondence distance -> not converged, zero iterations, identity
+    far = src.copy()
+    far[:, 0] += 1000
+    none = O.icp_align(far, tgt)
+    assert none.converged == 0 and none.state == 5 and none.iterations == 0
+    assert np.array_equal(none.T, np.eye(4, dtype=np.float32))
+
+
+def test_correct_pose_composes_like_pcl():
+    from tests.synth import rot_rpy
+    rng = np.random.default_rng(12)
+    for _ in range(100):
+        pose = np.concatenate([rng.uniform(-1.2, 1.2, 3), rng.uniform(-50, 50, 3)]).astype(np.float32)
+        corr = np.eye(4)
+        corr[:3, :3] = rot_rpy(*rng.uniform(-0.2, 0.2, 3))
+        corr[:3, 3] = rng.uniform(-2, 2, 3)
+        out = O.correct_pose(corr.astype(np.float32), pose)
+        W = np.eye(4)
+        W[:3, :3] = rot_rpy(*pose[:3])
+        W[:3, 3] = pose[3:]
+        Cm = corr @ W
+        assert np.abs(out[3:] - Cm[:3, 3]).max() < 1e-4
+        assert np.abs(rot_rpy(*out[:3]) - Cm[:3, :3]).max() < 1e-5
