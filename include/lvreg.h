@@ -304,6 +304,29 @@ int lvreg_correct_pose(const float* correction4x4, const float pose[6], float ou
 int lvreg_perform_loop_closure(lvreg_handle* h, int key_cur, int key_pre, int search_num,
                                const lvreg_icp_params* prm, float fitness_gate, lvreg_loop_result* out);
 
+/* ---- "next" row: LiDAR depth for tracked visual features --------------------------
+ * Replaces the point-cloud work of the visual front end:
+ *   lidar_callback  feature_tracker/src/feature_tracker_node.cpp:303-371  0.2 m VoxelGrid of the new
+ *       cloud, camera-view filter, transform by transNow into the odometry frame, 5 s queue, fuse,
+ *       0.2 m VoxelGrid -> depthCloud (stays on the device)
+ *   DepthRegister::get_depth  feature_tracker/src/feature_tracker.h:150-283  depthCloud into the
+ *       camera frame (T_inv = transNow.inverse(), row-major 3x4, computed by the caller from tf),
+ *       num_bins x num_bins range image keeping the closest point per bin, unit-sphere projection,
+ *       exact 3-NN per feature, ray / plane intersection with the reference's clamps.
+ * features_xyz: n x 3 undistorted normalised image coordinates (z = 1), as features_2d.
+ * depth_out[n]: depth_of_point.values (-1 = none).  features_3d_out (optional, n x 4 floats):
+ * features_3d_sphere as published on /vins/depth/depth_feature.  atan2 is evaluated in double and
+ * rounded to float. */
+int lvreg_depth_clear(lvreg_handle* h);
+int lvreg_depth_add_cloud(lvreg_handle* h, const lvreg_cloud* cloud, const float T_now[12], double stamp,
+                          size_t* n_depth);
+/* stage level: set depthCloud directly */
+int lvreg_depth_set_cloud(lvreg_handle* h, const lvreg_cloud* depth_cloud);
+/* which = 0: depthCloud; 1: depth_cloud_local after the range-image filter of the last lvreg_get_depth */
+int lvreg_depth_get_cloud(lvreg_handle* h, int which, lvreg_cloud_out* out, size_t* n);
+int lvreg_get_depth(lvreg_handle* h, const float T_inv[12], const float* features_xyz, size_t n, int num_bins,
+                    float* depth_out, float* features_3d_out);
+
 /* ---- measurement -------------------------------------------------------------------------- */
 int lvreg_get_timings(const lvreg_handle* h, lvreg_timings* t);
 /* Phase profile of the last lvreg_scan2map / lvreg_register_scan launch, from block 0's

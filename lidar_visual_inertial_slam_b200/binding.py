@@ -361,6 +361,36 @@ class Lvreg:
                                                    C.byref(params), C.c_float(fitness_gate), C.byref(out)))
         return out
 
+    # ---- LiDAR depth for visual features ----
+    def depth_clear(self):
+        self._ck(self.L.lvreg_depth_clear(self.h))
+
+    def depth_add_cloud(self, cloud, T_now, stamp):
+        c, _keep = _cloud(cloud)
+        T = np.ascontiguousarray(T_now, np.float32).reshape(12)
+        n = C.c_size_t(0)
+        self._ck(self.L.lvreg_depth_add_cloud(self.h, C.byref(c), T.ctypes.data_as(C.c_void_p), C.c_double(stamp),
+                                              C.byref(n)))
+        return n.value
+
+    def depth_set_cloud(self, cloud):
+        c, _keep = _cloud(cloud)
+        self._ck(self.L.lvreg_depth_set_cloud(self.h, C.byref(c)))
+
+    def depth_get_cloud(self, which=0, pcl_layout=False):
+        return self._get_cloud(self.L.lvreg_depth_get_cloud, which, pcl_layout)
+
+    def get_depth(self, T_inv, features_xyz, num_bins=360):
+        """-> (depth per feature (-1 = none), features_3d_sphere [n,4])"""
+        T = np.ascontiguousarray(T_inv, np.float32).reshape(12)
+        f = np.ascontiguousarray(features_xyz, np.float32).reshape(-1, 3)
+        depth = np.zeros(len(f), np.float32)
+        f3d = np.zeros((len(f), 4), np.float32)
+        self._ck(self.L.lvreg_get_depth(self.h, T.ctypes.data_as(C.c_void_p), f.ctypes.data_as(C.c_void_p),
+                                        C.c_size_t(len(f)), int(num_bins), depth.ctypes.data_as(C.c_void_p),
+                                        f3d.ctypes.data_as(C.c_void_p)))
+        return depth, f3d
+
     # ---- stage level ----
     def transform_cloud(self, pts, pose):
         c, keep = _cloud(pts)

@@ -9,10 +9,12 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <deque>
 #include <string>
 #include <vector>
 
 #include "common.cuh"
+#include "depth.cuh"
 #include "feature.cuh"
 #include "fit.cuh"
 #include "icp.cuh"
@@ -51,6 +53,12 @@ struct Keyframe {
     DevBuf cloud[2];          // sensor-frame corner / surf, float4
     uint32_t n[2] = {0, 0};
     float pose[6] = {0, 0, 0, 0, 0, 0};
+};
+
+struct DepthEntry {            // one entry of cloudQueue / timeQueue (feature_tracker_node.cpp:343-344)
+    DevBuf pts;
+    uint32_t n = 0;
+    double stamp = 0.0;
 };
 
 struct MapSide {
@@ -101,6 +109,11 @@ struct lvreg_handle {
     // loop closure: [0] source (cureKeyframeCloud), [1] target (prevKeyframeCloud) + its search grid
     MapSide icp_cloud[2];
     MapSide icp_coarse;                    // second, coarse search grid over the target's points
+    // visual side: stacked depth cloud (depthCloud) and the scratch of get_depth
+    std::deque<DepthEntry*> depth_queue;
+    std::vector<DepthEntry*> depth_free;   // expired entries, buffers kept for reuse (no cudaMalloc per scan)
+    DevBuf depth_cloud, depth_concat, depth_bins, depth_local, depth_unit, depth_feat, depth_out, depth_f3d;
+    uint32_t n_depth = 0, n_depth_local = 0;
     DevBuf icp_cur, icp_partials, icp_state, icp_idx, icp_d2;
     // scratch of the main stream
     DevBuf feat_pts, feat_range, feat_col, feat_rings, feat_curv, feat_picked, feat_label, feat_flag, feat_ringof,
@@ -876,6 +889,13 @@ void lvreg_destroy(lvreg_handle* h) {
         h->icp_cloud[s].ds.release(); h->icp_cloud[s].cell_pts.release(); h->icp_cloud[s].cell_start.release();
     }
     h->icp_coarse.cell_pts.release(); h->icp_coarse.cell_start.release();
+    for (DepthEntry* e : h->depth_queue) { e->pts.release(); delete e; }
+    for (DepthEntry* e : h->depth_free) { e->pts.release(); delete e; }
+    {
+        DevBuf* db[] = {&h->depth_cloud, &h->depth_concat, &h->depth_bins, &h->depth_local, &h->depth_unit, &h->depth_feat,
+                        &h->depth_out, &h->depth_f3d};
+        for (DevBuf* b : db) b->release();
+    }
     DevBuf* bufs[] = {&h->icp_cur, &h->icp_partials, &h->icp_state, &h->icp_idx, &h->icp_d2, &h->feat_pts, &h->feat_range, &h->feat_col, &h->feat_rings, &h->feat_curv, &h->feat_picked,
                       &h->feat_label, &h->feat_flag, &h->feat_ringof, &h->feat_cidx, &h->feat_ccnt, &h->feat_pos,
                       &h->feat_cand, &h->feat_spec, &h->feat_idx, &h->feat_pidx, &h->feat_corner, &h->feat_surf,
@@ -1930,6 +1950,168 @@ int lvreg_perform_loop_closure(lvreg_handle* h, int key_cur, int key_pre, int se
     finish_timings(h);
     end_call(h);
     return s;
+}
+
+// ---- LiDAR depth for visual features -----------------------------------------------------
+namespace {
+Affine affine_from(const float T[12]) {
+    Affine A;
+    for (int i = 0; i < 12; ++i) A.m[i] = T[i];
+    return A;
+}
+}  // namespace
+
+int lvreg_depth_clear(lvreg_handle* h) {
+    if (!h) return LVREG_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->st));
+    for (DepthEntry* e : h->depth_queue) h->depth_free.push_back(e);
+    h->depth_queue.clear();
+    h->n_depth = 0;
+    return LVREG_OK;
+}
+
+int lvreg_depth_add_cloud(lvreg_handle* h, const lvreg_cloud* cloud, const float T_now[12], double stamp, size_t* n_depth) {
+    if (!h || !cloud || !T_now) return LVREG_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    begin_call(h);
+    mark(h, EV_BEGIN);
+    // 2. 0.2 m VoxelGrid of the new cloud (FN:303-309)
+    Lane& L = h->lane[LANE_SCAN_CORNER];
+    lanes_fork(h, 0x4);
+    CKS(upload_cloud(h, cloud, L.raw, L.stage, L.st));
+    uint32_t n1 = 0;
+    VgJob J;
+    J.lane = LANE_SCAN_CORNER;
+    J.pts = L.raw.as<float4>();
+    J.n = (uint32_t)cloud->n;
+    J.leaf = 0.2f;
+    J.out = &h->vgout;
+    J.n_out = &n1;
+    CKS(voxelgrid_batch(h, &J, 1));
+    lanes_join(h, 0x4);
+    // 3. + 5. camera-view filter and transform into the odometry frame, order kept (FN:313-331)
+    DepthEntry* e;
+    if (!h->depth_free.empty()) { e = h->depth_free.back(); h->depth_free.pop_back(); }
+    else e = new DepthEntry();
+    e->stamp = stamp;
+    e->n = 0;
+    h->depth_queue.push_back(e);             // owned by the queue from here on (error paths included)
+    if (n1) {
+        CK(e->pts.reserve((size_t)n1 * 16));
+        CK(L.scan_temp.reserve((size_t)(scan_num_tiles(n1) + 2) * 4));
+        uint32_t* d_total = L.small.as<uint32_t>() + SM_TOTAL;
+        exclusive_scan(ViewFlagIn{h->vgout.as<float4>()}, ViewCompactOut{h->vgout.as<float4>(), affine_from(T_now), e->pts.as<float4>()},
+                       n1, L.scan_temp.as<uint32_t>(), d_total, h->st, &h->call_launches);
+        CK(cudaMemcpyAsync(L.pinned, d_total, 4, cudaMemcpyDeviceToHost, h->st));
+        CK(cudaStreamSynchronize(h->st));
+        e->n = L.pinned[0];
+    }
+    // 6. + 7. queue, drop clouds older than 5 s (FN:341-357)
+    while (!h->depth_queue.empty() && stamp - h->depth_queue.front()->stamp > 5.0) {
+        h->depth_free.push_back(h->depth_queue.front());
+        h->depth_queue.pop_front();
+    }
+    // 8. + 9. fuse and down-sample again (FN:360-371)
+    uint64_t total = 0;
+    for (DepthEntry* q : h->depth_queue) total += q->n;
+    if (total > 0x7fffffffull) return fail(h, LVREG_ERR_INVALID, "depth cloud too large");
+    CK(h->depth_concat.reserve((size_t)(total ? total : 1) * 16));
+    uint64_t at = 0;
+    for (DepthEntry* q : h->depth_queue) {
+        if (q->n) CK(cudaMemcpyAsync(h->depth_concat.as<float4>() + at, q->pts.p, (size_t)q->n * 16, cudaMemcpyDeviceToDevice, h->st));
+        at += q->n;
+    }
+    lanes_fork(h, 0x4);
+    VgJob J2;
+    J2.lane = LANE_SCAN_CORNER;
+    J2.pts = h->depth_concat.as<float4>();
+    J2.n = (uint32_t)total;
+    J2.leaf = 0.2f;
+    J2.out = &h->depth_cloud;
+    J2.n_out = &h->n_depth;
+    CKS(voxelgrid_batch(h, &J2, 1));
+    lanes_join(h, 0x4);
+    mark(h, EV_DS);
+    CK(cudaStreamSynchronize(h->st));
+    h->last.downsample_ms = span(h, EV_BEGIN, EV_DS);
+    finish_timings(h);
+    end_call(h);
+    if (n_depth) *n_depth = h->n_depth;
+    return LVREG_OK;
+}
+
+int lvreg_depth_set_cloud(lvreg_handle* h, const lvreg_cloud* depth_cloud) {
+    if (!h || !depth_cloud) return LVREG_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    begin_call(h);
+    CKS(upload_cloud(h, depth_cloud, h->depth_cloud, h->lane[LANE_SCAN_CORNER].stage, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    h->n_depth = (uint32_t)depth_cloud->n;
+    end_call(h);
+    return LVREG_OK;
+}
+
+int lvreg_depth_get_cloud(lvreg_handle* h, int which, lvreg_cloud_out* out, size_t* n) {
+    if (!h || which < 0 || which > 1) return LVREG_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    const uint32_t cnt = which == 0 ? h->n_depth : h->n_depth_local;
+    if (n) *n = cnt;
+    if (!out) return LVREG_OK;
+    return download_cloud(h, (which == 0 ? h->depth_cloud : h->depth_local).as<float4>(), cnt, out);
+}
+
+int lvreg_get_depth(lvreg_handle* h, const float T_inv[12], const float* features_xyz, size_t n, int num_bins,
+                    float* depth_out, float* features_3d_out) {
+    if (!h || !T_inv || (n && (!features_xyz || !depth_out)) || num_bins < 1 || num_bins > 4096 || n > 0x7fffffffull)
+        return LVREG_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    begin_call(h);
+    mark(h, EV_BEGIN);
+    h->n_depth_local = 0;
+    for (size_t i = 0; i < n; ++i) depth_out[i] = -1.f;              // FT:121-123
+    const uint32_t m = h->n_depth;
+    const uint32_t nb = (uint32_t)num_bins * (uint32_t)num_bins;
+    Lane& L = h->lane[LANE_SCAN_CORNER];
+    uint32_t* d_total = L.small.as<uint32_t>() + SM_TOTAL;
+    const Affine Ti = affine_from(T_inv);
+    CK(h->depth_bins.reserve((size_t)nb * 8));
+    CK(h->depth_local.reserve((size_t)nb * 16));
+    CK(h->depth_unit.reserve((size_t)nb * 16));
+    CK(cudaMemsetAsync(h->depth_bins.p, 0xff, (size_t)nb * 8, h->st));
+    if (m) {
+        depth_bin_kernel<<<nblk(m, 256), 256, 0, h->st>>>(h->depth_cloud.as<float4>(), m, Ti, num_bins,
+                                                         h->depth_bins.as<unsigned long long>());
+        launched(h);
+    }
+    CK(L.scan_temp.reserve((size_t)(scan_num_tiles(nb) + 2) * 4));
+    exclusive_scan(BinFlagIn{h->depth_bins.as<unsigned long long>()},
+                   BinCompactOut{h->depth_bins.as<unsigned long long>(), h->depth_cloud.as<float4>(), Ti,
+                                 h->depth_local.as<float4>(), h->depth_unit.as<float4>()},
+                   nb, L.scan_temp.as<uint32_t>(), d_total, h->st, &h->call_launches);
+    CK(cudaMemcpyAsync(L.pinned, d_total, 4, cudaMemcpyDeviceToHost, h->st));
+    if (n) {
+        CK(h->depth_feat.reserve(n * 12));
+        CK(h->depth_out.reserve(n * 4));
+        CK(h->depth_f3d.reserve(n * 16));
+        CK(cudaMemcpyAsync(h->depth_feat.p, features_xyz, n * 12, cudaMemcpyHostToDevice, h->st));
+        const float bin_res = 180.0 / (float)num_bins;
+        const float thr = (float)pow(sin(bin_res / 180.0 * M_PI) * 5.0, 2);                   // FT:234
+        depth_feature_kernel<<<(uint32_t)n, kDepthThreads, 0, h->st>>>(h->depth_feat.as<float>(), (uint32_t)n,
+                                                                      h->depth_unit.as<float4>(), d_total, thr,
+                                                                      h->depth_out.as<float>(), h->depth_f3d.as<float4>());
+        launched(h);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(depth_out, h->depth_out.p, n * 4, cudaMemcpyDeviceToHost, h->st));
+        if (features_3d_out) CK(cudaMemcpyAsync(features_3d_out, h->depth_f3d.p, n * 16, cudaMemcpyDeviceToHost, h->st));
+    }
+    mark(h, EV_REG);
+    CK(cudaStreamSynchronize(h->st));
+    h->n_depth_local = L.pinned[0];
+    h->last.register_ms = span(h, EV_BEGIN, EV_REG);
+    finish_timings(h);
+    end_call(h);
+    return LVREG_OK;
 }
 
 // ---- measurement ---------------------------------------------------------------------------------

@@ -218,6 +218,18 @@ int    orc_mo_detect_loop_closure_distance(orc_mo* mo, double time_cur, float ra
 void   orc_mo_perform_loop_closure(orc_mo* mo, int key_cur, int key_pre, int search_num,
                                    const orc_icp_params* P, float fitness_gate, orc_loop_result* out);
 
+/* ---- "next" row: LiDAR depth for visual features, oracle_depth.cpp ----------------
+ * feature_tracker_node.cpp:273-375 (lidar_callback: stack + 0.2 m VoxelGrid) and
+ * feature_tracker.h:150-283 (DepthRegister::get_depth from the camera-frame transform on). */
+typedef struct orc_depth orc_depth;
+orc_depth* orc_depth_create(void);
+void   orc_depth_destroy(orc_depth* d);
+size_t orc_depth_add_cloud(orc_depth* d, const float* cloud, size_t n, const float T_now[12], double stamp);
+size_t orc_depth_cloud_size(const orc_depth* d);
+void   orc_depth_get_cloud(const orc_depth* d, float* out);
+size_t orc_get_depth(const float* depth_cloud, size_t m, const float Tinv[12], const float* feat_xyz,
+                     size_t n, int num_bins, float* depth_out, float* feat3d_out, float* local_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -60,6 +60,10 @@ def lib():
         _lib.orc_mo_extract_nearby.restype = C.c_size_t
         _lib.orc_mo_map_size.restype = C.c_size_t
         _lib.orc_mo_loop_find_near_keyframes.restype = C.c_size_t
+        _lib.orc_depth_create.restype = C.c_void_p
+        _lib.orc_depth_add_cloud.restype = C.c_size_t
+        _lib.orc_depth_cloud_size.restype = C.c_size_t
+        _lib.orc_get_depth.restype = C.c_size_t
     return _lib
 
 
@@ -353,6 +357,44 @@ def correct_pose(correction4x4, pose):
     out = np.zeros(6, np.float32)
     lib().orc_correct_pose(_p(T), _p(pose), _p(out))
     return out
+
+
+# ---- LiDAR depth for visual features, oracle_depth.cpp ------------------------
+class DepthRegister:
+    """lidar_callback's cloud queue + depthCloud (feature_tracker_node.cpp:273-375)"""
+
+    def __init__(self):
+        self.h = C.c_void_p(lib().orc_depth_create())
+
+    def add_cloud(self, cloud, T_now, stamp):
+        cloud = _f32(cloud)
+        T = _f32(T_now).reshape(12)
+        return lib().orc_depth_add_cloud(self.h, _p(cloud), C.c_size_t(len(cloud)), _p(T), C.c_double(stamp))
+
+    def cloud(self):
+        n = lib().orc_depth_cloud_size(self.h)
+        out = np.zeros((n, 4), np.float32)
+        if n:
+            lib().orc_depth_get_cloud(self.h, _p(out))
+        return out
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_depth_destroy(self.h)
+            self.h = None
+
+
+def get_depth(depth_cloud, T_inv, features_xyz, num_bins=360):
+    """DepthRegister::get_depth -> (depth [n], features_3d_sphere [n,4], filtered local cloud [k,4])"""
+    dc = _f32(depth_cloud)
+    T = _f32(T_inv).reshape(12)
+    f = _f32(features_xyz).reshape(-1, 3)
+    depth = np.zeros(len(f), np.float32)
+    f3d = np.zeros((len(f), 4), np.float32)
+    local = np.zeros((max(len(dc), 1), 4), np.float32)
+    k = lib().orc_get_depth(_p(dc), C.c_size_t(len(dc)), _p(T), _p(f), C.c_size_t(len(f)), C.c_int(num_bins),
+                            _p(depth), _p(f3d), _p(local))
+    return depth, f3d, local[:k].copy()
 
 
 class MapOptimization:

@@ -60,6 +60,7 @@ def main():
                         start_ring_index=fsr, end_ring_index=fer, edge_threshold=np.float32(0.5), corner=fc, surf=fs,
                         label=fl.astype(np.int8))
     icp_golden()
+    depth_golden()
     print("golden vectors written to", HERE)
 
 
@@ -89,8 +90,41 @@ def icp_golden():
                         corrected_pose=O.correct_pose(res.T, stored))
 
 
+def depth_golden():
+    """5. LiDAR depth for visual features ("next" row 8f-3): stacked depth cloud + get_depth"""
+    rng = np.random.default_rng(20261020)
+    cw, sw = room_world(rng, n_surf=30000, n_corner=3000, half=8.0, height=5.0)
+    world = np.concatenate([cw, sw]).astype(np.float32)
+    from tests.synth import rot_rpy
+    reg = O.DepthRegister()
+    clouds, Ts, stamps = [], [], []
+    for k in range(3):
+        pose = np.array([0.01 * k, -0.02, 0.15 * k, 0.4 * k - 1.0, 0.1 * k, 0.05], np.float32)
+        R = rot_rpy(*pose[:3])
+        sel = world[rng.choice(len(world), 1200, replace=False)]
+        loc = np.concatenate([(sel[:, :3].astype(np.float64) - pose[3:].astype(np.float64)) @ R, sel[:, 3:4]], 1).astype(np.float32)
+        T = O.pose_to_affine(pose)
+        reg.add_cloud(loc, T, 3.0 * k)                # the first cloud expires when the third arrives
+        clouds.append(loc); Ts.append(T); stamps.append(3.0 * k)
+    depth_cloud = reg.cloud()
+    pose = np.array([0.02, -0.01, 0.3, 0.5, -0.2, 0.1], np.float32)
+    T4 = np.eye(4)
+    T4[:3] = O.pose_to_affine(pose).reshape(3, 4)
+    Tinv = np.linalg.inv(T4)[:3].astype(np.float32).reshape(12)
+    f = np.ones((60, 3), np.float32)
+    f[:, 0] = rng.uniform(-0.9, 0.9, 60)
+    f[:, 1] = rng.uniform(-0.6, 0.6, 60)
+    dense = world[rng.choice(len(world), 7000, replace=False)]
+    d, f3, local = O.get_depth(dense, Tinv, f)
+    np.savez_compressed(os.path.join(HERE, "depth.npz"), cloud0=clouds[0], cloud1=clouds[1], cloud2=clouds[2],
+                        T_now=np.array(Ts), stamps=np.array(stamps), depth_cloud=depth_cloud, dense=dense, T_inv=Tinv,
+                        features=f, depth=d, features_3d=f3, local=local)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "icp":
         icp_golden()
+    elif len(sys.argv) > 1 and sys.argv[1] == "depth":
+        depth_golden()
     else:
         main()

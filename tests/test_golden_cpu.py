@@ -65,6 +65,17 @@ def test_oracle_matches_golden_icp():
     assert np.abs(res.T[:3, 3] - z["pose"][3:]).max() < 3e-2
 
 
+def test_oracle_matches_golden_depth():
+    z = np.load(os.path.join(G, "depth.npz"))
+    reg = O.DepthRegister()
+    for k in range(3):
+        reg.add_cloud(z["cloud%d" % k], z["T_now"][k], float(z["stamps"][k]))
+    assert np.array_equal(reg.cloud(), z["depth_cloud"])
+    d, f3, local = O.get_depth(z["dense"], z["T_inv"], z["features"])
+    assert np.array_equal(d, z["depth"]) and np.array_equal(f3, z["features_3d"]) and np.array_equal(local, z["local"])
+    assert (d > 0).sum() >= 10
+
+
 def _declared_symbols():
     text = open(os.path.join(ROOT, "include", "lvreg.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)

@@ -357,3 +357,48 @@ def test_correct_pose_composes_like_pcl():
         Cm = corr @ W
         assert np.abs(out[3:] - Cm[:3, 3]).max() < 1e-4
         assert np.abs(rot_rpy(*out[:3]) - Cm[:3, :3]).max() < 1e-5
+
+
+# ---- LiDAR depth for visual features ----------------------------------------------
+def test_get_depth_against_a_numpy_restatement():
+    """independent numpy version of feature_tracker.h:150-283 on a small cloud (identity transform)"""
+    rng = np.random.default_rng(17)
+    # a wall at x = 8 m seen through the camera cone, plus clutter behind the camera
+    n = 6000
+    wall = np.stack([np.full(n, 8.0) + rng.normal(0, 0.02, n), rng.uniform(-9, 9, n), rng.uniform(-6, 6, n),
+                     rng.uniform(0, 255, n)], 1).astype(np.float32)
+    back = np.stack([rng.uniform(-9, -1, 500), rng.uniform(-9, 9, 500), rng.uniform(-3, 3, 500), np.zeros(500)], 1).astype(np.float32)
+    dc = np.concatenate([wall, back])
+    f = np.ones((80, 3), np.float32)
+    f[:, 0] = rng.uniform(-0.8, 0.8, 80)
+    f[:, 1] = rng.uniform(-0.5, 0.5, 80)
+    ident = np.array([1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0], np.float32)
+    depth, f3, local = O.get_depth(dc, ident, f)
+    # range image
+    x, y, z = dc[:, 0], dc[:, 1], dc[:, 2]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        keep = (x >= 0) & (np.abs(y / x) <= 10) & (np.abs(z / x) <= 10)
+    row = np.round((np.arctan2(z.astype(np.float64), np.sqrt(x * x + y * y).astype(np.float64)).astype(np.float32).astype(np.float64)
+                    * 180.0 / np.pi + 90.0).astype(np.float32) / np.float32(0.5)).astype(int)
+    col = np.round((np.arctan2(x.astype(np.float64), y.astype(np.float64)).astype(np.float32).astype(np.float64)
+                    * 180.0 / np.pi).astype(np.float32) / np.float32(0.5)).astype(int)
+    keep &= (row >= 0) & (row < 360) & (col >= 0) & (col < 360)
+    dist = np.sqrt((x * x + y * y).astype(np.float32) + z * z)
+    best = {}
+    for i in np.flatnonzero(keep):
+        b = row[i] * 360 + col[i]
+        if b not in best or dist[i] < dist[best[b]]:
+            best[b] = i
+    order = [best[b] for b in sorted(best)]
+    assert np.array_equal(local, dc[order])
+    # depth of a feature that looks at the wall: close to 8 m along the optical axis
+    got = depth[depth > 0]
+    assert len(got) > 40
+    assert np.all(np.abs(got - 8.0) < 0.15)
+    # features_3d: unit vectors (no depth, intensity -1) or scaled by s with intensity = x
+    for i in range(len(f)):
+        v = f3[i, :3].astype(np.float64)
+        if depth[i] > 0:
+            assert f3[i, 3] == f3[i, 0] == depth[i]
+        elif f3[i, 3] == -1:
+            assert abs(np.linalg.norm(v) - 1.0) < 1e-6
