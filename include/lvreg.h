@@ -217,7 +217,8 @@ int lvreg_lm_step(lvreg_handle* h, const float* ori_xyzi, const float* coeff_xyz
 
 /* ---- "next" row: FeatureExtraction on the device ----------------------------- */
 /* The per-point side channels of lidar_odometry/msg/CloudInfo.msg that FeatureExtraction consumes
- * (imageProjection.cpp:624-647); host arrays. */
+ * (imageProjection.cpp:624-647).  The ring indices are host arrays; point_col_ind / point_range may be
+ * host or device pointers (lvreg_get_projection hands out device ones). */
 typedef struct lvreg_scan_info {
     const int32_t* start_ring_index;   /* n_scan entries */
     const int32_t* end_ring_index;     /* n_scan entries */
@@ -326,6 +327,46 @@ int lvreg_depth_set_cloud(lvreg_handle* h, const lvreg_cloud* depth_cloud);
 int lvreg_depth_get_cloud(lvreg_handle* h, int which, lvreg_cloud_out* out, size_t* n);
 int lvreg_get_depth(lvreg_handle* h, const float T_inv[12], const float* features_xyz, size_t n, int num_bins,
                     float* depth_out, float* features_3d_out);
+
+/* ---- "next" row: deskew + range-image projection -------------------------------------
+ * Replaces the per-point work of lidar_odometry/src/imageProjection.cpp: projectPointCloud (571-623)
+ * with deskewPoint (538-569) / findRotation (495-526), and cloudExtraction (625-647).  The IMU
+ * integration that fills imuTime / imuRot{X,Y,Z} (340-408) and the odometry lookup stay on the host
+ * and are inputs.  The result -- extractedCloud plus the CloudInfo side channels start_ring_index,
+ * end_ring_index, point_col_ind, point_range (msg/CloudInfo.msg) -- stays on the device and feeds
+ * lvreg_extract_features directly (lvreg_get_projection), so that a raw scan goes to a registered
+ * pose with one upload. */
+typedef struct lvreg_raw_cloud {       /* laserCloudIn, any AoS layout (PointXYZIRT) */
+    const void* data;
+    size_t      n;
+    uint32_t    stride;                /* bytes per point; x, y, z are floats at offsets 0, 4, 8 */
+    uint32_t    intensity_offset;      /* float */
+    uint32_t    ring_offset;           /* uint16_t */
+    uint32_t    time_offset;           /* float, seconds relative to the scan start */
+    int32_t     on_device;
+    int32_t     reserved;
+} lvreg_raw_cloud;
+typedef struct lvreg_projection_params {
+    int32_t n_scan, horizon_scan, downsample_rate;   /* N_SCAN (<= 255), Horizon_SCAN, downsampleRate */
+    int32_t sensor;                    /* SensorType: 0 VELODYNE, 1 OUSTER, 2 LIVOX */
+    float   lidar_min_range, lidar_max_range;
+    int32_t deskew;                    /* deskewFlag != -1 && cloudInfo.imu_available */
+    int32_t imu_pointer_cur;           /* index of the last valid IMU sample (imuPointerCur after imuDeskewInfo) */
+    double  time_scan_cur;             /* timeScanCur */
+    const double* imu_time;            /* host arrays, imu_pointer_cur + 1 entries */
+    const double* imu_rot_x;
+    const double* imu_rot_y;
+    const double* imu_rot_z;
+} lvreg_projection_params;
+int lvreg_project_cloud(lvreg_handle* h, const lvreg_raw_cloud* in, const lvreg_projection_params* prm,
+                        size_t* n_extracted);
+/* device-resident extractedCloud + side channels of the last projection, in the form
+ * lvreg_extract_features takes (ring indices: host arrays owned by the handle, valid until the next
+ * lvreg_project_cloud; the per-point arrays: device pointers) */
+int lvreg_get_projection(const lvreg_handle* h, lvreg_cloud* extracted, lvreg_scan_info* info);
+/* host copies for the CloudInfo message; every output is optional */
+int lvreg_download_projection(lvreg_handle* h, lvreg_cloud_out* extracted, float* point_range, int32_t* point_col_ind,
+                              int32_t* start_ring_index, int32_t* end_ring_index, size_t* n);
 
 /* ---- measurement -------------------------------------------------------------------------- */
 int lvreg_get_timings(const lvreg_handle* h, lvreg_timings* t);

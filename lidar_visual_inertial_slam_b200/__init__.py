@@ -9,6 +9,7 @@ from .binding import (  # noqa: F401
     CORNER, SURF, KNN_GRID_GATED, KNN_GRID_EXACT, KNN_BRUTE,
     OK, ERR_INVALID, ERR_CUDA, ERR_NOT_ENOUGH_FEATURES, ERR_NO_KEYFRAMES, ERR_NO_MAP, ERR_CAPACITY,
     pose_to_affine, host_alloc_f32,
+    RawCloud, ProjectionParams, make_raw_cloud, SENSOR_VELODYNE, SENSOR_OUSTER, SENSOR_LIVOX, LAYOUT_VELODYNE, LAYOUT_LIVOX,
     IcpParams, IcpResult, LoopResult, icp_default_params, correct_pose,
     ICP_NOT_CONVERGED, ICP_ITERATIONS, ICP_TRANSFORM, ICP_ABS_MSE, ICP_REL_MSE, ICP_NO_CORRESPONDENCES, ICP_NO_INPUT,
     LOOP_OK, LOOP_SUBMAP_TOO_SMALL, LOOP_NOT_CONVERGED, LOOP_FITNESS_TOO_HIGH,

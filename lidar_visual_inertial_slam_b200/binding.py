@@ -81,6 +81,38 @@ class LoopResult(C.Structure):
                 ("noise", C.c_float), ("reserved2", C.c_float)]
 
 
+class RawCloud(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("n", C.c_size_t), ("stride", C.c_uint32), ("intensity_offset", C.c_uint32),
+                ("ring_offset", C.c_uint32), ("time_offset", C.c_uint32), ("on_device", C.c_int32), ("reserved", C.c_int32)]
+
+
+class ProjectionParams(C.Structure):
+    _fields_ = [("n_scan", C.c_int32), ("horizon_scan", C.c_int32), ("downsample_rate", C.c_int32), ("sensor", C.c_int32),
+                ("lidar_min_range", C.c_float), ("lidar_max_range", C.c_float), ("deskew", C.c_int32),
+                ("imu_pointer_cur", C.c_int32), ("time_scan_cur", C.c_double), ("imu_time", C.c_void_p),
+                ("imu_rot_x", C.c_void_p), ("imu_rot_y", C.c_void_p), ("imu_rot_z", C.c_void_p)]
+
+
+SENSOR_VELODYNE, SENSOR_OUSTER, SENSOR_LIVOX = 0, 1, 2
+# (intensity, ring, time) byte offsets of the reference's 32-byte point structs (imageProjection.cpp:4-29)
+LAYOUT_VELODYNE = (16, 20, 24)
+LAYOUT_LIVOX = (16, 24, 20)
+
+
+def make_raw_cloud(xyzi, ring, rel_time, layout=LAYOUT_LIVOX):
+    """pack [n,4] float32 + ring (uint16) + time (float32) into the reference's 32-byte AoS point"""
+    xyzi = np.ascontiguousarray(xyzi, np.float32)
+    n = len(xyzi)
+    buf = np.zeros((n, 32), np.uint8)
+    f = buf.view(np.float32).reshape(n, 8)
+    f[:, 0:3] = xyzi[:, 0:3]
+    f[:, 3] = 1.0
+    f[:, layout[0] // 4] = xyzi[:, 3]
+    f[:, layout[2] // 4] = np.asarray(rel_time, np.float32)
+    buf.view(np.uint16).reshape(n, 16)[:, layout[1] // 2] = np.asarray(ring, np.uint16)
+    return buf
+
+
 ICP_NOT_CONVERGED, ICP_ITERATIONS, ICP_TRANSFORM, ICP_ABS_MSE, ICP_REL_MSE, ICP_NO_CORRESPONDENCES, ICP_NO_INPUT = range(7)
 LOOP_OK, LOOP_SUBMAP_TOO_SMALL, LOOP_NOT_CONVERGED, LOOP_FITNESS_TOO_HIGH = range(4)
 
@@ -360,6 +392,69 @@ class Lvreg:
         self._ck(self.L.lvreg_perform_loop_closure(self.h, int(key_cur), int(key_pre), int(search_num),
                                                    C.byref(params), C.c_float(fitness_gate), C.byref(out)))
         return out
+
+    # ---- deskew + range-image projection ----
+    def project_cloud(self, raw, layout=LAYOUT_LIVOX, n_scan=4, horizon_scan=6000, downsample_rate=1,
+                      sensor=SENSOR_LIVOX, lidar_min_range=0.5, lidar_max_range=1000.0, deskew=False,
+                      time_scan_cur=0.0, imu_time=None, imu_rot=None):
+        """raw: uint8 [n, stride] AoS (make_raw_cloud).  imu_rot: [k,3] integrated rotations.  -> n_extracted"""
+        raw = np.ascontiguousarray(raw, np.uint8)
+        rc = RawCloud()
+        rc.data = raw.ctypes.data if len(raw) else None
+        rc.n = len(raw)
+        rc.stride = raw.shape[1] if raw.ndim == 2 else 32
+        rc.intensity_offset, rc.ring_offset, rc.time_offset = layout
+        rc.on_device = 0
+        pp = ProjectionParams()
+        pp.n_scan, pp.horizon_scan, pp.downsample_rate, pp.sensor = n_scan, horizon_scan, downsample_rate, sensor
+        pp.lidar_min_range, pp.lidar_max_range = lidar_min_range, lidar_max_range
+        pp.deskew = int(bool(deskew))
+        pp.time_scan_cur = time_scan_cur
+        keep = []
+        if deskew:
+            t = np.ascontiguousarray(imu_time, np.float64)
+            r = np.asarray(imu_rot, np.float64)
+            cols = [np.ascontiguousarray(r[:, k]) for k in range(3)]
+            keep = [t] + cols
+            pp.imu_pointer_cur = len(t) - 1
+            pp.imu_time = t.ctypes.data
+            pp.imu_rot_x, pp.imu_rot_y, pp.imu_rot_z = (c.ctypes.data for c in cols)
+        n = C.c_size_t(0)
+        self._ck(self.L.lvreg_project_cloud(self.h, C.byref(rc), C.byref(pp), C.byref(n)))
+        del keep
+        self._proj_n_scan = n_scan
+        return n.value
+
+    def download_projection(self):
+        """-> (extracted [m,4], point_range, point_col_ind, start_ring_index, end_ring_index)"""
+        n = C.c_size_t(0)
+        self._ck(self.L.lvreg_download_projection(self.h, None, None, None, None, None, C.byref(n)))
+        m, ns = n.value, self._proj_n_scan
+        out = np.zeros((m, 4), np.float32)
+        rg = np.zeros(m, np.float32)
+        col = np.zeros(m, np.int32)
+        sr = np.zeros(ns, np.int32)
+        er = np.zeros(ns, np.int32)
+        co = CloudOut()
+        co.data = out.ctypes.data if m else None
+        co.capacity = m
+        co.stride = 16
+        co.intensity_offset = 12
+        self._ck(self.L.lvreg_download_projection(self.h, C.byref(co), rg.ctypes.data_as(C.c_void_p),
+                                                  col.ctypes.data_as(C.c_void_p), sr.ctypes.data_as(C.c_void_p),
+                                                  er.ctypes.data_as(C.c_void_p), C.byref(n)))
+        return out, rg, col, sr, er
+
+    def extract_features_projected(self, edge_threshold=1.0, surf_threshold=0.1, surf_leaf=0.4):
+        """FeatureExtraction on the device-resident result of the last project_cloud -> (n_corner, n_surf)"""
+        cloud = Cloud()
+        info = ScanInfo()
+        self._ck(self.L.lvreg_get_projection(self.h, C.byref(cloud), C.byref(info)))
+        nc, ns = C.c_size_t(0), C.c_size_t(0)
+        self._ck(self.L.lvreg_extract_features(self.h, C.byref(cloud), C.byref(info), C.c_float(edge_threshold),
+                                               C.c_float(surf_threshold), C.c_float(surf_leaf), None, C.byref(nc),
+                                               None, C.byref(ns), None))
+        return nc.value, ns.value
 
     # ---- LiDAR depth for visual features (SURVEY 8f-3) ----
     def depth_clear(self):

@@ -20,6 +20,7 @@
 #include "icp.cuh"
 #include "knn.cuh"
 #include "prims.cuh"
+#include "projection.cuh"
 #include "register.cuh"
 #include "voxelgrid.cuh"
 
@@ -109,6 +110,12 @@ struct lvreg_handle {
     // loop closure: [0] source (cureKeyframeCloud), [1] target (prevKeyframeCloud) + its search grid
     MapSide icp_cloud[2];
     MapSide icp_coarse;                    // second, coarse search grid over the target's points
+    // front end: deskewed + projected scan (extractedCloud and the CloudInfo side channels)
+    DevBuf proj_raw, proj_imu, proj_pts, proj_rangein, proj_colin, proj_small, proj_owner, proj_cloud, proj_range, proj_col,
+        proj_rings;
+    uint32_t n_proj = 0;
+    int proj_n_scan = 0;
+    std::vector<int32_t> proj_start_host, proj_end_host;
     // visual side: stacked depth cloud (depthCloud) and the scratch of get_depth
     std::deque<DepthEntry*> depth_queue;
     std::vector<DepthEntry*> depth_free;   // expired entries, buffers kept for reuse (no cudaMalloc per scan)
@@ -892,6 +899,11 @@ void lvreg_destroy(lvreg_handle* h) {
     for (DepthEntry* e : h->depth_queue) { e->pts.release(); delete e; }
     for (DepthEntry* e : h->depth_free) { e->pts.release(); delete e; }
     {
+        DevBuf* pb[] = {&h->proj_raw, &h->proj_imu, &h->proj_pts, &h->proj_rangein, &h->proj_colin, &h->proj_small,
+                        &h->proj_owner, &h->proj_cloud, &h->proj_range, &h->proj_col, &h->proj_rings};
+        for (DevBuf* b : pb) b->release();
+    }
+    {
         DevBuf* db[] = {&h->depth_cloud, &h->depth_concat, &h->depth_bins, &h->depth_local, &h->depth_unit, &h->depth_feat,
                         &h->depth_out, &h->depth_f3d};
         for (DevBuf* b : db) b->release();
@@ -1486,8 +1498,9 @@ int lvreg_extract_features(lvreg_handle* h, const lvreg_cloud* deskewed, const l
     CK(h->feat_cand.reserve((size_t)(n + 8) * 4));
     CK(h->feat_spec.reserve((size_t)ns * sizeof(RingSpec)));
     CKS(ensure_sort_buffers(h, L, n));
-    CK(cudaMemcpyAsync(h->feat_range.p, info->point_range, (size_t)n * 4, cudaMemcpyHostToDevice, h->st));
-    CK(cudaMemcpyAsync(h->feat_col.p, info->point_col_ind, (size_t)n * 4, cudaMemcpyHostToDevice, h->st));
+    // host or device pointers (lvreg_get_projection hands out device ones): unified addressing decides
+    CK(cudaMemcpyAsync(h->feat_range.p, info->point_range, (size_t)n * 4, cudaMemcpyDefault, h->st));
+    CK(cudaMemcpyAsync(h->feat_col.p, info->point_col_ind, (size_t)n * 4, cudaMemcpyDefault, h->st));
     int32_t* d_start = h->feat_rings.as<int32_t>();
     int32_t* d_end = d_start + ns;
     CK(cudaMemcpyAsync(d_start, info->start_ring_index, (size_t)ns * 4, cudaMemcpyHostToDevice, h->st));
@@ -2111,6 +2124,158 @@ int lvreg_get_depth(lvreg_handle* h, const float T_inv[12], const float* feature
     h->last.register_ms = span(h, EV_BEGIN, EV_REG);
     finish_timings(h);
     end_call(h);
+    return LVREG_OK;
+}
+
+// ---- deskew + range-image projection -----------------------------------------------------
+int lvreg_project_cloud(lvreg_handle* h, const lvreg_raw_cloud* in, const lvreg_projection_params* prm, size_t* n_extracted) {
+    if (!h || !in || !prm) return LVREG_ERR_INVALID;
+    if (in->n && !in->data) return fail(h, LVREG_ERR_INVALID, "raw cloud has n > 0 but no data");
+    if (in->n > 0x7fffffffull) return fail(h, LVREG_ERR_INVALID, "raw cloud too large");
+    if (in->stride < 16 || (in->stride & 3) || in->intensity_offset + 4 > in->stride || (in->intensity_offset & 3) ||
+        in->ring_offset + 2 > in->stride || (in->ring_offset & 1) || in->time_offset + 4 > in->stride || (in->time_offset & 3))
+        return fail(h, LVREG_ERR_INVALID, "bad raw cloud layout");
+    if (prm->n_scan < 1 || prm->n_scan > 255 || prm->horizon_scan < 1 || prm->downsample_rate < 1 ||
+        (int64_t)prm->n_scan * prm->horizon_scan > (1 << 26))
+        return fail(h, LVREG_ERR_INVALID, "bad N_SCAN / Horizon_SCAN / downsampleRate");
+    if (prm->sensor < 0 || prm->sensor > 2) return fail(h, LVREG_ERR_INVALID, "unknown sensor type");
+    if (prm->deskew && (prm->imu_pointer_cur < 0 || !prm->imu_time || !prm->imu_rot_x || !prm->imu_rot_y || !prm->imu_rot_z))
+        return fail(h, LVREG_ERR_INVALID, "deskew requested without IMU rotation samples");
+    CK(cudaSetDevice(h->device));
+    begin_call(h);
+    mark(h, EV_BEGIN);
+    const uint32_t n = (uint32_t)in->n;
+    const int ns = prm->n_scan, H = prm->horizon_scan;
+    const uint32_t cells = (uint32_t)ns * (uint32_t)H;
+    Lane& L = h->lane[LANE_SCAN_SURF];
+    h->n_proj = 0;
+    h->proj_n_scan = ns;
+    h->proj_start_host.assign(ns, 4);        // empty scan: count = 0 everywhere (IP:631, 646)
+    h->proj_end_host.assign(ns, -6);
+    if (n_extracted) *n_extracted = 0;
+    // inputs
+    RawLayout raw;
+    raw.stride = in->stride; raw.intensity_off = in->intensity_offset; raw.ring_off = in->ring_offset; raw.time_off = in->time_offset;
+    if (in->on_device) raw.data = (const uint8_t*)in->data;
+    else {
+        CK(h->proj_raw.reserve((size_t)(n ? n : 1) * in->stride));
+        if (n) CK(cudaMemcpyAsync(h->proj_raw.p, in->data, (size_t)n * in->stride, cudaMemcpyHostToDevice, h->st));
+        raw.data = h->proj_raw.as<uint8_t>();
+    }
+    ProjParams P;
+    P.n_scan = ns; P.horizon = H; P.downsample_rate = prm->downsample_rate; P.sensor = prm->sensor;
+    P.min_range = prm->lidar_min_range; P.max_range = prm->lidar_max_range;
+    P.deskew = prm->deskew ? 1 : 0; P.imu_pointer_cur = prm->imu_pointer_cur; P.time_scan_cur = prm->time_scan_cur;
+    P.imu_time = P.imu_rx = P.imu_ry = P.imu_rz = nullptr;
+    if (P.deskew) {
+        const size_t cnt = (size_t)prm->imu_pointer_cur + 1;
+        CK(h->proj_imu.reserve(cnt * 4 * 8));
+        double* d = h->proj_imu.as<double>();
+        CK(cudaMemcpyAsync(d, prm->imu_time, cnt * 8, cudaMemcpyHostToDevice, h->st));
+        CK(cudaMemcpyAsync(d + cnt, prm->imu_rot_x, cnt * 8, cudaMemcpyHostToDevice, h->st));
+        CK(cudaMemcpyAsync(d + 2 * cnt, prm->imu_rot_y, cnt * 8, cudaMemcpyHostToDevice, h->st));
+        CK(cudaMemcpyAsync(d + 3 * cnt, prm->imu_rot_z, cnt * 8, cudaMemcpyHostToDevice, h->st));
+        P.imu_time = d; P.imu_rx = d + cnt; P.imu_ry = d + 2 * cnt; P.imu_rz = d + 3 * cnt;
+    }
+    // scratch: [0,256) ring counts, [256,512) ring starts, [512] first index, [513] total, [520..) row prefixes,
+    // then transStartInverse
+    const size_t small_words = 520 + (size_t)ns + 8;
+    CK(h->proj_small.reserve(small_words * 4 + sizeof(Affine) + 64));
+    uint32_t* sm = h->proj_small.as<uint32_t>();
+    uint32_t* d_ring_count = sm, *d_ring_start = sm + 256, *d_first = sm + 512, *d_total = sm + 513, *d_row_prefix = sm + 520;
+    Affine* d_start_inv = reinterpret_cast<Affine*>(reinterpret_cast<uint8_t*>(sm) + ((small_words * 4 + 63) & ~(size_t)63));
+    CK(h->proj_pts.reserve((size_t)(n ? n : 1) * 16));
+    CK(h->proj_rangein.reserve((size_t)(n ? n : 1) * 4));
+    CK(h->proj_colin.reserve((size_t)(n ? n : 1) * 4));
+    CK(h->proj_owner.reserve((size_t)(cells + 8) * 4));
+    CK(h->proj_cloud.reserve((size_t)cells * 16));
+    CK(h->proj_range.reserve((size_t)cells * 4));
+    CK(h->proj_col.reserve((size_t)cells * 4));
+    CK(h->proj_rings.reserve((size_t)ns * 8));
+    CKS(ensure_sort_buffers(h, L, n ? n : 1));
+    CK(L.scan_temp.reserve((size_t)(scan_num_tiles(cells) + 2) * 4));
+    CK(cudaMemsetAsync(sm, 0, 512 * 4, h->st));
+    CK(cudaMemsetAsync(d_first, 0xff, 4, h->st));
+    CK(cudaMemsetAsync(h->proj_owner.p, 0xff, (size_t)(cells + 8) * 4, h->st));
+    if (n) {
+        uint32_t* keys = L.keys[0].as<uint32_t>();
+        uint32_t* vals = L.vals[0].as<uint32_t>();
+        proj_classify_kernel<<<nblk(n, 256), 256, 0, h->st>>>(raw, n, P, h->proj_pts.as<float4>(), h->proj_rangein.as<float>(), keys,
+                                                            vals, h->proj_colin.as<int32_t>(), d_ring_count);
+        launched(h);
+        if (P.sensor == 2) {
+            // columnIdnCountVec: rank of the point among the earlier accepted points of its ring
+            proj_ring_starts_kernel<<<1, 32, 0, h->st>>>(d_ring_count, ns, d_ring_start);
+            // the sort permutes (keys, vals); the claim kernel needs the unsorted keys: sort a copy
+            CK(cudaMemcpyAsync(L.keys[1].p, keys, (size_t)n * 4, cudaMemcpyDeviceToDevice, h->st));
+            CK(cudaMemcpyAsync(L.vals[1].p, vals, (size_t)n * 4, cudaMemcpyDeviceToDevice, h->st));
+            CK(h->feat_idx.reserve((size_t)n * 4));
+            CK(h->feat_pidx.reserve((size_t)n * 4));
+            int cur = radix_sort_pairs(L.keys[1].as<uint32_t>(), L.vals[1].as<uint32_t>(), h->feat_idx.as<uint32_t>(),
+                                       h->feat_pidx.as<uint32_t>(), n, 8, L.sort_scratch.as<uint32_t>(), h->st, &h->call_launches);
+            const uint32_t* sk = cur ? h->feat_idx.as<uint32_t>() : L.keys[1].as<uint32_t>();
+            const uint32_t* sv = cur ? h->feat_pidx.as<uint32_t>() : L.vals[1].as<uint32_t>();
+            proj_livox_columns_kernel<<<nblk(n, 256), 256, 0, h->st>>>(sk, sv, n, d_ring_start, h->proj_colin.as<int32_t>());
+            launched(h, 2);
+        }
+        proj_claim_kernel<<<nblk(n, 256), 256, 0, h->st>>>(keys, h->proj_colin.as<int32_t>(), n, H, h->proj_owner.as<uint32_t>(), d_first);
+        proj_start_kernel<<<1, 32, 0, h->st>>>(P, raw, d_first, d_start_inv);
+        launched(h, 2);
+    }
+    CellExtractOut out;
+    out.owner = h->proj_owner.as<uint32_t>(); out.pts = h->proj_pts.as<float4>(); out.range = h->proj_rangein.as<float>();
+    out.in = raw; out.P = P; out.start_inv = d_start_inv; out.extracted = h->proj_cloud.as<float4>();
+    out.point_range = h->proj_range.as<float>(); out.point_col_ind = h->proj_col.as<int32_t>(); out.row_prefix = d_row_prefix;
+    exclusive_scan(CellFlagIn{h->proj_owner.as<uint32_t>()}, out, cells, L.scan_temp.as<uint32_t>(), d_total, h->st, &h->call_launches);
+    int32_t* d_start = h->proj_rings.as<int32_t>();
+    int32_t* d_end = d_start + ns;
+    proj_ring_index_kernel<<<nblk((uint32_t)ns, 128), 128, 0, h->st>>>(d_row_prefix, d_total, ns, d_start, d_end);
+    launched(h);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(L.pinned, d_total, 4, cudaMemcpyDeviceToHost, h->st));
+    CK(cudaMemcpyAsync(h->proj_start_host.data(), d_start, (size_t)ns * 4, cudaMemcpyDeviceToHost, h->st));
+    CK(cudaMemcpyAsync(h->proj_end_host.data(), d_end, (size_t)ns * 4, cudaMemcpyDeviceToHost, h->st));
+    mark(h, EV_DS);
+    CK(cudaStreamSynchronize(h->st));
+    h->n_proj = L.pinned[0];
+    h->last.downsample_ms = span(h, EV_BEGIN, EV_DS);
+    finish_timings(h);
+    end_call(h);
+    if (n_extracted) *n_extracted = h->n_proj;
+    return LVREG_OK;
+}
+
+int lvreg_get_projection(const lvreg_handle* h, lvreg_cloud* extracted, lvreg_scan_info* info) {
+    if (!h || !extracted || !info) return LVREG_ERR_INVALID;
+    if (h->proj_n_scan == 0) return LVREG_ERR_INVALID;
+    extracted->data = h->proj_cloud.p;
+    extracted->n = h->n_proj;
+    extracted->stride = 16;
+    extracted->intensity_offset = 12;
+    extracted->on_device = 1;
+    extracted->reserved = 0;
+    info->start_ring_index = h->proj_start_host.data();
+    info->end_ring_index = h->proj_end_host.data();
+    info->n_scan = h->proj_n_scan;
+    info->reserved = 0;
+    info->point_col_ind = h->proj_col.as<int32_t>();
+    info->point_range = h->proj_range.as<float>();
+    return LVREG_OK;
+}
+
+int lvreg_download_projection(lvreg_handle* h, lvreg_cloud_out* extracted, float* point_range, int32_t* point_col_ind,
+                              int32_t* start_ring_index, int32_t* end_ring_index, size_t* n) {
+    if (!h) return LVREG_ERR_INVALID;
+    if (h->proj_n_scan == 0) return fail(h, LVREG_ERR_INVALID, "no projected scan");
+    CK(cudaSetDevice(h->device));
+    if (n) *n = h->n_proj;
+    const uint32_t m = h->n_proj;
+    if (start_ring_index) memcpy(start_ring_index, h->proj_start_host.data(), (size_t)h->proj_n_scan * 4);
+    if (end_ring_index) memcpy(end_ring_index, h->proj_end_host.data(), (size_t)h->proj_n_scan * 4);
+    if (point_range && m) CK(cudaMemcpyAsync(point_range, h->proj_range.p, (size_t)m * 4, cudaMemcpyDeviceToHost, h->st));
+    if (point_col_ind && m) CK(cudaMemcpyAsync(point_col_ind, h->proj_col.p, (size_t)m * 4, cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    if (extracted) return download_cloud(h, h->proj_cloud.as<float4>(), m, extracted);
     return LVREG_OK;
 }
 

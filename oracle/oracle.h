@@ -230,6 +230,26 @@ void   orc_depth_get_cloud(const orc_depth* d, float* out);
 size_t orc_get_depth(const float* depth_cloud, size_t m, const float Tinv[12], const float* feat_xyz,
                      size_t n, int num_bins, float* depth_out, float* feat3d_out, float* local_out);
 
+/* ---- "next" row: deskew + range-image projection, oracle_projection.cpp -----------
+ * imageProjection.cpp:495-647 (findRotation, deskewPoint, projectPointCloud, cloudExtraction). */
+typedef struct orc_projection_params {
+    int n_scan, horizon_scan, downsample_rate;
+    int sensor;                      /* 0 velodyne, 1 ouster, 2 livox (utility.h SensorType) */
+    float lidar_min_range, lidar_max_range;
+    int deskew;                      /* deskewFlag != -1 && cloudInfo.imu_available */
+    int imu_pointer_cur;             /* index of the last valid IMU sample */
+    double time_scan_cur;
+    const double* imu_time;
+    const double* imu_rot_x;
+    const double* imu_rot_y;
+    const double* imu_rot_z;
+} orc_projection_params;
+void orc_find_rotation(double point_time, const double* imu_time, const double* rx, const double* ry,
+                       const double* rz, int imu_pointer_cur, float rot[3]);
+size_t orc_project_cloud(const float* pts, const uint16_t* ring, const float* rel_time, size_t n,
+                         const orc_projection_params* P, float* extracted, float* point_range,
+                         int32_t* point_col_ind, int32_t* start_ring_index, int32_t* end_ring_index);
+
 #ifdef __cplusplus
 }
 #endif

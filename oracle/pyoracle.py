@@ -60,6 +60,7 @@ def lib():
         _lib.orc_mo_extract_nearby.restype = C.c_size_t
         _lib.orc_mo_map_size.restype = C.c_size_t
         _lib.orc_mo_loop_find_near_keyframes.restype = C.c_size_t
+        _lib.orc_project_cloud.restype = C.c_size_t
         _lib.orc_depth_create.restype = C.c_void_p
         _lib.orc_depth_add_cloud.restype = C.c_size_t
         _lib.orc_depth_cloud_size.restype = C.c_size_t
@@ -357,6 +358,56 @@ def correct_pose(correction4x4, pose):
     out = np.zeros(6, np.float32)
     lib().orc_correct_pose(_p(T), _p(pose), _p(out))
     return out
+
+
+# ---- deskew + range-image projection, oracle_projection.cpp ------------------
+class ProjectionParams(C.Structure):
+    _fields_ = [("n_scan", C.c_int), ("horizon_scan", C.c_int), ("downsample_rate", C.c_int), ("sensor", C.c_int),
+                ("lidar_min_range", C.c_float), ("lidar_max_range", C.c_float), ("deskew", C.c_int),
+                ("imu_pointer_cur", C.c_int), ("time_scan_cur", C.c_double), ("imu_time", C.c_void_p),
+                ("imu_rot_x", C.c_void_p), ("imu_rot_y", C.c_void_p), ("imu_rot_z", C.c_void_p)]
+
+
+def find_rotation(point_time, imu_time, imu_rot):
+    t = np.ascontiguousarray(imu_time, np.float64)
+    r = np.asarray(imu_rot, np.float64)
+    cols = [np.ascontiguousarray(r[:, k]) for k in range(3)]
+    rot = np.zeros(3, np.float32)
+    lib().orc_find_rotation(C.c_double(point_time), _p(t), _p(cols[0]), _p(cols[1]), _p(cols[2]), C.c_int(len(t) - 1), _p(rot))
+    return rot
+
+
+def project_cloud(xyzi, ring, rel_time, n_scan=4, horizon_scan=6000, downsample_rate=1, sensor=2,
+                  lidar_min_range=0.5, lidar_max_range=1000.0, deskew=False, time_scan_cur=0.0, imu_time=None,
+                  imu_rot=None):
+    """projectPointCloud + cloudExtraction -> (extracted, point_range, point_col_ind, start_ring, end_ring)"""
+    pts = _f32(xyzi)
+    ring = np.ascontiguousarray(ring, np.uint16)
+    rel = _f32(rel_time)
+    pp = ProjectionParams()
+    pp.n_scan, pp.horizon_scan, pp.downsample_rate, pp.sensor = n_scan, horizon_scan, downsample_rate, sensor
+    pp.lidar_min_range, pp.lidar_max_range = lidar_min_range, lidar_max_range
+    pp.deskew = int(bool(deskew))
+    pp.time_scan_cur = time_scan_cur
+    keep = []
+    if deskew:
+        t = np.ascontiguousarray(imu_time, np.float64)
+        r = np.asarray(imu_rot, np.float64)
+        cols = [np.ascontiguousarray(r[:, k]) for k in range(3)]
+        keep = [t] + cols
+        pp.imu_pointer_cur = len(t) - 1
+        pp.imu_time = t.ctypes.data
+        pp.imu_rot_x, pp.imu_rot_y, pp.imu_rot_z = (c.ctypes.data for c in cols)
+    cells = n_scan * horizon_scan
+    out = np.zeros((cells, 4), np.float32)
+    rg = np.zeros(cells, np.float32)
+    col = np.zeros(cells, np.int32)
+    sr = np.zeros(n_scan, np.int32)
+    er = np.zeros(n_scan, np.int32)
+    m = lib().orc_project_cloud(_p(pts), _p(ring), _p(rel), C.c_size_t(len(pts)), C.byref(pp), _p(out), _p(rg), _p(col),
+                                _p(sr), _p(er))
+    del keep
+    return out[:m].copy(), rg[:m].copy(), col[:m].copy(), sr, er
 
 
 # ---- LiDAR depth for visual features (SURVEY 8f-3), oracle_depth.cpp ------------------------

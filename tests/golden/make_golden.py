@@ -61,6 +61,7 @@ def main():
                         label=fl.astype(np.int8))
     icp_golden()
     depth_golden()
+    projection_golden()
     print("golden vectors written to", HERE)
 
 
@@ -121,8 +122,28 @@ def depth_golden():
                         features=f, depth=d, features_3d=f3, local=local)
 
 
+def projection_golden():
+    """6. deskew + range-image projection ("next" row 8f-4)"""
+    rng = np.random.default_rng(20261021)
+    n, NS, H = 6000, 4, 1200
+    d = rng.normal(0, 1, (n, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    xyzi = np.concatenate([d * rng.uniform(0.3, 28, (n, 1)), rng.uniform(0, 255, (n, 1))], 1).astype(np.float32)
+    ring = rng.integers(0, NS + 1, n).astype(np.uint16)
+    rel = np.sort(rng.uniform(0, 0.1, n)).astype(np.float32)
+    t = 200.0 - 0.01 + np.arange(30) * 0.005
+    rot = np.cumsum(rng.normal(0, 0.004, (30, 3)), 0)
+    ext, rg, col, sr, er = O.project_cloud(xyzi, ring, rel, n_scan=NS, horizon_scan=H, sensor=2, lidar_min_range=1.0,
+                                           lidar_max_range=25.0, deskew=True, time_scan_cur=200.0, imu_time=t, imu_rot=rot)
+    np.savez_compressed(os.path.join(HERE, "projection.npz"), xyzi=xyzi, ring=ring, rel_time=rel, imu_time=t, imu_rot=rot,
+                        n_scan=np.int32(NS), horizon=np.int32(H), extracted=ext, point_range=rg, point_col_ind=col,
+                        start_ring_index=sr, end_ring_index=er)
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "icp":
+    if len(sys.argv) > 1 and sys.argv[1] == "projection":
+        projection_golden()
+    elif len(sys.argv) > 1 and sys.argv[1] == "icp":
         icp_golden()
     elif len(sys.argv) > 1 and sys.argv[1] == "depth":
         depth_golden()

@@ -76,6 +76,22 @@ def test_oracle_matches_golden_depth():
     assert (d > 0).sum() >= 10
 
 
+def _golden_projection():
+    z = np.load(os.path.join(G, "projection.npz"))
+    kw = dict(n_scan=int(z["n_scan"]), horizon_scan=int(z["horizon"]), sensor=2, lidar_min_range=1.0, lidar_max_range=25.0,
+              deskew=True, time_scan_cur=200.0, imu_time=z["imu_time"], imu_rot=z["imu_rot"])
+    want = (z["extracted"], z["point_range"], z["point_col_ind"], z["start_ring_index"], z["end_ring_index"])
+    return z, kw, want
+
+
+def test_oracle_matches_golden_projection():
+    z, kw, want = _golden_projection()
+    got = O.project_cloud(z["xyzi"], z["ring"], z["rel_time"], **kw)
+    for a, b in zip(got, want):
+        assert np.array_equal(a, b)
+    assert len(got[0]) > 1000
+
+
 def _declared_symbols():
     text = open(os.path.join(ROOT, "include", "lvreg.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)

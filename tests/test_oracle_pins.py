@@ -402,3 +402,72 @@ def test_get_depth_against_a_numpy_restatement():
             assert f3[i, 3] == f3[i, 0] == depth[i]
         elif f3[i, 3] == -1:
             assert abs(np.linalg.norm(v) - 1.0) < 1e-6
+
+
+# ---- deskew + range-image projection ----------------------------------------------
+def test_find_rotation_matches_linear_interpolation():
+    rng = np.random.default_rng(21)
+    t = 50.0 + np.cumsum(rng.uniform(0.004, 0.006, 30))
+    rot = np.cumsum(rng.normal(0, 0.01, (30, 3)), 0)
+    for pt in np.concatenate([rng.uniform(t[0], t[-1], 200), t[[3, 7, 29]]]):
+        got = O.find_rotation(pt, t, rot)
+        want = np.array([np.interp(pt, t, rot[:, k]) for k in range(3)])
+        assert np.abs(got - want).max() < 1e-6
+    # before the first sample: the first sample; after the last: the last (imageProjection.cpp:507-511)
+    assert np.array_equal(O.find_rotation(t[0] - 1.0, t, rot), rot[0].astype(np.float32))
+    assert np.array_equal(O.find_rotation(t[-1] + 1.0, t, rot), rot[-1].astype(np.float32))
+
+
+def test_project_cloud_against_a_python_loop():
+    """projectPointCloud + cloudExtraction (imageProjection.cpp:571-647) restated as a plain loop, Livox mode,
+    no deskew: column counters advance for every point that passes the range / ring / rate filters"""
+    rng = np.random.default_rng(22)
+    n, NS, H = 3000, 4, 400
+    xyzi = np.concatenate([rng.normal(0, 6, (n, 3)), rng.uniform(0, 255, (n, 1))], 1).astype(np.float32)
+    ring = rng.integers(0, NS + 2, n).astype(np.uint16)
+    rel = np.zeros(n, np.float32)
+    ext, rg, col, sr, er = O.project_cloud(xyzi, ring, rel, n_scan=NS, horizon_scan=H, downsample_rate=2, sensor=2,
+                                           lidar_min_range=2.0, lidar_max_range=15.0)
+    counters = [0] * NS
+    cells = {}
+    for i in range(n):
+        x, y, z = xyzi[i, :3]
+        r = np.sqrt(np.float32(np.float32(x * x + y * y) + z * z))
+        if r < 2.0 or r > 15.0 or ring[i] >= NS or ring[i] % 2 != 0:
+            continue
+        c = counters[ring[i]]
+        counters[ring[i]] += 1
+        if c >= H or (int(ring[i]), c) in cells:
+            continue
+        cells[(int(ring[i]), c)] = (i, r)
+    order = sorted(cells)
+    assert np.array_equal(ext, xyzi[[cells[k][0] for k in order]])
+    assert np.array_equal(col, np.array([k[1] for k in order], np.int32))
+    assert np.array_equal(rg, np.array([cells[k][1] for k in order], np.float32))
+    count = 0
+    for r_ in range(NS):
+        assert sr[r_] == count - 1 + 5
+        count += sum(1 for k in order if k[0] == r_)
+        assert er[r_] == count - 1 - 5
+    assert any(v > H for v in counters)          # the overflow branch was exercised
+
+
+def test_deskew_is_identity_for_a_constant_rotation_and_undoes_a_known_spin():
+    from tests.synth import rot_rpy
+    rng = np.random.default_rng(23)
+    n = 500
+    xyzi = np.concatenate([rng.normal(0, 8, (n, 3)), np.zeros((n, 1))], 1).astype(np.float32)
+    ring = np.zeros(n, np.uint16)
+    rel = np.linspace(0, 0.1, n).astype(np.float32)
+    t = np.linspace(-0.01, 0.12, 27)
+    const = np.tile([0.1, -0.05, 0.3], (27, 1))
+    ext, *_ = O.project_cloud(xyzi, ring, rel, n_scan=1, horizon_scan=n, sensor=2, lidar_min_range=0.0, deskew=True,
+                              time_scan_cur=0.0, imu_time=t, imu_rot=const)
+    assert np.abs(ext[:, :3] - xyzi[:, :3]).max() < 2e-5           # R_start^-1 R_start = identity up to rounding
+    # pure yaw spin at 1 rad/s: a point seen at time s is rotated back by yaw(s) - yaw(0)
+    spin = np.stack([np.zeros(27), np.zeros(27), t - t[0]], 1)
+    ext, *_ = O.project_cloud(xyzi, ring, rel, n_scan=1, horizon_scan=n, sensor=2, lidar_min_range=0.0, deskew=True,
+                              time_scan_cur=0.0, imu_time=t, imu_rot=spin)
+    for i in (0, 100, 499):
+        want = rot_rpy(0, 0, float(rel[i]) - float(rel[0])) @ xyzi[i, :3].astype(np.float64)
+        assert np.abs(ext[i, :3] - want).max() < 1e-4
