@@ -291,6 +291,13 @@ typedef struct lvreg_loop_result {
 void lvreg_icp_default_params(lvreg_icp_params* p);
 /* loopFindNearKeyframes into slot 0 (ICP source) or 1 (ICP target, also builds its search grid) */
 int lvreg_loop_find_near_keyframes(lvreg_handle* h, int key, int search_num, int slot, size_t* n_out);
+/* Global map for visualisation / saving (publishGlobalMap MO:493-508; saveMapService MO:199-231): the
+ * clouds selected by `which` (1 corner, 2 surf, 3 corner then surf of each keyframe) of the listed
+ * keyframes under their stored poses, concatenated in list order, then one VoxelGrid with `leaf`
+ * (globalMapVisualizationLeafSize / the service's resolution).  The result replaces slot 0; read it back
+ * with lvreg_icp_get_cloud(h, 0, ...).  The key-pose selection (radius search + pose-density VoxelGrid,
+ * MO:476-491) is host logic over a few hundred poses. */
+int lvreg_build_global_map(lvreg_handle* h, const int32_t* ids, size_t n_ids, int which, float leaf, size_t* n_out);
 /* setInputSource (slot 0) / setInputTarget (slot 1) from a caller-provided cloud */
 int lvreg_icp_set_cloud(lvreg_handle* h, int slot, const lvreg_cloud* cloud);
 int lvreg_icp_get_cloud(lvreg_handle* h, int slot, lvreg_cloud_out* out, size_t* n);

@@ -365,6 +365,13 @@ class Lvreg:
         self._ck(self.L.lvreg_loop_find_near_keyframes(self.h, int(key), int(search_num), int(slot), C.byref(n)))
         return n.value
 
+    def build_global_map(self, ids, which=3, leaf=1.0):
+        ids = np.ascontiguousarray(ids, np.int32)
+        n = C.c_size_t(0)
+        self._ck(self.L.lvreg_build_global_map(self.h, ids.ctypes.data_as(C.c_void_p), C.c_size_t(len(ids)), int(which),
+                                               C.c_float(leaf), C.byref(n)))
+        return self.icp_get_cloud(0)
+
     def icp_set_cloud(self, slot, cloud):
         c, _keep = _cloud(cloud)
         self._ck(self.L.lvreg_icp_set_cloud(self.h, int(slot), C.byref(c)))

@@ -1685,19 +1685,20 @@ int build_icp_grids(lvreg_handle* h, const float* mn, const float* mx) {
 }
 constexpr size_t kPinnedIcpState = 48 * 1024;
 
-// loopFindNearKeyframes for one slot: fills the lane's segment list and the VoxelGrid job
-int prepare_loop_job(lvreg_handle* h, int key, int search_num, int slot, VgJob& J) {
+// segment list + VoxelGrid job of a keyframe submap on lane `slot`: the clouds selected by `which`
+// (bit 0 corner, bit 1 surf; corner first) of every listed keyframe under its stored pose, in list order
+int prepare_submap_job(lvreg_handle* h, const int32_t* ids, size_t n_ids, int which, float leaf, int slot, VgJob& J) {
     Lane& L = h->lane[slot];
     MapSide& ms = h->icp_cloud[slot];
     L.seg_host.clear();
     uint64_t total = 0;
     const int K = (int)h->kfs.size();
-    for (int i = -search_num; i <= search_num; ++i) {
-        const int k = key + i;
-        if (k < 0 || k >= K) continue;
+    for (size_t i = 0; i < n_ids; ++i) {
+        const int k = ids[i];
+        if (k < 0 || k >= K) return fail(h, LVREG_ERR_INVALID, "keyframe id out of range");
         const Keyframe* kf = h->kfs[k];
-        for (int s = 0; s < 2; ++s) {              // corner, then surf, of every keyframe (MO:730-731)
-            if (kf->n[s] == 0) continue;
+        for (int s = 0; s < 2; ++s) {              // corner, then surf, of every keyframe (MO:730-731, 500-501)
+            if (!(which & (1 << s)) || kf->n[s] == 0) continue;
             Segment sg;
             sg.src = kf->cloud[s].as<float4>();
             sg.begin = (uint32_t)total;
@@ -1707,17 +1708,29 @@ int prepare_loop_job(lvreg_handle* h, int key, int search_num, int slot, VgJob& 
             total += kf->n[s];
         }
     }
-    if (total > 0x7fffffffull) return fail(h, LVREG_ERR_INVALID, "loop-closure submap too large");
+    if (total > 0x7fffffffull) return fail(h, LVREG_ERR_INVALID, "submap too large");
     ms.n_in = total;
     ms.valid = false;
     J = VgJob();
     J.lane = slot;
     J.n = (uint32_t)total;
     J.from_segments = true;
-    J.leaf = h->prm.surf_leaf;                     // downSizeFilterICP, MO:249
+    J.leaf = leaf;
     J.out = &ms.ds;
     J.n_out = &ms.m;
     return LVREG_OK;
+}
+
+// loopFindNearKeyframes for one slot (MO:719-741): keyframes [key - n, key + n], downSizeFilterICP (MO:249)
+int prepare_loop_job(lvreg_handle* h, int key, int search_num, int slot, VgJob& J) {
+    std::vector<int32_t> ids;
+    const int K = (int)h->kfs.size();
+    for (int i = -search_num; i <= search_num; ++i) {
+        const int k = key + i;
+        if (k < 0 || k >= K) continue;
+        ids.push_back(k);
+    }
+    return prepare_submap_job(h, ids.data(), ids.size(), 3, h->prm.surf_leaf, slot, J);
 }
 
 IcpParams icp_params_dev(const lvreg_icp_params* p) {
@@ -1834,6 +1847,29 @@ int lvreg_loop_find_near_keyframes(lvreg_handle* h, int key, int search_num, int
     finish_timings(h);
     end_call(h);
     if (n_out) *n_out = h->icp_cloud[slot].m;
+    return LVREG_OK;
+}
+
+// global map for visualisation / saving (publishGlobalMap MO:493-508, saveMapService MO:199-231): the selected
+// clouds of the listed keyframes under their stored poses, concatenated in list order, then one VoxelGrid
+int lvreg_build_global_map(lvreg_handle* h, const int32_t* ids, size_t n_ids, int which, float leaf, size_t* n_out) {
+    if (!h || (!ids && n_ids) || which < 1 || which > 3 || !(leaf > 0.f)) return LVREG_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    if (h->kfs.empty()) return fail(h, LVREG_ERR_NO_KEYFRAMES, "no keyframes");
+    begin_call(h);
+    mark(h, EV_BEGIN);
+    VgJob J;
+    CKS(prepare_submap_job(h, ids, n_ids, which, leaf, 0, J));
+    lanes_fork(h, 0x1);
+    CKS(voxelgrid_batch(h, &J, 1));
+    lanes_join(h, 0x1);
+    mark(h, EV_MAP);
+    CK(cudaStreamSynchronize(h->st));
+    h->icp_cloud[0].valid = true;                 // read back with lvreg_icp_get_cloud(h, 0, ...)
+    h->last.map_build_ms = span(h, EV_BEGIN, EV_MAP);
+    finish_timings(h);
+    end_call(h);
+    if (n_out) *n_out = h->icp_cloud[0].m;
     return LVREG_OK;
 }
 

@@ -175,6 +175,62 @@ bool mapOptimization::performLoopClosure() {
     return true;
 }
 
+// publishGlobalMap, MO:460-510: key poses within the visualisation radius, thinned by a pose-density
+// VoxelGrid, their corner + surf clouds under the stored poses, one VoxelGrid -- all point work on the device
+Cloud mapOptimization::publishGlobalMap() {
+    Cloud out;
+    const size_t K = cloudKeyPoses3D.size();
+    if (K == 0) return out;
+    const PointType& last = cloudKeyPoses3D.back();
+    const float r2 = P_.globalMapVisualizationSearchRadius * P_.globalMapVisualizationSearchRadius;
+    std::vector<std::pair<float, int>> hits;
+    for (size_t i = 0; i < K; ++i) {
+        const PointType& p = cloudKeyPoses3D[i];
+        float dx = last.x - p.x, dy = last.y - p.y, dz = last.z - p.z;
+        float d2 = dx * dx;
+        d2 += dy * dy;
+        d2 += dz * dz;
+        if (d2 < r2) hits.emplace_back(d2, (int)i);
+    }
+    std::sort(hits.begin(), hits.end());
+    Cloud globalMapKeyPoses(hits.size());
+    for (size_t i = 0; i < hits.size(); ++i) globalMapKeyPoses[i] = cloudKeyPoses3D[hits[i].second];
+    Cloud globalMapKeyPosesDS(globalMapKeyPoses.size());
+    size_t nds = 0;
+    {
+        lvreg_cloud in = as_lvreg_cloud(globalMapKeyPoses);
+        lvreg_cloud_out o = as_lvreg_out(globalMapKeyPosesDS);
+        int pt = 0;
+        int st = lvreg_voxelgrid(h_, &in, P_.globalMapVisualizationPoseDensity, &o, &nds, nullptr, &pt);
+        if (st != LVREG_OK) throw std::runtime_error(std::string("lvreg_voxelgrid: ") + lvreg_last_error(h_));
+    }
+    globalMapKeyPosesDS.resize(nds);
+    std::vector<int32_t> ids;
+    for (PointType& pt : globalMapKeyPosesDS) {               // 1-NN back to a real key pose, MO:487-491
+        float best = INFINITY;
+        int besti = 0;
+        for (size_t i = 0; i < K; ++i) {
+            const PointType& p = cloudKeyPoses3D[i];
+            float dx = pt.x - p.x, dy = pt.y - p.y, dz = pt.z - p.z;
+            float d2 = dx * dx;
+            d2 += dy * dy;
+            d2 += dz * dz;
+            if (d2 < best) { best = d2; besti = (int)i; }
+        }
+        pt.intensity = cloudKeyPoses3D[besti].intensity;
+        if (pointDistance(pt, last) > P_.globalMapVisualizationSearchRadius) continue;   // MO:496-497
+        ids.push_back((int32_t)pt.intensity);
+    }
+    size_t n = 0;
+    int st = lvreg_build_global_map(h_, ids.data(), ids.size(), 3, P_.globalMapVisualizationLeafSize, &n);
+    if (st != LVREG_OK) throw std::runtime_error(std::string("lvreg_build_global_map: ") + lvreg_last_error(h_));
+    out.resize(n);
+    lvreg_cloud_out o = as_lvreg_out(out);
+    st = lvreg_icp_get_cloud(h_, 0, &o, &n);
+    if (st != LVREG_OK) throw std::runtime_error(std::string("lvreg_icp_get_cloud: ") + lvreg_last_error(h_));
+    return out;
+}
+
 void mapOptimization::extractSurroundingKeyFrames() {
     if (cloudKeyPoses3D.empty()) return;                     // MO:974-975
     std::vector<int32_t> ids = extractNearby();

@@ -44,6 +44,9 @@ struct ParamServer {
     float surroundingkeyframeAddingAngleThreshold = 0.2f;   // utility.h:281
     bool  sensorIsLivox = true;                             // MO:1392-1396: keyframe every > 1.0 s
     double mappingProcessInterval = 0.15;                   // utility.h:283, MO:311-314
+    float globalMapVisualizationSearchRadius = 1000.0f;     // utility.h:306
+    float globalMapVisualizationPoseDensity = 10.0f;        // utility.h:308
+    float globalMapVisualizationLeafSize = 1.0f;            // utility.h:310
     float historyKeyframeSearchRadius = 15.0f;              // utility.h:296
     float historyKeyframeSearchTimeDiff = 30.0f;            // utility.h:298
     int   historyKeyframeSearchNum = 25;                    // utility.h:300
@@ -98,6 +101,9 @@ class mapOptimization {
     lvreg_loop_result lastLoop;
     bool detectLoopClosureDistance(int* latestID, int* closestID);   // MO:630-661
     bool performLoopClosure();                                       // MO:549-628; true when a constraint was queued
+
+    // publishGlobalMap (MO:460-510) without the ROS publisher: returns globalMapKeyFramesDS
+    Cloud publishGlobalMap();
 
     // read-backs of device-resident clouds (laserCloud*LastDS / *FromMapDS)
     Cloud getLaserCloudLastDS(int which);

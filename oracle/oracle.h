@@ -212,6 +212,8 @@ void orc_correct_pose(const float* correction4x4, const float pose[6], float out
 /* loopFindNearKeyframes into slot 0 (source) or 1 (target); returns the row count */
 size_t orc_mo_loop_find_near_keyframes(orc_mo* mo, int key, int search_num, int slot);
 void   orc_mo_get_loop_cloud(const orc_mo* mo, int slot, float* out);
+/* publishGlobalMap MO:493-508 / saveMapService MO:199-231 for an explicit id list; result in slot 0 */
+size_t orc_mo_build_global_map(orc_mo* mo, const int32_t* ids, size_t n_ids, int which, float leaf);
 /* detectLoopClosureDistance without the loopIndexContainer bookkeeping; returns 1 when a pair was found */
 int    orc_mo_detect_loop_closure_distance(orc_mo* mo, double time_cur, float radius, float time_diff,
                                            int* key_cur, int* key_pre);

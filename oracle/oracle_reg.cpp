@@ -566,3 +566,29 @@ extern "C" void orc_mo_perform_loop_closure(orc_mo* mo, int key_cur, int key_pre
     out->noise = (float)out->icp.fitness;
     out->status = 0;
 }
+
+// global map (publishGlobalMap MO:493-508, saveMapService MO:199-231): selected clouds of the listed
+// keyframes under their stored poses, list order, one VoxelGrid; result in loop slot 0
+extern "C" size_t orc_mo_build_global_map(orc_mo* mo, const int32_t* ids, size_t n_ids, int which, float leaf) {
+    std::vector<float> cat;
+    for (size_t i = 0; i < n_ids; ++i) {
+        const int k = ids[i];
+        float T[12];
+        orc_pose_to_affine(&mo->poses[6 * (size_t)k], T);
+        for (int w = 0; w < 2; ++w) {
+            if (!(which & (1 << w))) continue;
+            const std::vector<float>& src = w == 0 ? mo->corner_kf[k] : mo->surf_kf[k];
+            const size_t at = cat.size();
+            cat.resize(at + src.size());
+            orc_transform_cloud(src.data(), src.size() / 4, T, cat.data() + at, mo->P.num_threads);
+        }
+    }
+    std::vector<float>& out = mo->loop_cloud[0];
+    out.clear();
+    if (cat.empty()) return 0;
+    out.resize(cat.size());
+    int pass;
+    const size_t n = orc_voxelgrid(cat.data(), cat.size() / 4, leaf, out.data(), nullptr, nullptr, &pass);
+    out.resize(4 * n);
+    return n;
+}

@@ -60,6 +60,7 @@ def lib():
         _lib.orc_mo_extract_nearby.restype = C.c_size_t
         _lib.orc_mo_map_size.restype = C.c_size_t
         _lib.orc_mo_loop_find_near_keyframes.restype = C.c_size_t
+        _lib.orc_mo_build_global_map.restype = C.c_size_t
         _lib.orc_project_cloud.restype = C.c_size_t
         _lib.orc_depth_create.restype = C.c_void_p
         _lib.orc_depth_add_cloud.restype = C.c_size_t
@@ -498,6 +499,14 @@ class MapOptimization:
         out = np.zeros((n, 4), np.float32)
         if n:
             lib().orc_mo_get_loop_cloud(self.h, C.c_int(slot), _p(out))
+        return out
+
+    def build_global_map(self, ids, which=3, leaf=1.0):
+        ids = np.ascontiguousarray(ids, np.int32)
+        n = lib().orc_mo_build_global_map(self.h, _p(ids), C.c_size_t(len(ids)), C.c_int(which), C.c_float(leaf))
+        out = np.zeros((n, 4), np.float32)
+        if n:
+            lib().orc_mo_get_loop_cloud(self.h, C.c_int(0), _p(out))
         return out
 
     def detect_loop_closure_distance(self, time_cur, radius=15.0, time_diff=30.0):

@@ -201,6 +201,14 @@ def test_loop_find_near_keyframes_bit_exact(loop_sequence):
         assert np.array_equal(got, ref)
 
 
+def test_global_map_bit_exact(loop_sequence):
+    hd, mo, _ = loop_sequence
+    for ids, which, leaf in (([0, 5, 3, 25, 12], 3, 1.0), (list(range(26)), 3, 0.4), ([7, 7, 2], 1, 0.2), ([9], 2, 0.4)):
+        got = hd.build_global_map(ids, which, leaf)
+        ref = mo.build_global_map(ids, which, leaf)
+        assert len(got) > 0 and np.array_equal(got, ref)
+
+
 def test_perform_loop_closure_matches_oracle(lv, loop_sequence):
     hd, mo, truth = loop_sequence
     pair = mo.detect_loop_closure_distance(time_cur=50.0)
