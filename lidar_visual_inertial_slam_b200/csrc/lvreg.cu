@@ -104,6 +104,7 @@ struct lvreg_handle {
     int force_tpq = -1;           // -1 auto, 0 grouped, 1 thread-per-query (LVREG_TPQ)
     bool reg_occ_is_tpq = false;
     std::vector<Keyframe*> kfs;
+    std::vector<Keyframe*> kf_free;   // keyframes of a cleared session: their device buffers are reused
     MapSide map[2];
     DevBuf scan_ds[2];
     uint32_t n_scan[2] = {0, 0};
@@ -881,6 +882,11 @@ void lvreg_destroy(lvreg_handle* h) {
         kf->cloud[1].release();
         delete kf;
     }
+    for (Keyframe* kf : h->kf_free) {
+        kf->cloud[0].release();
+        kf->cloud[1].release();
+        delete kf;
+    }
     for (int l = 0; l < kLanes; ++l) {
         Lane& L = h->lane[l];
         if (L.st) cudaStreamSynchronize(L.st);
@@ -923,12 +929,22 @@ void lvreg_destroy(lvreg_handle* h) {
 }
 
 // ---- keyframes -----------------------------------------------------------------------------------
+namespace {
+Keyframe* take_keyframe(lvreg_handle* h) {
+    if (h->kf_free.empty()) return new Keyframe();
+    Keyframe* kf = h->kf_free.back();
+    h->kf_free.pop_back();
+    kf->n[0] = kf->n[1] = 0;
+    return kf;
+}
+}  // namespace
+
 int lvreg_add_keyframe(lvreg_handle* h, const lvreg_cloud* corner, const lvreg_cloud* surf,
                        const float pose[6], int32_t* id_out) {
     if (!h || !pose) return LVREG_ERR_INVALID;
     CK(cudaSetDevice(h->device));
     begin_call(h);
-    Keyframe* kf = new Keyframe();
+    Keyframe* kf = take_keyframe(h);
     int s0 = upload_cloud(h, corner, kf->cloud[0], h->lane[LANE_SCAN_CORNER].stage, h->st);
     int s1 = s0 == LVREG_OK ? upload_cloud(h, surf, kf->cloud[1], h->lane[LANE_SCAN_SURF].stage, h->st) : s0;
     if (s1 != LVREG_OK || cudaStreamSynchronize(h->st) != cudaSuccess) {
@@ -949,7 +965,7 @@ int lvreg_add_keyframe(lvreg_handle* h, const lvreg_cloud* corner, const lvreg_c
 int lvreg_add_keyframe_from_scan(lvreg_handle* h, const float pose[6], int32_t* id_out) {
     if (!h || !pose) return LVREG_ERR_INVALID;
     CK(cudaSetDevice(h->device));
-    Keyframe* kf = new Keyframe();
+    Keyframe* kf = take_keyframe(h);
     for (int s = 0; s < 2; ++s) {
         const uint32_t n = h->n_scan[s];
         cudaError_t e = kf->cloud[s].reserve((size_t)(n ? n : 1) * 16);
@@ -991,10 +1007,14 @@ int lvreg_clear_keyframes(lvreg_handle* h) {
     if (!h) return LVREG_ERR_INVALID;
     CK(cudaSetDevice(h->device));
     CK(cudaStreamSynchronize(h->st));
+    // keep the buffers for the next session (bounded: a long session is not pinned in memory for ever)
     for (Keyframe* kf : h->kfs) {
-        kf->cloud[0].release();
-        kf->cloud[1].release();
-        delete kf;
+        if (h->kf_free.size() < 4096) h->kf_free.push_back(kf);
+        else {
+            kf->cloud[0].release();
+            kf->cloud[1].release();
+            delete kf;
+        }
     }
     h->kfs.clear();
     h->map[0].valid = h->map[1].valid = false;

@@ -2,6 +2,7 @@
 #include "harness.hpp"
 
 #include <chrono>
+#include <memory>
 #include <cmath>
 #include <cstring>
 
@@ -25,7 +26,7 @@ void guess_pose(const SequenceSpec& s, int k, const float truth[6], float guess[
     for (int i = 3; i < 6; ++i) guess[i] = truth[i] + (float)rng.uniform(-s.guess_trans, s.guess_trans);
 }
 
-ReplayStats replay_sequence(const SequenceSpec& s, int device, int gen_threads) {
+ReplayStats replay_sequence(const SequenceSpec& s, int device, int gen_threads, mapOptimization* reuse) {
     ReplayStats st;
     const SensorSpec sensor = s.sensor == 1 ? sensor_128beam() : sensor_mid360();
     const World world = make_world(s.seed, s.sensor == 1 ? world_urban() : world_indoor());
@@ -38,7 +39,10 @@ ReplayStats replay_sequence(const SequenceSpec& s, int device, int gen_threads) 
         corners[k] = cloud_from_xyzi(c.data(), c.size() / 4);
         surfs[k] = cloud_from_xyzi(f.data(), f.size() / 4);
     }
-    mapOptimization mo(ParamServer(), device);
+    std::unique_ptr<mapOptimization> own;
+    if (!reuse) own.reset(new mapOptimization(ParamServer(), device));
+    mapOptimization& mo = reuse ? *reuse : *own;
+    if (reuse) mo.reset();
     const auto t0 = std::chrono::steady_clock::now();
     for (int k = 0; k < s.n_scans; ++k) {
         float guess[6];

@@ -37,6 +37,8 @@ struct ReplayStats {
 // Replays one synthetic sequence through the mirror: scan 0 bootstraps the first keyframe at the
 // truth pose, scans 1.. are registered against the local map.  Scans are generated up front
 // (outside the timed region).
-ReplayStats replay_sequence(const SequenceSpec& s, int device, int gen_threads);
+// `reuse`: an existing mirror object (one per GPU / robot slot) to replay on after reset(), so that a batch of
+// sequences does not pay the first-use device allocations once per sequence; nullptr creates a fresh one
+ReplayStats replay_sequence(const SequenceSpec& s, int device, int gen_threads, class mapOptimization* reuse = nullptr);
 
 }  // namespace lvreg_host

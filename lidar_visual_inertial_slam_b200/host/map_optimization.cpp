@@ -57,6 +57,23 @@ mapOptimization::mapOptimization(const ParamServer& params, int device) : P_(par
 
 mapOptimization::~mapOptimization() { lvreg_destroy(h_); }
 
+void mapOptimization::reset() {
+    cornerCloudKeyFrames.clear();
+    surfCloudKeyFrames.clear();
+    cloudKeyPoses3D.clear();
+    cloudKeyPoses6D.clear();
+    loopIndexContainer.clear();
+    loopQueue.clear();
+    lastIds_.clear();
+    mapDirty_ = true;
+    timeLastProcessing_ = -1;
+    scanDownsampled_ = false;
+    isDegenerate = false;
+    std::memset(transformTobeMapped, 0, sizeof(transformTobeMapped));
+    lvreg_clear_keyframes(h_);
+    lvreg_reset_lm_state(h_);
+}
+
 // pointDistance (utility.h:409-412)
 static inline float pointDistance(const PointType& a, const PointType& b) {
     return std::sqrt((a.x - b.x) * (a.x - b.x) + (a.y - b.y) * (a.y - b.y) + (a.z - b.z) * (a.z - b.z));
@@ -396,9 +413,40 @@ bool mapOptimization::laserCloudInfoHandler(const Cloud& corner, const Cloud& su
     std::memset(&lastTimings, 0, sizeof(lastTimings));
     scanDownsampled_ = false;
     if (guess) std::memcpy(transformTobeMapped, guess, sizeof(transformTobeMapped));   // updateInitialGuess
-    extractSurroundingKeyFrames();
-    downsampleCurrentScan();
-    scan2MapOptimization();
+    if (!fusedHandler || cloudKeyPoses3D.empty()) {
+        extractSurroundingKeyFrames();
+        downsampleCurrentScan();
+        scan2MapOptimization();
+        saveKeyFramesAndFactor();
+        return true;
+    }
+    // MO:318-322 as ONE library call: the local-map rebuild (when the selection changed) and the scan
+    // down-sampling run concurrently on the device and share their host synchronisations
+    std::vector<int32_t> ids = extractNearby();
+    const bool rebuild = mapDirty_ || ids != lastIds_;
+    lvreg_cloud c = as_lvreg_cloud(laserCloudCornerLast), s = as_lvreg_cloud(laserCloudSurfLast);
+    lastStatus = lvreg_register_scan(h_, &c, &s, rebuild ? ids.data() : nullptr, ids.size(), transformTobeMapped, &lastResult);
+    if (lastStatus != LVREG_OK && lastStatus != LVREG_ERR_NOT_ENOUGH_FEATURES)
+        throw std::runtime_error(std::string("lvreg_register_scan: ") + lvreg_last_error(h_));
+    if (rebuild) {
+        lastIds_ = ids;
+        mapDirty_ = false;
+    }
+    laserCloudCornerLastDSNum = lastResult.n_corner_ds;
+    laserCloudSurfLastDSNum = lastResult.n_surf_ds;
+    laserCloudCornerFromMapDSNum = lastResult.n_corner_map;
+    laserCloudSurfFromMapDSNum = lastResult.n_surf_map;
+    scanDownsampled_ = true;
+    lvreg_timings t;
+    lvreg_get_timings(h_, &t);
+    lastTimings = t;
+    if (lastStatus == LVREG_ERR_NOT_ENOUGH_FEATURES) {
+        std::fprintf(stderr, "Not enough features! Only %d edge and %d planar features available.\n",
+                     laserCloudCornerLastDSNum, laserCloudSurfLastDSNum);          // MO:1341
+    } else {
+        isDegenerate = lastResult.degenerate != 0;
+        if (imuAvailable) lvreg_transform_update(h_, transformTobeMapped, 1, imuRollInit, imuPitchInit);
+    }
     saveKeyFramesAndFactor();
     return true;
 }

