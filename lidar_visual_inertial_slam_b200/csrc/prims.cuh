@@ -207,6 +207,7 @@ __global__ void __launch_bounds__(kSortThreads, 4) rs_onesweep_kernel(
     uint32_t* ticket) {
     __shared__ uint2 skv[kSortTile];         // (key, payload) staged together: one 64-bit access each way
     __shared__ uint32_t wcnt[kSortWarps][256];
+    __shared__ uint32_t thist[256];         // the tile's digit counts, known before the ranking
     __shared__ uint32_t gofs[256];          // global offset of a digit run minus its tile-local start
     __shared__ uint32_t scan_ws[2][8];
     __shared__ uint32_t tile_s;
@@ -216,11 +217,11 @@ __global__ void __launch_bounds__(kSortThreads, 4) rs_onesweep_kernel(
 #endif
     if (threadIdx.x == 0) tile_s = atomicAdd(ticket, 1u);
     for (int i = threadIdx.x; i < kSortWarps * 256; i += kSortThreads) (&wcnt[0][0])[i] = 0;
+    thist[threadIdx.x] = 0;
     __syncthreads();
     const uint32_t tile = tile_s;
     SORT_STAMP(0);
 
-    // ---- rank the tile's elements (stable) ----
     const uint32_t base = tile * kSortTile + warp * (32 * kSortItems);
     uint32_t k[kSortItems];
     uint16_t rank[kSortItems];
@@ -233,43 +234,17 @@ __global__ void __launch_bounds__(kSortThreads, 4) rs_onesweep_kernel(
     if (k[0] == 0x12345678u && k[kSortItems - 1] == 0x9abcdef0u) t_prev_ += 1;   // wait for the loads
     SORT_STAMP(1);
 #endif
-#pragma unroll
-    for (int r = 0; r < kSortItems; ++r) {
-        // lanes with the same digit, from 8 ballots: the hardware match.any iterates over the
-        // distinct values in the warp (~30 here) and measured ~2x slower under load
-        const uint32_t d = (k[r] >> shift) & 255u;
-        uint32_t peers = 0xffffffffu;
-#pragma unroll
-        for (int b = 0; b < 8; ++b) {
-            const bool bit = (d >> b) & 1u;
-            const uint32_t bal = __ballot_sync(0xffffffffu, bit);
-            peers &= bit ? bal : ~bal;
-        }
-        // the counters are private to the warp and each digit has one leader: a plain
-        // read-modify-write is enough (a shared-memory atomic with a result is slower)
-        const int leader = __ffs(peers) - 1;
-        uint32_t old = 0;
-        if (lane == leader) {
-            old = wcnt[warp][d];
-            wcnt[warp][d] = old + (uint32_t)__popc(peers);
-        }
-        __syncwarp();
-        old = __shfl_sync(0xffffffffu, old, leader);
-        rank[r] = (uint16_t)(old + __popc(peers & ((1u << lane) - 1u)));
-    }
-    SORT_STAMP(2);
-    __syncthreads();
-    SORT_STAMP(3);
 
-    // ---- per digit: tile count, exclusive prefix over warps, publish, look back ----
-    const int d = threadIdx.x;               // one thread per digit
-    uint32_t cnt = 0;
+    // ---- the tile's digit counts first: they are all the other tiles wait for.  Publishing them (and
+    // resolving this tile's own offsets) BEFORE the ranking takes the ranking out of the chain of
+    // dependent tiles: a predecessor's count is ~5k cycles away from its start instead of ~15k, and the
+    // look-back below rarely meets a tile that has not published yet. ----
 #pragma unroll
-    for (int w = 0; w < kSortWarps; ++w) {
-        const uint32_t c = wcnt[w][d];
-        wcnt[w][d] = cnt;
-        cnt += c;
-    }
+    for (int r = 0; r < kSortItems; ++r) atomicAdd(&thist[(k[r] >> shift) & 255u], 1u);
+    __syncthreads();
+    SORT_STAMP(2);
+    const int d = threadIdx.x;               // one thread per digit
+    const uint32_t cnt = thist[d];
     // the padding of the last tile was counted under digit 255: remove it from the published count
     uint32_t pad = 0;
     if (d == 255) {
@@ -278,6 +253,83 @@ __global__ void __launch_bounds__(kSortThreads, 4) rs_onesweep_kernel(
     }
     const uint32_t real_cnt = cnt - pad;
     status[(size_t)tile * 256 + d] = (tile == 0 ? kFlagIncl : kFlagAgg) | real_cnt;
+    uint32_t excl = 0;
+    if (tile > 0) {
+        // decoupled look-back, 16 predecessors per round trip (independent loads in flight).  Measured at
+        // 11.4 M pairs: 2.6 round trips per tile, a third of them meet a predecessor that has not published
+        // yet; wider batches (32, 48) were slower -- the cost of a round trip grows with the loads issued.
+        constexpr int LB = 16;
+        int pred = (int)tile - 1;
+        bool done = false;
+        while (!done) {
+            uint32_t s[LB];
+#pragma unroll
+            for (int j = 0; j < LB; ++j) {
+                const int idx = pred - j;
+                s[j] = 0x80000000u;                                            // before tile 0: inclusive prefix 0
+                if (idx >= 0) s[j] = status[(size_t)idx * 256 + d];
+            }
+            // common case, branch-free: everything up to the first inclusive prefix is published
+            uint32_t incl_mask = 0, miss_mask = 0;
+#pragma unroll
+            for (int j = 0; j < LB; ++j) {
+                incl_mask |= ((s[j] >> 31) & 1u) << j;
+                miss_mask |= ((s[j] & kFlagMask) == 0 ? 1u : 0u) << j;
+            }
+            const int first = incl_mask ? __ffs(incl_mask) - 1 : LB;          // LB: no inclusive prefix in this batch
+            const uint32_t upto = first < LB ? ((2u << first) - 1u) : ((LB == 32) ? 0xffffffffu : ((1u << LB) - 1u));
+#ifdef LVREG_SORT_PROF
+            if (threadIdx.x == 0) { atomicAdd(&g_sort_prof[10], 1ull); if (miss_mask & upto) atomicAdd(&g_sort_prof[11], 1ull); }
+            if (threadIdx.x == 0 && first < LB) atomicAdd(&g_sort_prof[12], (unsigned long long)first);
+#endif
+            if ((miss_mask & upto) == 0) {
+#pragma unroll
+                for (int j = 0; j < LB; ++j)
+                    if ((upto >> j) & 1u) excl += s[j] & ~kFlagMask;
+                done = first < LB;
+            } else {
+#pragma unroll
+                for (int j = 0; j < LB; ++j) {
+                    if (!done) {
+                        uint32_t sv = s[j];
+                        while ((sv & kFlagMask) == 0) sv = status[(size_t)(pred - j) * 256 + d];
+                        excl += sv & ~kFlagMask;
+                        if (sv & kFlagIncl) done = true;
+                    }
+                }
+            }
+            pred -= LB;
+        }
+        status[(size_t)tile * 256 + d] = kFlagIncl | (excl + real_cnt);
+    }
+    SORT_STAMP(3);
+
+    // ---- rank the tile's elements (stable) ----
+#pragma unroll
+    for (int r = 0; r < kSortItems; ++r) {
+        // lanes with the same digit, from 8 ballots: the hardware match.any iterates over the
+        // distinct values in the warp (~30 here) and measured ~2x slower under load
+        const uint32_t dg = (k[r] >> shift) & 255u;
+        uint32_t peers = 0xffffffffu;
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            const bool bit = (dg >> b) & 1u;
+            const uint32_t bal = __ballot_sync(0xffffffffu, bit);
+            peers &= bit ? bal : ~bal;
+        }
+        // the counters are private to the warp and each digit has one leader: a plain
+        // read-modify-write is enough (a shared-memory atomic with a result is slower)
+        const int leader = __ffs(peers) - 1;
+        uint32_t old = 0;
+        if (lane == leader) {
+            old = wcnt[warp][dg];
+            wcnt[warp][dg] = old + (uint32_t)__popc(peers);
+        }
+        __syncwarp();
+        old = __shfl_sync(0xffffffffu, old, leader);
+        rank[r] = (uint16_t)(old + __popc(peers & ((1u << lane) - 1u)));
+    }
+    SORT_STAMP(4);
 
     // the payloads are not needed before the staging: load them now, off the ranking's registers
     uint32_t v[kSortItems];
@@ -294,47 +346,25 @@ __global__ void __launch_bounds__(kSortThreads, 4) rs_onesweep_kernel(
         const uint32_t a = warp_inclusive_scan(gh, lane);
         const uint32_t b = warp_inclusive_scan(cnt, lane);
         if (lane == 31) { scan_ws[0][warp] = a; scan_ws[1][warp] = b; }
-        __syncthreads();
+        __syncthreads();                      // also: every warp's counters are final
         uint32_t wa = 0, wb = 0;
         for (int w = 0; w < warp; ++w) { wa += scan_ws[0][w]; wb += scan_ws[1][w]; }
         gb = a - gh + wa;
         tl = b - cnt + wb;
     }
-    SORT_STAMP(4);
-    uint32_t excl = 0;
-    if (tile > 0) {
-        // decoupled look-back, 16 predecessors per round trip (independent loads in flight).
-        // Measured: ~4 round trips + ~9 polls of a predecessor that has not ranked yet per tile.
-        constexpr int LB = 16;
-        int pred = (int)tile - 1;
-        bool done = false;
-        while (!done) {
-            uint32_t s[LB];
-#pragma unroll
-            for (int j = 0; j < LB; ++j) {
-                const int idx = pred - j;
-                s[j] = 0x80000000u;                                            // before tile 0: inclusive prefix 0
-                if (idx >= 0) s[j] = status[(size_t)idx * 256 + d];
-            }
-#pragma unroll
-            for (int j = 0; j < LB; ++j) {
-                if (!done) {
-                    uint32_t sv = s[j];
-                    while ((sv & kFlagMask) == 0) sv = status[(size_t)(pred - j) * 256 + d];
-                    excl += sv & ~kFlagMask;
-                    if (sv & kFlagIncl) done = true;
-                }
-            }
-            pred -= LB;
-        }
-        status[(size_t)tile * 256 + d] = kFlagIncl | (excl + real_cnt);
-    }
-    SORT_STAMP(5);
     gofs[d] = gb + excl - tl;
-    // tile-local start of each (warp, digit) run
+    // tile-local start of each (warp, digit) run: exclusive prefix over the warps + the digit's start
+    {
+        uint32_t run = tl;
 #pragma unroll
-    for (int w = 0; w < kSortWarps; ++w) wcnt[w][d] += tl;
+        for (int w = 0; w < kSortWarps; ++w) {
+            const uint32_t c = wcnt[w][d];
+            wcnt[w][d] = run;
+            run += c;
+        }
+    }
     __syncthreads();
+    SORT_STAMP(5);
 
     // ---- stage in shared memory in tile-sorted order, then write coalesced runs ----
 #pragma unroll

@@ -6,8 +6,8 @@ import lidar_visual_inertial_slam_b200 as lv
 from lidar_visual_inertial_slam_b200 import binding
 h = lv.Lvreg()
 lib = ctypes.CDLL('/root/repo/lidar_visual_inertial_slam_b200/liblvreg.so')
-names = ["ticket+zero+sync", "key loads", "ballot match + counter chain x16", "sync after rank",
-         "prefix+publish+val loads+scans", "look-back", "offsets + stage to smem + syncs", "write-out"]
+names = ["ticket+zero+sync", "key loads", "tile histogram + sync", "publish + look-back", "ballot match + counter chain x16",
+         "val loads + scans + offsets + syncs", "stage to smem + sync", "write-out"]
 for n, bits in ((11375817, 28), (1660000, 31), (62000, 24)):
     h.bench_sort(n, bits, 2)
     out = (ctypes.c_ulonglong * 16)()
@@ -18,5 +18,7 @@ for n, bits in ((11375817, 28), (1660000, 31), (62000, 24)):
     tiles = ((n + 4095) // 4096) * p * (reps + 2)
     tot = sum(out[:8])
     print("n=%d passes=%d us/pass=%.1f  tiles=%d  cycles/tile=%.0f" % (n, p, ms * 1e3 / p, tiles, tot / tiles))
+    print("   look-back: %.2f batches/tile, %.2f of them met an unpublished tile, inclusive prefix found %.1f entries into its batch"
+          % (out[10] / tiles, out[11] / max(1, out[10]), out[12] / tiles))
     for k in range(8):
         print("   %-32s %8.0f cyc  %5.1f%%" % (names[k], out[k] / tiles, 100.0 * out[k] / tot))
