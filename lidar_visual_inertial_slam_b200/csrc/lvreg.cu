@@ -853,7 +853,10 @@ int lvreg_create(const lvreg_params* p, int device, void* cuda_stream, lvreg_han
         return bail(LVREG_ERR_CUDA);
     cudaMemsetAsync(h->lmstate.p, 0, sizeof(LmState), h->st);
     // the sort pass keeps 42 KB of staging per block: ask for the large shared-memory carveout
-    cudaFuncSetAttribute(rs_onesweep_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(rs_onesweep_kernel<kSortThreads>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(rs_onesweep_kernel<kSortThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem_bytes(kSortThreads));
+    cudaFuncSetAttribute(rs_onesweep_kernel<kSortThreadsBig>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(rs_onesweep_kernel<kSortThreadsBig>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem_bytes(kSortThreadsBig));
     const char* e = getenv("LVREG_LPQ");
     if (e) {
         int v = atoi(e);

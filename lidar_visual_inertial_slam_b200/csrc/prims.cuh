@@ -164,11 +164,12 @@ inline void exclusive_scan(In in, Out out, uint32_t n, uint32_t* temp, uint32_t*
 // already running; within a tile the element order is (warp, round, lane) == index order, which
 // makes the sort stable.
 // ------------------------------------------------------------------------------------------
-constexpr int kSortThreads = 256;
+constexpr int kSortThreads = 256;           // tile of 4096 pairs: inputs up to kSortBigN (shorter tiles, lower latency)
+constexpr int kSortThreadsBig = 512;        // tile of 8192 pairs: large inputs (half as many tiles in the look-back chain)
+constexpr uint32_t kSortBigN = 600000;
 constexpr int kSortItems = 16;
-constexpr int kSortTile = kSortThreads * kSortItems;   // 4096 pairs per tile
-constexpr int kSortWarps = kSortThreads / 32;
 constexpr int kSortMaxPasses = 4;
+constexpr size_t sort_smem_bytes(int threads) { return (size_t)threads * kSortItems * 8 + (size_t)(threads / 32 + 2) * 256 * 4 + 128; }
 constexpr uint32_t kFlagAgg = 1u << 30, kFlagIncl = 2u << 30, kFlagMask = 3u << 30;
 
 __global__ void __launch_bounds__(256) rs_global_hist_kernel(const uint32_t* __restrict__ keys, uint32_t n,
@@ -200,29 +201,33 @@ __device__ unsigned long long g_sort_prof[16];
 #define SORT_STAMP(k) do {} while (0)
 #endif
 
-__global__ void __launch_bounds__(kSortThreads, 4) rs_onesweep_kernel(
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, 1024 / THREADS) rs_onesweep_kernel(
     const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
     uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, uint32_t n, int shift,
     const uint32_t* __restrict__ ghist /*256, this pass*/, volatile uint32_t* status /*[tiles][256]*/,
     uint32_t* ticket) {
-    __shared__ uint2 skv[kSortTile];         // (key, payload) staged together: one 64-bit access each way
-    __shared__ uint32_t wcnt[kSortWarps][256];
-    __shared__ uint32_t thist[256];         // the tile's digit counts, known before the ranking
-    __shared__ uint32_t gofs[256];          // global offset of a digit run minus its tile-local start
-    __shared__ uint32_t scan_ws[2][8];
-    __shared__ uint32_t tile_s;
+    // dynamic shared memory (more than 48 KB with 512 threads): staging | per-warp counters | small arrays
+    constexpr int TILE = THREADS * kSortItems, WARPS = THREADS / 32;
+    extern __shared__ __align__(16) unsigned char sort_smem[];
+    uint2* skv = reinterpret_cast<uint2*>(sort_smem);            // [TILE] (key, payload): one 64-bit access each way
+    uint32_t (*wcnt)[256] = reinterpret_cast<uint32_t (*)[256]>(sort_smem + (size_t)TILE * 8);   // [WARPS][256]
+    uint32_t* thist = &wcnt[WARPS][0];  // [256] the tile's digit counts, known before the ranking
+    uint32_t* gofs = thist + 256;            // [256] global offset of a digit run minus its tile-local start
+    uint32_t (*scan_ws)[8] = reinterpret_cast<uint32_t (*)[8]>(gofs + 256);   // [2][8]
+    uint32_t& tile_s = *(gofs + 256 + 16);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #ifdef LVREG_SORT_PROF
     long long t_prev_ = clock64();
 #endif
     if (threadIdx.x == 0) tile_s = atomicAdd(ticket, 1u);
-    for (int i = threadIdx.x; i < kSortWarps * 256; i += kSortThreads) (&wcnt[0][0])[i] = 0;
-    thist[threadIdx.x] = 0;
+    for (int i = threadIdx.x; i < WARPS * 256; i += THREADS) (&wcnt[0][0])[i] = 0;
+    if (threadIdx.x < 256) thist[threadIdx.x] = 0;
     __syncthreads();
     const uint32_t tile = tile_s;
     SORT_STAMP(0);
 
-    const uint32_t base = tile * kSortTile + warp * (32 * kSortItems);
+    const uint32_t base = tile * TILE + warp * (32 * kSortItems);
     uint32_t k[kSortItems];
     uint16_t rank[kSortItems];
 #pragma unroll
@@ -243,18 +248,19 @@ __global__ void __launch_bounds__(kSortThreads, 4) rs_onesweep_kernel(
     for (int r = 0; r < kSortItems; ++r) atomicAdd(&thist[(k[r] >> shift) & 255u], 1u);
     __syncthreads();
     SORT_STAMP(2);
-    const int d = threadIdx.x;               // one thread per digit
+    const int d = threadIdx.x & 255;         // the first 256 threads own one digit each
+    const bool digit_thread = threadIdx.x < 256;
     const uint32_t cnt = thist[d];
     // the padding of the last tile was counted under digit 255: remove it from the published count
     uint32_t pad = 0;
     if (d == 255) {
-        const uint32_t tile_end = (tile + 1) * kSortTile;
+        const uint32_t tile_end = (tile + 1) * TILE;
         pad = tile_end > n ? tile_end - n : 0;
     }
     const uint32_t real_cnt = cnt - pad;
-    status[(size_t)tile * 256 + d] = (tile == 0 ? kFlagIncl : kFlagAgg) | real_cnt;
+    if (digit_thread) status[(size_t)tile * 256 + d] = (tile == 0 ? kFlagIncl : kFlagAgg) | real_cnt;
     uint32_t excl = 0;
-    if (tile > 0) {
+    if (digit_thread && tile > 0) {
         // decoupled look-back, 16 predecessors per round trip (independent loads in flight).  Measured at
         // 11.4 M pairs: 2.6 round trips per tile, a third of them meet a predecessor that has not published
         // yet; wider batches (32, 48) were slower -- the cost of a round trip grows with the loads issued.
@@ -345,19 +351,19 @@ __global__ void __launch_bounds__(kSortThreads, 4) rs_onesweep_kernel(
         const uint32_t gh = ghist[d];
         const uint32_t a = warp_inclusive_scan(gh, lane);
         const uint32_t b = warp_inclusive_scan(cnt, lane);
-        if (lane == 31) { scan_ws[0][warp] = a; scan_ws[1][warp] = b; }
+        if (lane == 31 && digit_thread) { scan_ws[0][warp] = a; scan_ws[1][warp] = b; }
         __syncthreads();                      // also: every warp's counters are final
         uint32_t wa = 0, wb = 0;
-        for (int w = 0; w < warp; ++w) { wa += scan_ws[0][w]; wb += scan_ws[1][w]; }
+        for (int w = 0; w < (warp & 7); ++w) { wa += scan_ws[0][w]; wb += scan_ws[1][w]; }
         gb = a - gh + wa;
         tl = b - cnt + wb;
     }
-    gofs[d] = gb + excl - tl;
     // tile-local start of each (warp, digit) run: exclusive prefix over the warps + the digit's start
-    {
+    if (digit_thread) {
+        gofs[d] = gb + excl - tl;
         uint32_t run = tl;
 #pragma unroll
-        for (int w = 0; w < kSortWarps; ++w) {
+        for (int w = 0; w < WARPS; ++w) {
             const uint32_t c = wcnt[w][d];
             wcnt[w][d] = run;
             run += c;
@@ -375,10 +381,10 @@ __global__ void __launch_bounds__(kSortThreads, 4) rs_onesweep_kernel(
     }
     __syncthreads();
     SORT_STAMP(6);
-    const uint32_t tile_n = min((uint32_t)kSortTile, n - tile * kSortTile);
+    const uint32_t tile_n = min((uint32_t)TILE, n - tile * TILE);
 #pragma unroll
     for (int r = 0; r < kSortItems; ++r) {
-        const uint32_t e = r * kSortThreads + threadIdx.x;
+        const uint32_t e = r * THREADS + threadIdx.x;
         if (e < tile_n) {
             const uint2 kv = skv[e];
             const uint32_t dst = gofs[(kv.x >> shift) & 255u] + e;
@@ -389,10 +395,18 @@ __global__ void __launch_bounds__(kSortThreads, 4) rs_onesweep_kernel(
     SORT_STAMP(7);
 }
 
-inline uint32_t sort_num_blocks(uint32_t n) { return (n + kSortTile - 1) / kSortTile; }
+inline int sort_threads_for(uint32_t n) { return n > kSortBigN ? kSortThreadsBig : kSortThreads; }
+inline uint32_t sort_num_blocks(uint32_t n) {
+    const uint32_t tile = (uint32_t)sort_threads_for(n) * kSortItems;
+    return (n + tile - 1) / tile;
+}
 // scratch needed by radix_sort_pairs, in uint32 words: look-back status per pass + histograms + tickets
+// (sized for any input of up to n pairs: just below kSortBigN the tiles are shorter, hence more of them)
 inline size_t sort_scratch_words(uint32_t n) {
-    return (size_t)kSortMaxPasses * 256 * sort_num_blocks(n) + kSortMaxPasses * 256 + 8;
+    uint32_t nb = sort_num_blocks(n);
+    const uint32_t small = n < kSortBigN ? n : kSortBigN;
+    if (sort_num_blocks(small) > nb) nb = sort_num_blocks(small);
+    return (size_t)kSortMaxPasses * 256 * nb + kSortMaxPasses * 256 + 8;
 }
 
 inline int sort_num_passes(int key_bits) {
@@ -460,8 +474,12 @@ inline int radix_sort_run(uint32_t* keys0, uint32_t* vals0, uint32_t* keys1, uin
         const uint32_t* vin = cur ? vals1 : vals0;
         uint32_t* kout = cur ? keys0 : keys1;
         uint32_t* vout = cur ? vals0 : vals1;
-        rs_onesweep_kernel<<<nblocks, kSortThreads, 0, st>>>(kin, vin, kout, vout, n, 8 * p, ghist + 256 * p,
-                                                             status + (size_t)p * 256 * nblocks, tickets + p);
+        if (sort_threads_for(n) == kSortThreadsBig)
+            rs_onesweep_kernel<kSortThreadsBig><<<nblocks, kSortThreadsBig, sort_smem_bytes(kSortThreadsBig), st>>>(
+                kin, vin, kout, vout, n, 8 * p, ghist + 256 * p, status + (size_t)p * 256 * nblocks, tickets + p);
+        else
+            rs_onesweep_kernel<kSortThreads><<<nblocks, kSortThreads, sort_smem_bytes(kSortThreads), st>>>(
+                kin, vin, kout, vout, n, 8 * p, ghist + 256 * p, status + (size_t)p * 256 * nblocks, tickets + p);
         cur ^= 1;
     }
     if (launches) *launches += passes;
