@@ -208,7 +208,7 @@ def main():
         ids, times, poses, results = cpu_arm(ds, args.steps, args.warmup, threads, log)
         ms = 1e3 * float(np.sum(times)) / max(1, len(times))
         val = 1e3 / ms
-        line = dict(metric="scan-to-map registrations/sec", value=val, unit="registrations/s", n_gpus=0,
+        line = dict(metric="scan-to-map registrations/sec", value=val, unit="registrations/s", n_gpus=int(args.gpus),
                     steps=args.steps, warmup=args.warmup, ms_per_step=ms, higher_is_better=True, scaling="weak",
                     vs_baseline=None, dtype="f32", data="synthetic", impl="reference",
                     config=dict(workload=wl_name, keyframes=len(ds["kf_pose"]), l2="inputs larger than L2"),
