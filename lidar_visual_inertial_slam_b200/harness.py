@@ -98,6 +98,34 @@ class MapOptimizationMirror:
             raise RuntimeError(self.L.lvh_last_error().decode())
         return st, pose, res, tim, nk.value
 
+    def raw_scan_to_pose(self, raw, n_scan, horizon, sensor, guess, ids=None, min_range=0.5, max_range=1000.0,
+                         deskew=False, time_scan_cur=0.0, imu_time=None, imu_rot=None, edge_threshold=1.0):
+        """ImageProjection + FeatureExtraction + registration mirrors on one handle: raw Livox-layout points
+        (uint8 [n,32]) in, pose out -> (status, pose, Result, (n_extracted, n_corner, n_surf))"""
+        raw = np.ascontiguousarray(raw, np.uint8)
+        pose = np.ascontiguousarray(guess, np.float32).copy()
+        res = Result()
+        n_out = (C.c_size_t * 3)()
+        if deskew:
+            t = np.ascontiguousarray(imu_time, np.float64)
+            r = np.ascontiguousarray(imu_rot, np.float64).reshape(-1, 3)
+            tp, rp, k = t.ctypes.data_as(C.c_void_p), r.ctypes.data_as(C.c_void_p), len(t)
+        else:
+            tp, rp, k = None, None, 0
+        if ids is None:
+            idp, nid = None, 0
+        else:
+            ids = np.ascontiguousarray(ids, np.int32)
+            idp, nid = ids.ctypes.data_as(C.c_void_p), len(ids)
+        st = self.L.lvh_mo_raw_scan_to_pose(self.mo, raw.ctypes.data_as(C.c_void_p), C.c_size_t(len(raw)), int(n_scan),
+                                            int(horizon), int(sensor), C.c_float(min_range), C.c_float(max_range),
+                                            int(bool(deskew)), C.c_double(time_scan_cur), tp, rp, int(k),
+                                            C.c_float(edge_threshold), idp, C.c_size_t(nid),
+                                            pose.ctypes.data_as(C.c_void_p), C.byref(res), n_out)
+        if st == -2:
+            raise RuntimeError(self.L.lvh_last_error().decode())
+        return st, pose, res, tuple(int(v) for v in n_out)
+
     def perform_loop_closure(self):
         """mapOptimization::performLoopClosure -> (queued, key_cur, key_pre, LoopResult)"""
         from .binding import LoopResult

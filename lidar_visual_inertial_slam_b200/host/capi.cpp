@@ -2,8 +2,10 @@
 // tests): the synthetic generator and the mapOptimization mirror.  Packed {x,y,z,intensity} rows.
 #include <cstring>
 #include <exception>
+#include <stdexcept>
 #include <string>
 
+#include "front_end.hpp"
 #include "harness.hpp"
 
 using namespace lvreg_host;
@@ -105,6 +107,49 @@ int lvh_mo_perform_loop_closure(void* p, int* cur, int* pre, lvreg_loop_result* 
         const bool queued = mo->performLoopClosure();
         if (out) *out = mo->lastLoop;
         return queued ? 1 : 0;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return -2;
+    }
+}
+
+// Front-end mirrors (ImageProjection + FeatureExtraction) on the handle of a mapOptimization mirror:
+// raw Livox-layout points (n x 32 bytes) in, registered pose out, nothing but the raw scan uploaded.
+// Returns the lvreg status of the registration, -2 on exception.  n_out = {extracted, corner, surf}.
+int lvh_mo_raw_scan_to_pose(void* p, const void* raw_points, size_t n, int n_scan, int horizon, int sensor,
+                            float min_range, float max_range, int deskew, double time_scan_cur,
+                            const double* imu_time, const double* imu_rot_xyz /* k x 3 */, int k,
+                            float edge_threshold, const int32_t* ids, size_t n_ids, float pose[6], lvreg_result* res,
+                            size_t n_out[3]) {
+    mapOptimization* mo = (mapOptimization*)p;
+    try {
+        ImageProjection ip(mo->handle());
+        ip.N_SCAN = n_scan;
+        ip.Horizon_SCAN = horizon;
+        ip.sensor = (SensorType)sensor;
+        ip.lidarMinRange = min_range;
+        ip.lidarMaxRange = max_range;
+        ip.timeScanCur = time_scan_cur;
+        ip.cloudInfo.imu_available = deskew ? 1 : 0;
+        ip.laserCloudIn.assign((const PointXYZIRT*)raw_points, (const PointXYZIRT*)raw_points + n);
+        if (deskew) {
+            for (int i = 0; i < k && i < queueLength; ++i) {
+                ip.imuTime[i] = imu_time[i];
+                ip.imuRotX[i] = imu_rot_xyz[3 * i];
+                ip.imuRotY[i] = imu_rot_xyz[3 * i + 1];
+                ip.imuRotZ[i] = imu_rot_xyz[3 * i + 2];
+            }
+            ip.imuPointerCur = (k < queueLength ? k : queueLength) - 1;
+        }
+        ip.projectPointCloud(false);
+        FeatureExtraction fe(mo->handle());
+        fe.N_SCAN = n_scan;
+        fe.edgeThreshold = edge_threshold;
+        fe.laserCloudInfoHandlerOnDevice(false);
+        lvreg_cloud c, s;
+        if (lvreg_get_feature_clouds(mo->handle(), &c, &s) != LVREG_OK) throw std::runtime_error("no feature clouds");
+        if (n_out) { n_out[0] = ip.extractedCloudSize(); n_out[1] = fe.numCorner(); n_out[2] = fe.numSurface(); }
+        return lvreg_register_scan(mo->handle(), &c, &s, ids, n_ids, pose, res);
     } catch (const std::exception& e) {
         g_err = e.what();
         return -2;

@@ -139,3 +139,43 @@ def test_projection_golden_vectors(h, lv):
     h.project_cloud(raw, layout=lv.LAYOUT_LIVOX, **kw)
     for a, b in zip(h.download_projection(), want):
         assert np.array_equal(a, b)
+
+
+def test_front_end_mirrors_raw_scan_to_pose(lv):
+    """C++ mirrors of ImageProjection + FeatureExtraction + mapOptimization on one handle: a raw ring scan goes
+    to a registered pose with nothing but the raw points uploaded; checked against the oracle chain."""
+    from lidar_visual_inertial_slam_b200 import harness as H
+    from tests.synth import ring_scan, rot_rpy
+    rng = np.random.default_rng(13)
+    pts, rg, col, sr, er = ring_scan(rng, 16, 900)
+    ring = np.zeros(len(pts), np.uint16)
+    for r in range(16):
+        ring[sr[r] - 4:er[r] + 6] = r
+    rel = np.linspace(0, 0.1, len(pts)).astype(np.float32)
+    kw = dict(n_scan=16, horizon_scan=900, sensor=0, lidar_min_range=0.1, lidar_max_range=1000.0)
+    # oracle chain: projection -> features; the features double as the keyframe (identity pose) = the map
+    oe, org, ocol, osr, oer = O.project_cloud(pts, ring, rel, **kw)
+    oc, os_, ol = O.extract_features(oe, org, ocol, osr, oer, edge_threshold=0.5)
+    mo = H.MapOptimizationMirror()
+    st, pose0, res0, tim, nkf = mo.handle_scan(oc, os_, 0.0, np.zeros(6, np.float32))
+    assert nkf == 1
+    omo = O.MapOptimization()
+    omo.add_keyframe(O.voxelgrid(oc, 0.2)[0], O.voxelgrid(os_, 0.4)[0], np.zeros(6, np.float32), 0.0)
+    omo.build_local_map([0])
+    # the same scan seen from a slightly different pose: transform the raw points into that sensor frame
+    true = np.array([0.01, -0.008, 0.03, 0.12, -0.08, 0.02], np.float32)
+    R = rot_rpy(*true[:3])
+    moved = pts.copy()
+    moved[:, :3] = ((pts[:, :3].astype(np.float64) - true[3:].astype(np.float64)) @ R).astype(np.float32)
+    raw = lv.make_raw_cloud(moved, ring, rel, lv.LAYOUT_LIVOX)
+    guess = true + np.array([0.004, -0.003, 0.01, 0.03, -0.02, 0.01], np.float32)
+    st, pose, res, (n_ext, n_c, n_s) = mo.raw_scan_to_pose(raw, 16, 900, 0, guess, ids=[0], min_range=0.1, edge_threshold=0.5)
+    me, mrg, mcol, msr, mer = O.project_cloud(moved, ring, rel, **kw)
+    mc, ms, _ = O.extract_features(me, mrg, mcol, msr, mer, edge_threshold=0.5)
+    assert (n_ext, n_c, n_s) == (len(me), len(mc), len(ms))
+    opose, ores, nc, ns = omo.register_scan(mc, ms, guess)
+    assert st == lv.OK and ores.status == 0
+    assert res.iterations == ores.iterations and res.converged == ores.converged
+    assert np.abs(pose[:3] - opose[:3]).max() <= 1e-5 and np.abs(pose[3:] - opose[3:]).max() <= 1e-4
+    assert np.abs(pose[3:] - true[3:]).max() < 0.05
+    mo.close()
