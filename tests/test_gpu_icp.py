@@ -248,3 +248,42 @@ def test_perform_loop_closure_gates(lv, loop_sequence):
     assert g.status == o.status == lv.LOOP_SUBMAP_TOO_SMALL
     assert g.n_source == o.n_source and g.n_target == o.n_target
     hs.close()
+
+
+def test_next_row_apis_reject_bad_input(lv):
+    """error behaviour of the loop-closure / global-map / depth / projection entry points"""
+    hd = lv.Lvreg()
+    with pytest.raises(lv.LvregError) as e:
+        hd.icp_align()
+    assert e.value.status == lv.ERR_NO_MAP
+    with pytest.raises(lv.LvregError) as e:
+        hd.perform_loop_closure(0, 0)
+    assert e.value.status == lv.ERR_NO_KEYFRAMES
+    with pytest.raises(lv.LvregError) as e:
+        hd.build_global_map([0])
+    assert e.value.status == lv.ERR_NO_KEYFRAMES
+    pts = np.random.default_rng(0).uniform(-5, 5, (400, 4)).astype(np.float32)
+    hd.add_keyframe(pts, pts, np.zeros(6, np.float32))
+    with pytest.raises(lv.LvregError) as e:
+        hd.build_global_map([3])
+    assert e.value.status == lv.ERR_INVALID
+    with pytest.raises(lv.LvregError) as e:
+        hd.perform_loop_closure(0, 5)
+    assert e.value.status == lv.ERR_INVALID
+    with pytest.raises(lv.LvregError) as e:
+        hd.icp_set_cloud(1, pts)
+        hd.icp_set_cloud(0, pts)
+        hd.icp_align(lv.icp_default_params(max_iterations=0))
+    assert e.value.status == lv.ERR_INVALID
+    # no depth cloud yet: every feature comes back without depth
+    d, f3 = hd.get_depth(np.array([1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0], np.float32), np.array([[0.1, 0.2, 1.0]], np.float32))
+    assert d[0] == -1 and f3[0, 3] == -1
+    raw = lv.make_raw_cloud(pts, np.zeros(len(pts), np.uint16), np.zeros(len(pts), np.float32))
+    for bad in (dict(n_scan=0), dict(n_scan=300), dict(horizon_scan=0), dict(downsample_rate=0), dict(sensor=7),
+                dict(deskew=True, imu_time=np.zeros(0), imu_rot=np.zeros((0, 3)))):
+        with pytest.raises(lv.LvregError) as e:
+            hd.project_cloud(raw, **bad)
+        assert e.value.status == lv.ERR_INVALID, bad
+    # a handle keeps working after rejected calls
+    assert hd.project_cloud(raw, n_scan=1, horizon_scan=1000, lidar_min_range=0.0) > 0
+    hd.close()
