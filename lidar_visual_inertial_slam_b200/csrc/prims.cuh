@@ -311,6 +311,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) rs_onesweep_kernel(
     SORT_STAMP(3);
 
     // ---- rank the tile's elements (stable) ----
+    const uint32_t lt_mask = (1u << lane) - 1u;
 #pragma unroll
     for (int r = 0; r < kSortItems; ++r) {
         // lanes with the same digit, from 8 ballots: the hardware match.any iterates over the
@@ -319,21 +320,18 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) rs_onesweep_kernel(
         uint32_t peers = 0xffffffffu;
 #pragma unroll
         for (int b = 0; b < 8; ++b) {
-            const bool bit = (dg >> b) & 1u;
+            const bool bit = (dg & (1u << b)) != 0;
             const uint32_t bal = __ballot_sync(0xffffffffu, bit);
-            peers &= bit ? bal : ~bal;
+            peers &= bal ^ (bit ? 0u : 0xffffffffu);
         }
-        // the counters are private to the warp and each digit has one leader: a plain
-        // read-modify-write is enough (a shared-memory atomic with a result is slower)
-        const int leader = __ffs(peers) - 1;
-        uint32_t old = 0;
-        if (lane == leader) {
-            old = wcnt[warp][dg];
-            wcnt[warp][dg] = old + (uint32_t)__popc(peers);
-        }
+        // The counters are private to the warp.  Every lane reads its digit's counter (peers read the same
+        // word), then the lowest peer alone stores the new value: no atomic, no branch, no shuffle.  Shared
+        // memory accesses of one warp execute in program order, so the next round sees the store.
+        const uint32_t lower = peers & lt_mask;
+        const uint32_t old = wcnt[warp][dg];
+        if (lower == 0) wcnt[warp][dg] = old + (uint32_t)__popc(peers);
         __syncwarp();
-        old = __shfl_sync(0xffffffffu, old, leader);
-        rank[r] = (uint16_t)(old + __popc(peers & ((1u << lane) - 1u)));
+        rank[r] = (uint16_t)(old + __popc(lower));
     }
     SORT_STAMP(4);
 
