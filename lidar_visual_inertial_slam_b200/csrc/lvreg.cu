@@ -166,7 +166,7 @@ inline int fail(lvreg_handle* h, int code, const char* msg) {
 inline uint32_t nblk(uint32_t n, uint32_t per) { return (n + per - 1) / per; }
 
 // small device scalars inside h->small
-enum { SM_MM = 0 /*6 u32*/, SM_NVOX = 8, SM_TOTAL = 9, SM_CONV = 10, SM_WORDS = 64 };
+enum { SM_MM = 0 /*6 u32*/, SM_NVOX = 8, SM_TOTAL = 9, SM_CONV = 10, SM_SMALLVG = 32 /*VgSmallInfo, 8 words*/, SM_WORDS = 64 };
 
 inline void launched(lvreg_handle* h, int k = 1) { h->call_launches += k; }
 
@@ -297,6 +297,7 @@ struct VgJob {
     uint32_t* n_out = nullptr;
     bool want_out_keys = false;        // per-voxel idx into Lane::vox_keys
     uint32_t* d_point_keys = nullptr;  // optional device array (n): per-point idx
+    bool small = false;                // internal: handled by the single-block kernel
     // results
     float mn[3] = {0, 0, 0}, mx[3] = {0, 0, 0};   // bbox of the input cloud
     int passthrough = 0;
@@ -317,16 +318,33 @@ int voxelgrid_batch(lvreg_handle* h, VgJob* jobs, int nj) {
         for (int b2 = a2 + 1; b2 < nj; ++b2)
             if (jobs[order[b2]].n > jobs[order[a2]].n) { int t2 = order[a2]; order[a2] = order[b2]; order[b2] = t2; }
     // ---- phase 1: (transform + concatenate +) bounding box ----
+    unsigned sync1_mask = 0;
     for (int jo = 0; jo < nj; ++jo) {
         VgJob& J = jobs[order[jo]];
         Lane& L = h->lane[J.lane];
         *J.n_out = 0;
         J.passthrough = 0;
+        J.small = false;
         if (J.n == 0) {
             CK(J.out->reserve(16));
             continue;
         }
         if (!(J.leaf > 0.f)) return fail(h, LVREG_ERR_INVALID, "leaf size must be positive");
+        J.small = !J.from_segments && J.n <= (uint32_t)kVgSmallMax;
+        if (J.small) {
+            // the whole filter in one block, no host round trip until the shared final synchronisation
+            CK(J.out->reserve((size_t)J.n * 16));
+            uint32_t* okeys = nullptr;
+            if (J.want_out_keys) {
+                CK(L.vox_keys.reserve((size_t)J.n * 4));
+                okeys = L.vox_keys.as<uint32_t>();
+            }
+            VgSmallInfo* d_info = reinterpret_cast<VgSmallInfo*>(L.small.as<uint32_t>() + SM_SMALLVG);
+            voxelgrid_small_kernel<<<1, kVgSmallThreads, 0, L.st>>>(J.pts, J.n, J.leaf, J.out->as<float4>(), okeys, J.d_point_keys, d_info);
+            launched(h);
+            CK(cudaMemcpyAsync(L.pinned + 32, d_info, sizeof(VgSmallInfo), cudaMemcpyDeviceToHost, L.st));
+            continue;
+        }
         uint32_t* mm = L.small.as<uint32_t>() + SM_MM;
         CK(cudaMemsetAsync(mm, 0xff, 3 * sizeof(uint32_t), L.st));
         CK(cudaMemsetAsync(mm + 3, 0, 3 * sizeof(uint32_t), L.st));
@@ -342,12 +360,13 @@ int voxelgrid_batch(lvreg_handle* h, VgJob* jobs, int nj) {
         }
         launched(h);
         CK(cudaMemcpyAsync(L.pinned, mm, 6 * sizeof(uint32_t), cudaMemcpyDeviceToHost, L.st));
+        sync1_mask |= 1u << J.lane;
     }
-    CK(lanes_sync(h, mask));
+    if (sync1_mask) CK(lanes_sync(h, sync1_mask));
     // ---- phase 2: keys, stable sort, run heads ----
     for (int jo = 0; jo < nj; ++jo) {
         VgJob& J = jobs[order[jo]];
-        if (J.n == 0) continue;
+        if (J.n == 0 || J.small) continue;
         Lane& L = h->lane[J.lane];
         for (int a = 0; a < 3; ++a) {
             J.mn[a] = ordered_to_float(L.pinned[a]);
@@ -398,6 +417,13 @@ int voxelgrid_batch(lvreg_handle* h, VgJob* jobs, int nj) {
     // ---- phase 3: centroids (left running on the lane streams) ----
     for (int jo = 0; jo < nj; ++jo) {
         VgJob& J = jobs[order[jo]];
+        if (J.small) {                                 // everything already happened in one block
+            const VgSmallInfo* info = reinterpret_cast<const VgSmallInfo*>(h->lane[J.lane].pinned + 32);
+            *J.n_out = info->nvox;
+            J.passthrough = info->passthrough;
+            for (int a = 0; a < 3; ++a) { J.mn[a] = info->mn[a]; J.mx[a] = info->mx[a]; }
+            continue;
+        }
         if (J.n == 0 || J.passthrough) continue;
         Lane& L = h->lane[J.lane];
         const uint32_t nvox = L.pinned[8];

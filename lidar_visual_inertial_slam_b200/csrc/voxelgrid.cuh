@@ -213,4 +213,152 @@ __global__ void __launch_bounds__(128) centroid_kernel(const float4* __restrict_
     if (out_keys) out_keys[v] = sorted_keys[b];
 }
 
+
+// ---- small clouds: the whole filter in ONE block ------------------------------------------------------
+// Up to kVgSmallMax points (key poses in extractNearby MO:910-911, the MID360 corner cloud, ...): bounding
+// box, PCL's bounds / overflow rule, keys, a bitonic sort of (key << 32 | input index) -- stable by
+// construction --, run heads and the sequential centroids, without leaving the SM and without a host round
+// trip in between.  Same fp32 expressions as the multi-kernel path, so the result is bit-identical to it.
+constexpr int kVgSmallMax = 2048;
+constexpr int kVgSmallThreads = 1024;
+struct VgSmallInfo {
+    uint32_t nvox;
+    int32_t passthrough;
+    float mn[3], mx[3];
+};
+
+__global__ void __launch_bounds__(kVgSmallThreads) voxelgrid_small_kernel(const float4* __restrict__ pts, uint32_t n, float leaf,
+                                                                          float4* __restrict__ out, uint32_t* __restrict__ out_keys,
+                                                                          uint32_t* __restrict__ point_keys,
+                                                                          VgSmallInfo* __restrict__ info) {
+    __shared__ unsigned long long sk[kVgSmallMax];
+    __shared__ uint32_t start[kVgSmallMax];
+    __shared__ float red[6][32];
+    __shared__ uint32_t wsum[32];
+    __shared__ VoxelSpec vs;
+    __shared__ int pass_s;
+    __shared__ uint32_t nv_s;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float mnx = 3.4e38f, mny = 3.4e38f, mnz = 3.4e38f, mxx = -3.4e38f, mxy = -3.4e38f, mxz = -3.4e38f;
+    for (uint32_t i = tid; i < n; i += kVgSmallThreads) {
+        const float4 p = pts[i];
+        mnx = fminf(mnx, p.x); mny = fminf(mny, p.y); mnz = fminf(mnz, p.z);
+        mxx = fmaxf(mxx, p.x); mxy = fmaxf(mxy, p.y); mxz = fmaxf(mxz, p.z);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mnx = fminf(mnx, __shfl_xor_sync(0xffffffffu, mnx, o)); mny = fminf(mny, __shfl_xor_sync(0xffffffffu, mny, o));
+        mnz = fminf(mnz, __shfl_xor_sync(0xffffffffu, mnz, o)); mxx = fmaxf(mxx, __shfl_xor_sync(0xffffffffu, mxx, o));
+        mxy = fmaxf(mxy, __shfl_xor_sync(0xffffffffu, mxy, o)); mxz = fmaxf(mxz, __shfl_xor_sync(0xffffffffu, mxz, o));
+    }
+    if (lane == 0) { red[0][warp] = mnx; red[1][warp] = mny; red[2][warp] = mnz; red[3][warp] = mxx; red[4][warp] = mxy; red[5][warp] = mxz; }
+    __syncthreads();
+    if (tid == 0) {
+        float mn[3], mx[3];
+        for (int a = 0; a < 3; ++a) {
+            float lo = red[a][0], hi = red[3 + a][0];
+            for (int w = 1; w < kVgSmallThreads / 32; ++w) { lo = fminf(lo, red[a][w]); hi = fmaxf(hi, red[3 + a][w]); }
+            mn[a] = lo; mx[a] = hi;
+            info->mn[a] = lo; info->mx[a] = hi;
+        }
+        // PCL voxel_grid.hpp: leaf-size overflow rule and bounds, fp32 exactly as PCL computes them
+        const float inv = 1.0f / leaf;
+        long long d[3];
+        for (int a = 0; a < 3; ++a) d[a] = (long long)((mx[a] - mn[a]) * inv) + 1;
+        pass_s = d[0] * d[1] * d[2] > 2147483647ll ? 1 : 0;
+        vs.inv = inv;
+        int div_b[3];
+        for (int a = 0; a < 3; ++a) {
+            vs.min_b[a] = (int)floorf(mn[a] * inv);
+            const int max_b = (int)floorf(mx[a] * inv);
+            div_b[a] = max_b - vs.min_b[a] + 1;
+        }
+        vs.mul[0] = 1; vs.mul[1] = div_b[0]; vs.mul[2] = div_b[0] * div_b[1];
+        vs.key_bits = 32;
+    }
+    __syncthreads();
+    if (pass_s) {
+        for (uint32_t i = tid; i < n; i += kVgSmallThreads) {
+            out[i] = pts[i];
+            if (point_keys) point_keys[i] = 0;
+        }
+        if (tid == 0) { info->nvox = n; info->passthrough = 1; }
+        return;
+    }
+    // keys; the sort size is the next power of two, padded with keys that sort last
+    uint32_t n2 = 2;
+    while (n2 < n) n2 <<= 1;
+    for (uint32_t i = tid; i < n2; i += kVgSmallThreads) {
+        unsigned long long kk = ~0ull;
+        if (i < n) {
+            const float4 p = pts[i];
+            const int ix = (int)(floorf(p.x * vs.inv) - (float)vs.min_b[0]);
+            const int iy = (int)(floorf(p.y * vs.inv) - (float)vs.min_b[1]);
+            const int iz = (int)(floorf(p.z * vs.inv) - (float)vs.min_b[2]);
+            const uint32_t key = (uint32_t)(ix * vs.mul[0] + iy * vs.mul[1] + iz * vs.mul[2]);
+            if (point_keys) point_keys[i] = key;
+            kk = ((unsigned long long)key << 32) | (unsigned long long)i;
+        }
+        sk[i] = kk;
+    }
+    __syncthreads();
+    for (uint32_t k = 2; k <= n2; k <<= 1)
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            for (uint32_t t = tid; t < n2 / 2; t += kVgSmallThreads) {
+                const uint32_t i = 2 * t - (t & (j - 1));          // lower index of the pair
+                const uint32_t l = i + j;
+                const unsigned long long a = sk[i], b = sk[l];
+                const bool up = (i & k) == 0;
+                if ((a > b) == up) { sk[i] = b; sk[l] = a; }
+            }
+            __syncthreads();
+        }
+    // run heads -> voxel starts (two consecutive elements per thread, block exclusive scan)
+    uint32_t f0 = 0, f1 = 0;
+    {
+        const uint32_t j0 = 2 * tid, j1 = 2 * tid + 1;
+        if (j0 < n) f0 = (j0 == 0 || (uint32_t)(sk[j0] >> 32) != (uint32_t)(sk[j0 - 1] >> 32)) ? 1u : 0u;
+        if (j1 < n) f1 = ((uint32_t)(sk[j1] >> 32) != (uint32_t)(sk[j1 - 1] >> 32)) ? 1u : 0u;
+    }
+    const uint32_t mine = f0 + f1;
+    uint32_t inc = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += v;
+    }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = wsum[lane];
+        uint32_t winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= o) winc += v;
+        }
+        wsum[lane] = winc - w;
+        if (lane == 31) nv_s = winc;
+    }
+    __syncthreads();
+    uint32_t pre = inc - mine + wsum[warp];
+    if (f0) start[pre] = 2 * tid;
+    pre += f0;
+    if (f1) start[pre] = 2 * tid + 1;
+    __syncthreads();
+    const uint32_t nv = nv_s;
+    for (uint32_t v = tid; v < nv; v += kVgSmallThreads) {
+        const uint32_t b = start[v], e = v + 1 < nv ? start[v + 1] : n;
+        float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
+        for (uint32_t j = b; j < e; ++j) {
+            const float4 p = __ldg(pts + (uint32_t)sk[j]);
+            sx += p.x; sy += p.y; sz += p.z; si += p.w;
+        }
+        const float cnt = (float)(e - b);
+        out[v] = make_float4(sx / cnt, sy / cnt, sz / cnt, si / cnt);
+        if (out_keys) out_keys[v] = (uint32_t)(sk[b] >> 32);
+    }
+    if (tid == 0) { info->nvox = nv; info->passthrough = 0; }
+}
+
 }  // namespace lvreg

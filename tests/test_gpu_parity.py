@@ -70,6 +70,20 @@ def test_voxelgrid_bit_exact(h, leaf, n, scale):
     assert np.array_equal(h.voxel_keys(pts, leaf), ref_keys)  # per-point keys
 
 
+@pytest.mark.parametrize("n", [2, 3, 31, 1000, 2047, 2048, 2049, 4097])
+def test_voxelgrid_single_block_path_and_its_threshold(h, n):
+    """clouds of up to 2048 points take the one-block kernel, larger ones the sort pipeline: both bit-exact"""
+    rng = np.random.default_rng(1000 + n)
+    pts = np.concatenate([rng.uniform(-6, 6, (n, 3)) * [1, 1, 0.2], rng.uniform(0, 255, (n, 1))], 1).astype(np.float32)
+    pts[n // 2:, :3] = pts[: n - n // 2, :3] + np.float32(0.01)        # many shared voxels, order-dependent centroids
+    for leaf in (0.2, 2.0):
+        ref, ref_keys, ref_okeys, _ = O.voxelgrid(pts, leaf)
+        out, okeys, passthrough = h.voxelgrid(pts, leaf)
+        assert not passthrough
+        assert np.array_equal(okeys, ref_okeys) and np.array_equal(out, ref)
+        assert np.array_equal(h.voxel_keys(pts, leaf), ref_keys)
+
+
 def test_voxelgrid_clustered_many_points_per_voxel(h):
     rng = np.random.default_rng(5)
     centers = rng.uniform(-10, 10, (50, 3))
