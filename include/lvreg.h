@@ -137,6 +137,12 @@ void        lvreg_host_free(void* p);
 
 /* ---- keyframe store: cornerCloudKeyFrames / surfCloudKeyFrames / cloudKeyPoses6D (MO:83-87) -- */
 /* saveKeyFramesAndFactor's push_back of the DS feature clouds + pose (MO:1600-1610). */
+/* Pre-sizes every per-call buffer (upper bounds; 0 skips a group) so that no later call allocates device
+ * memory: map_points_* = points entering the local-map VoxelGrid per class (sum over the selected
+ * keyframes), scan_points_* = raw feature points per scan, max_grid_cells = cells of a search grid
+ * (<= 2^26).  Without it the buffers grow geometrically on demand (each growth synchronises the device). */
+int lvreg_reserve(lvreg_handle* h, size_t map_points_corner, size_t map_points_surf, size_t scan_points_corner,
+                  size_t scan_points_surf, size_t max_grid_cells);
 int lvreg_add_keyframe(lvreg_handle* h, const lvreg_cloud* corner, const lvreg_cloud* surf,
                        const float pose_rpyxyz[6], int32_t* id_out);
 /* Same, taking the device-resident laserCloud{Corner,Surf}LastDS of the current scan (the

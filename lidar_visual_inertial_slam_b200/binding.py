@@ -256,6 +256,11 @@ class Lvreg:
             raise LvregError(st, self.L.lvreg_last_error(self.h).decode())
         return st
 
+    def reserve(self, map_points_corner=0, map_points_surf=0, scan_points_corner=0, scan_points_surf=0, max_grid_cells=0):
+        self._ck(self.L.lvreg_reserve(self.h, C.c_size_t(map_points_corner), C.c_size_t(map_points_surf),
+                                      C.c_size_t(scan_points_corner), C.c_size_t(scan_points_surf),
+                                      C.c_size_t(max_grid_cells)))
+
     # ---- keyframes / map ----
     def add_keyframe(self, corner, surf, pose):
         c, _k1 = _cloud(corner)

@@ -9,6 +9,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <chrono>
 #include <deque>
 #include <string>
 #include <vector>
@@ -28,12 +29,23 @@ using namespace lvreg;
 
 namespace {
 
+static double g_alloc_ms = 0.0;      // LVREG_DEBUG_ALLOC diagnostics
+static size_t g_alloc_bytes = 0;
+static int g_alloc_calls = 0;
 struct DevBuf {
     void* p = nullptr;
     size_t cap = 0;
     cudaError_t reserve(size_t bytes) {
         if (bytes <= cap) return cudaSuccess;
+        struct Timer {
+            std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+            ~Timer() { g_alloc_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); ++g_alloc_calls; }
+        } timer;
+        g_alloc_bytes += bytes;
+        // geometric growth: a buffer that has to grow doubles, so a session re-allocates O(log size) times
+        // (cudaFree / cudaMalloc synchronise the device and were measured to stall a call for up to seconds)
         size_t want = bytes + bytes / 4 + 256;
+        if (cap && want < 2 * cap) want = 2 * cap;
         want = (want + 255) & ~(size_t)255;
         if (p) cudaFree(p);
         p = nullptr;
@@ -957,6 +969,46 @@ void lvreg_destroy(lvreg_handle* h) {
     delete h;
 }
 
+
+// Pre-sizes every per-call buffer for the given workload so that no later call allocates device memory
+// (cudaMalloc / cudaFree synchronise the device; single calls were measured to stall for 10-100 ms, and
+// growth in the middle of a sequence shows up as a latency outlier).  All arguments are upper bounds;
+// 0 skips that group.  Without this call the buffers grow geometrically on demand.
+int lvreg_reserve(lvreg_handle* h, size_t map_points_corner, size_t map_points_surf, size_t scan_points_corner,
+                  size_t scan_points_surf, size_t max_grid_cells) {
+    if (!h) return LVREG_ERR_INVALID;
+    const size_t lim = 0x7fffffffull;
+    if (map_points_corner > lim || map_points_surf > lim || scan_points_corner > lim || scan_points_surf > lim ||
+        max_grid_cells > ((size_t)1 << 26))
+        return fail(h, LVREG_ERR_INVALID, "reserve: size out of range");
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->st));
+    const size_t npts[kLanes] = {map_points_corner, map_points_surf, scan_points_corner, scan_points_surf};
+    for (int l = 0; l < kLanes; ++l) {
+        const size_t n = npts[l];
+        if (!n) continue;
+        Lane& L = h->lane[l];
+        CKS(ensure_sort_buffers(h, L, (uint32_t)n));
+        CK(L.vox_start.reserve(n * 4));
+        CK(L.stage.reserve(n * 32));
+        if (l < 2) {
+            CK(L.concat.reserve(n * 16));
+            CK(h->map[l].ds.reserve(n * 16));
+            CK(h->map[l].cell_pts.reserve(n * 16));
+            if (max_grid_cells) {
+                CK(L.scan_in.reserve((max_grid_cells + 9) * 4));
+                CK(h->map[l].cell_start.reserve((max_grid_cells + 9) * 4));
+                CK(L.scan_temp.reserve((size_t)(scan_num_tiles((uint32_t)max_grid_cells + 1) + 2) * 4));
+            }
+        } else {
+            CK(L.raw.reserve(n * 16));
+            CK(h->scan_ds[l - 2].reserve(n * 16));
+        }
+    }
+    CK(cudaStreamSynchronize(h->st));
+    return LVREG_OK;
+}
+
 // ---- keyframes -----------------------------------------------------------------------------------
 namespace {
 Keyframe* take_keyframe(lvreg_handle* h) {
@@ -1197,6 +1249,11 @@ int lvreg_register_scan(lvreg_handle* h, const lvreg_cloud* corner_raw, const lv
         lanes_join(h, 0x3);
     }
     mark(h, EV_GRID);
+    if (getenv("LVREG_DEBUG_ALLOC") && g_alloc_calls) {
+        fprintf(stderr, "[lvreg] allocations in this call: %d calls, %.1f MB requested, %.2f ms\n", g_alloc_calls,
+                g_alloc_bytes / 1048576.0, g_alloc_ms);
+        g_alloc_ms = 0.0; g_alloc_bytes = 0; g_alloc_calls = 0;
+    }
     int s = scan2map_impl(h, pose, res);                      // scan2MapOptimization MO:322
     if (s == LVREG_OK || s == LVREG_ERR_NOT_ENOUGH_FEATURES) {
         CK(cudaStreamSynchronize(h->st));

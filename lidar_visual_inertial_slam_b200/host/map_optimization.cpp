@@ -53,6 +53,11 @@ mapOptimization::mapOptimization(const ParamServer& params, int device) : P_(par
     if (st != LVREG_OK)
         throw std::runtime_error(std::string("lvreg_create failed: ") + lvreg_status_string(st) +
                                  " (a CUDA device is required; there is no CPU fallback)");
+    if (P_.reserveMapCorner || P_.reserveMapSurf || P_.reserveScanCorner || P_.reserveScanSurf) {
+        st = lvreg_reserve(h_, P_.reserveMapCorner, P_.reserveMapSurf, P_.reserveScanCorner, P_.reserveScanSurf,
+                           P_.reserveGridCells);
+        if (st != LVREG_OK) throw std::runtime_error(std::string("lvreg_reserve: ") + lvreg_last_error(h_));
+    }
 }
 
 mapOptimization::~mapOptimization() { lvreg_destroy(h_); }

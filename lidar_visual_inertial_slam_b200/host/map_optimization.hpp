@@ -51,6 +51,9 @@ struct ParamServer {
     float historyKeyframeSearchTimeDiff = 30.0f;            // utility.h:298
     int   historyKeyframeSearchNum = 25;                    // utility.h:300
     float historyKeyframeFitnessScore = 0.3f;               // utility.h:302
+    // optional capacity hints (0 = grow on demand): points entering the local-map VoxelGrid per class, raw feature
+    // points per scan, cells of a search grid -- see lvreg_reserve
+    size_t reserveMapCorner = 0, reserveMapSurf = 0, reserveScanCorner = 0, reserveScanSurf = 0, reserveGridCells = 0;
     ParamServer() { lvreg_default_params(&lv); }
 };
 

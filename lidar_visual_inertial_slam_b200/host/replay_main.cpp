@@ -35,7 +35,12 @@ int main(int argc, char** argv) {
             // other (reset() in between), so only the first one pays the device allocations
             std::unique_ptr<mapOptimization> mo;
             try {       // untimed warm-up: CUDA context, lazy kernel loading, first allocations
-                mo.reset(new mapOptimization(ParamServer(), g));
+                ParamServer ps;                       // capacity hints: no device allocation inside the timed replay
+                if (sensor == 1) { ps.reserveMapCorner = 3000000; ps.reserveMapSurf = 12000000; ps.reserveScanCorner = 65536;
+                                   ps.reserveScanSurf = 400000; ps.reserveGridCells = (size_t)1 << 25; }
+                else { ps.reserveMapCorner = 200000; ps.reserveMapSurf = 800000; ps.reserveScanCorner = 20000;
+                       ps.reserveScanSurf = 60000; ps.reserveGridCells = (size_t)1 << 22; }
+                mo.reset(new mapOptimization(ps, g));
                 SequenceSpec w{sensor, seed + 7777ull, 8, 0.2, 1.0, 0.10f, 0.035f};
                 replay_sequence(w, g, 2, mo.get());
             } catch (const std::exception& e) {

@@ -120,6 +120,24 @@ def test_voxelgrid_edge_cases(h):
     assert passthrough and np.array_equal(out, big)
 
 
+def test_reserve_presizes_without_changing_results(lv, room):
+    """lvreg_reserve: same results, and it rejects sizes out of range"""
+    a = lv.Lvreg()
+    b = lv.Lvreg()
+    b.reserve(map_points_corner=50000, map_points_surf=200000, scan_points_corner=4000, scan_points_surf=20000,
+              max_grid_cells=1 << 20)
+    for hd in (a, b):
+        hd.add_keyframe(room["cw"], room["sw"], np.zeros(6, np.float32))
+    pa, ra, sa = a.register_scan(room["c"], room["s"], [0], room["guess"])
+    pb, rb, sb = b.register_scan(room["c"], room["s"], [0], room["guess"])
+    assert sa == sb == lv.OK and np.array_equal(pa, pb) and ra.iterations == rb.iterations
+    assert np.array_equal(a.get_local_map(lv.SURF), b.get_local_map(lv.SURF))
+    with pytest.raises(lv.LvregError):
+        b.reserve(max_grid_cells=1 << 30)
+    a.close()
+    b.close()
+
+
 # ---- 5-NN ------------------------------------------------------------------------------------
 def _set_map(h, m):
     h.set_local_map(m, m)
