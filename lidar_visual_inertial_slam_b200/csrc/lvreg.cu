@@ -29,9 +29,9 @@ using namespace lvreg;
 
 namespace {
 
-static double g_alloc_ms = 0.0;      // LVREG_DEBUG_ALLOC diagnostics
-static size_t g_alloc_bytes = 0;
-static int g_alloc_calls = 0;
+static thread_local double g_alloc_ms = 0.0;      // LVREG_DEBUG_ALLOC diagnostics (one handle per host thread)
+static thread_local size_t g_alloc_bytes = 0;
+static thread_local int g_alloc_calls = 0;
 struct DevBuf {
     void* p = nullptr;
     size_t cap = 0;
