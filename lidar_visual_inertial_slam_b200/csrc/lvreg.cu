@@ -32,9 +32,41 @@ namespace {
 static thread_local double g_alloc_ms = 0.0;      // LVREG_DEBUG_ALLOC diagnostics (one handle per host thread)
 static thread_local size_t g_alloc_bytes = 0;
 static thread_local int g_alloc_calls = 0;
+// bump allocator over large slabs: keyframe clouds come from here, so adding a keyframe does not call
+// cudaMalloc (one slab holds hundreds of keyframes); everything is returned when the handle is destroyed
+struct Arena {
+    std::vector<void*> slabs;
+    char* cur = nullptr;
+    size_t left = 0;
+    size_t slab_bytes = (size_t)64 << 20;
+    cudaError_t alloc(size_t bytes, void** out) {
+        bytes = (bytes + 255) & ~(size_t)255;
+        if (bytes > left) {
+            const size_t sz = bytes > slab_bytes ? bytes : slab_bytes;
+            void* p = nullptr;
+            cudaError_t e = cudaMalloc(&p, sz);
+            if (e != cudaSuccess) return e;
+            slabs.push_back(p);
+            cur = (char*)p;
+            left = sz;
+        }
+        *out = cur;
+        cur += bytes;
+        left -= bytes;
+        return cudaSuccess;
+    }
+    void release_all() {
+        for (void* p : slabs) cudaFree(p);
+        slabs.clear();
+        cur = nullptr;
+        left = 0;
+    }
+};
+
 struct DevBuf {
     void* p = nullptr;
     size_t cap = 0;
+    Arena* arena = nullptr;          // when set, the memory belongs to the arena (never freed individually)
     cudaError_t reserve(size_t bytes) {
         if (bytes <= cap) return cudaSuccess;
         struct Timer {
@@ -42,6 +74,13 @@ struct DevBuf {
             ~Timer() { g_alloc_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); ++g_alloc_calls; }
         } timer;
         g_alloc_bytes += bytes;
+        if (arena) {
+            const size_t want = (bytes + 255) & ~(size_t)255;
+            void* np = nullptr;
+            cudaError_t e = arena->alloc(want, &np);      // a previous, smaller block is simply abandoned
+            if (e == cudaSuccess) { p = np; cap = want; }
+            return e;
+        }
         // geometric growth: a buffer that has to grow doubles, so a session re-allocates O(log size) times
         // (cudaFree / cudaMalloc synchronise the device and were measured to stall a call for up to seconds)
         size_t want = bytes + bytes / 4 + 256;
@@ -55,7 +94,7 @@ struct DevBuf {
         return e;
     }
     void release() {
-        if (p) cudaFree(p);
+        if (p && !arena) cudaFree(p);
         p = nullptr;
         cap = 0;
     }
@@ -117,6 +156,7 @@ struct lvreg_handle {
     bool reg_occ_is_tpq = false;
     std::vector<Keyframe*> kfs;
     std::vector<Keyframe*> kf_free;   // keyframes of a cleared session: their device buffers are reused
+    Arena kf_arena;                   // backing store of every keyframe cloud
     MapSide map[2];
     DevBuf scan_ds[2];
     uint32_t n_scan[2] = {0, 0};
@@ -961,6 +1001,7 @@ void lvreg_destroy(lvreg_handle* h) {
                       &h->vgout, &h->partials, &h->regout, &h->lmstate, &h->posebuf, &h->tilectr, &h->tilens, &h->qbuf,
                       &h->idxbuf, &h->d2buf, &h->brute_partial, &h->coeffbuf, &h->flagbuf};
     for (DevBuf* b : bufs) b->release();
+    h->kf_arena.release_all();
     if (h->ev_main) cudaEventDestroy(h->ev_main);
     if (h->pinned) cudaFreeHost(h->pinned);
     for (int i = 0; i < EV_COUNT; ++i)
@@ -1012,7 +1053,11 @@ int lvreg_reserve(lvreg_handle* h, size_t map_points_corner, size_t map_points_s
 // ---- keyframes -----------------------------------------------------------------------------------
 namespace {
 Keyframe* take_keyframe(lvreg_handle* h) {
-    if (h->kf_free.empty()) return new Keyframe();
+    if (h->kf_free.empty()) {
+        Keyframe* kf = new Keyframe();
+        kf->cloud[0].arena = kf->cloud[1].arena = &h->kf_arena;
+        return kf;
+    }
     Keyframe* kf = h->kf_free.back();
     h->kf_free.pop_back();
     kf->n[0] = kf->n[1] = 0;
