@@ -70,6 +70,14 @@ def main():
                     row["hbm_frac_of_measured"] = gbs / hbm
                 rows.append(row)
                 print(json.dumps(row), file=sys.stderr, flush=True)
+            # "with fused residual/Jacobian" (SURVEY 8d C4): search + plane fit + residual in one kernel; per query
+            # 16 B read + 16 B coefficients + 1 B flag written, neighbour coordinates gathered from L2
+            ms = h.bench_residuals(lv.SURF, q, None, 10)
+            gbs = (96.0 * nq + 16.0 * m) / (ms * 1e-3) / 1e9
+            row = dict(M=m, Nq=nq, variant="grid_gated_fused_residual", ms=ms, queries_per_s=nq / (ms * 1e-3),
+                       algorithmic_gbs=gbs, hbm_frac_of_measured=gbs / hbm)
+            rows.append(row)
+            print(json.dumps(row), file=sys.stderr, flush=True)
     print(json.dumps(dict(benchmark="C4 kNN sweep", grid_cell_m=float(info.grid_cell[1]), hbm_peak_gbs=hbm, rows=rows)))
     h.close()
 

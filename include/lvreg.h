@@ -401,6 +401,10 @@ int lvreg_bench_knn5(lvreg_handle* h, int which_map, const lvreg_cloud* queries,
 /* Radix-sort micro-benchmark: sorts n pseudo-random (key, index) pairs with `key_bits` significant
  * bits `repeats` times on the handle's stream; returns the mean device time of one whole sort and the
  * number of 8-bit passes it took.  Algorithmic traffic per pass = 16 B per pair. */
+/* C4 "with fused residual": times the fused search + fit + residual kernel of one feature class on
+ * device-resident queries (CUDA events, ms per launch); nothing is copied back */
+int lvreg_bench_residuals(lvreg_handle* h, int which, const lvreg_cloud* queries, const float pose_rpyxyz[6],
+                          int repeats, float* ms);
 int lvreg_bench_sort(lvreg_handle* h, size_t n, int key_bits, int repeats, float* ms_per_sort, int* passes);
 
 #ifdef __cplusplus

@@ -548,6 +548,13 @@ class Lvreg:
         self._ck(self.L.lvreg_bench_knn5(self.h, which, C.byref(c), variant, repeats, C.byref(ms)))
         return ms.value
 
+    def bench_residuals(self, which, queries, pose=None, repeats=10):
+        c, keep = _cloud(queries)
+        pose = np.ascontiguousarray(np.zeros(6) if pose is None else pose, np.float32)
+        ms = C.c_float(0)
+        self._ck(self.L.lvreg_bench_residuals(self.h, which, C.byref(c), pose.ctypes.data_as(C.c_void_p), repeats, C.byref(ms)))
+        return ms.value
+
     def extract_features(self, pts, point_range, point_col_ind, start_ring, end_ring, edge_threshold=1.0,
                          surf_threshold=0.1, surf_leaf=0.4):
         """FeatureExtraction (featureExtraction.cpp:87-245) -> (corner, surf, label)"""

@@ -1514,6 +1514,38 @@ int lvreg_bench_knn5(lvreg_handle* h, int which, const lvreg_cloud* queries, int
     return LVREG_OK;
 }
 
+// C4 "with fused residual": search + fit + residual of surfOptimization / cornerOptimization in one kernel
+// (residual_kernel), device-resident queries, CUDA-event timing; nothing is copied back
+int lvreg_bench_residuals(lvreg_handle* h, int which, const lvreg_cloud* queries, const float pose[6], int repeats, float* ms) {
+    if (!h || which < 0 || which > 1 || !queries || !pose || repeats < 1) return LVREG_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    if (!h->map[which].valid) return fail(h, LVREG_ERR_NO_MAP, "no local map");
+    begin_call(h);
+    CKS(upload_cloud(h, queries, h->qbuf, h->lane[LANE_SCAN_CORNER].stage, h->st));
+    const uint32_t n = (uint32_t)queries->n;
+    if (n == 0) return fail(h, LVREG_ERR_INVALID, "no queries");
+    CK(h->coeffbuf.reserve((size_t)n * 16));
+    CK(h->flagbuf.reserve((size_t)n));
+    CK(h->idxbuf.reserve((size_t)n * 5 * 4));
+    Affine T;
+    pose_to_affine_host(pose, T.m);
+    const GridView g = grid_view(h->map[which]);
+    const RegParams P = reg_params(h);
+    const uint32_t blocks = min(nblk(nblk(n, 32), kRegWarps), (uint32_t)h->num_sms * 8);
+    for (int i = 0; i < repeats + 3; ++i) {
+        if (i == 3) mark(h, EV_BEGIN);
+        residual_kernel<8><<<blocks, kRegThreads, 0, h->st>>>(g, h->map[which].ds.as<float4>(), h->qbuf.as<float4>(), n, which, T, P,
+                                                              h->coeffbuf.as<float4>(), h->flagbuf.as<uint8_t>(), h->idxbuf.as<int32_t>());
+        launched(h);
+    }
+    mark(h, EV_REG);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(h->st));
+    if (ms) *ms = span(h, EV_BEGIN, EV_REG) / (float)repeats;
+    end_call(h);
+    return LVREG_OK;
+}
+
 static int residuals_api(lvreg_handle* h, int cls, const lvreg_cloud* pts, const float pose[6], float* coeff_out,
                          uint8_t* flag_out, int32_t* knn_idx_out) {
     if (!h || !pts || !pose) return LVREG_ERR_INVALID;
