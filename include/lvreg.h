@@ -47,6 +47,8 @@ extern "C" {
 #define LVREG_KNN_GRID_GATED 0   /* 27-cell search: exact whenever the 5th neighbour is inside the gate */
 #define LVREG_KNN_GRID_EXACT 1   /* ring expansion until provably exact (unbounded) */
 #define LVREG_KNN_BRUTE      2   /* exhaustive, FP32-pipe bound */
+#define LVREG_KNN_GRID_STAGED 3  /* GATED semantics through the registration kernel's search: 32-query tiles, the
+                                    cell box of a tile staged in shared memory by bulk copies (cp.async.bulk) */
 
 typedef struct lvreg_handle lvreg_handle;
 
@@ -391,6 +393,10 @@ int lvreg_get_iteration_profile(const lvreg_handle* h, float* us, int* iteration
 /* Diagnostics (set LVREG_DEBUG_TILES=1 before lvreg_create): duration in ns of every query tile of
  * iteration 1 of the last registration, in tile order (corner tiles first). */
 int lvreg_debug_tile_times(lvreg_handle* h, uint32_t* ns_out, size_t cap, size_t* n_tiles);
+/* Diagnostics (LVREG_DEBUG_TILES=1): how the shared-memory search of the last registration staged its
+ * query tiles in iteration 0: out[0..2] = tiles staged whole / as halves / as quarters, out[3] = queries that
+ * took the global-memory search, out[4] = copy-barrier time-outs (must be 0). */
+int lvreg_debug_stage_stats(lvreg_handle* h, uint32_t out[8]);
 /* total kernels launched by this handle since creation */
 int lvreg_get_launch_count(const lvreg_handle* h, uint64_t* n);
 /* kNN micro-benchmark on device-resident data: runs `repeats` launches of the chosen variant on

@@ -6,7 +6,7 @@ fails loudly if it is missing (there is no CPU fallback and nothing here touches
 """
 from .binding import (  # noqa: F401
     Lvreg, LvregError, Params, Result, MapInfo, Timings, lib, lib_path, default_params,
-    CORNER, SURF, KNN_GRID_GATED, KNN_GRID_EXACT, KNN_BRUTE,
+    CORNER, SURF, KNN_GRID_GATED, KNN_GRID_EXACT, KNN_BRUTE, KNN_GRID_STAGED,
     OK, ERR_INVALID, ERR_CUDA, ERR_NOT_ENOUGH_FEATURES, ERR_NO_KEYFRAMES, ERR_NO_MAP, ERR_CAPACITY,
     pose_to_affine, host_alloc_f32,
     RawCloud, ProjectionParams, make_raw_cloud, SENSOR_VELODYNE, SENSOR_OUSTER, SENSOR_LIVOX, LAYOUT_VELODYNE, LAYOUT_LIVOX,

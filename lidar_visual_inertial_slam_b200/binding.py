@@ -9,7 +9,7 @@ _LIBPATH = os.path.join(_HERE, "liblvreg.so")
 
 OK, ERR_INVALID, ERR_CUDA, ERR_NOT_ENOUGH_FEATURES, ERR_NO_KEYFRAMES, ERR_NO_MAP, ERR_CAPACITY = range(7)
 CORNER, SURF = 0, 1
-KNN_GRID_GATED, KNN_GRID_EXACT, KNN_BRUTE = 0, 1, 2
+KNN_GRID_GATED, KNN_GRID_EXACT, KNN_BRUTE, KNN_GRID_STAGED = 0, 1, 2, 3
 MAX_ITERS = 32
 
 
@@ -641,6 +641,11 @@ class Lvreg:
         out = np.zeros(n.value, np.uint32)
         if n.value:
             self._ck(self.L.lvreg_debug_tile_times(self.h, out.ctypes.data_as(C.c_void_p), C.c_size_t(n.value), C.byref(n)))
+        return out
+
+    def debug_stage_stats(self):
+        out = np.zeros(8, np.uint32)
+        self._ck(self.L.lvreg_debug_stage_stats(self.h, out.ctypes.data_as(C.c_void_p)))
         return out
 
     def launch_count(self):

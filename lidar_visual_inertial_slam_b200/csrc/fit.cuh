@@ -127,6 +127,83 @@ __device__ void jacobi_eigen(float* A, float* W, float* V) {
     }
 }
 
+// cv::eigen for the 3x3 covariance of cornerOptimization (MO:1050), entirely in registers: the same
+// operation sequence as jacobi_eigen<3> (pivot search through the row / column max-index caches,
+// including their staleness, rotation order, descending sort), but the three possible pivots
+// (0,1), (0,2), (1,2) are selected with predicated moves instead of indexing local arrays.  For
+// N = 3 only the strict upper triangle a01, a02, a12 is ever read; indR[1] = 2 and indC[1] = 0 are
+// constants, so the caches reduce to indR0 in {1, 2} and indC2 in {0, 1}.
+// Outputs: w0 >= w1 (the two largest eigenvalues) and the eigenvector row of w0.
+__device__ __forceinline__ void jacobi_eigen3_top(float a00, float a01, float a02, float a11, float a12,
+                                                  float a22, float* w_first, float* w_second,
+                                                  float* vx, float* vy, float* vz) {
+    float w0 = a00, w1 = a11, w2 = a22;
+    float v00 = 1.f, v01 = 0.f, v02 = 0.f, v10 = 0.f, v11 = 1.f, v12 = 0.f, v20 = 0.f, v21 = 0.f, v22 = 1.f;
+    int indR0 = (fabsf(a01) < fabsf(a02)) ? 2 : 1;
+    int indC2 = (fabsf(a02) < fabsf(a12)) ? 1 : 0;
+#pragma unroll 1
+    for (int it = 0; it < 3 * 3 * 30; ++it) {
+        // pivot: rows 0, 1 through indR, then columns 1, 2 through indC (strict '<' keeps the first maximum)
+        float mv = fabsf(indR0 == 1 ? a01 : a02);
+        int k = 0;
+        float v = fabsf(a12);
+        if (mv < v) { mv = v; k = 1; }
+        int l = (k == 0) ? indR0 : 2;
+        v = fabsf(a01);
+        if (mv < v) { mv = v; k = 0; l = 1; }
+        v = fabsf(indC2 == 0 ? a02 : a12);
+        if (mv < v) { mv = v; k = indC2; l = 2; }
+        const bool p01 = (l == 1), p12 = (k == 1);            // else the pivot is (0,2)
+        const float p = p01 ? a01 : (p12 ? a12 : a02);
+        if (fabsf(p) <= FLT_EPSILON) break;
+        const float wk = p12 ? w1 : w0, wl = p01 ? w1 : w2;
+        const float y = (wl - wk) * 0.5f;
+        float t = fabsf(y) + cv_hypot(p, y);
+        float s = cv_hypot(p, t);
+        const float c = t / s;
+        s = p / s;
+        t = (p / t) * p;
+        if (y < 0.0f) { s = -s; t = -t; }
+        // the two off-diagonal entries that are not the pivot rotate as one pair, in this order:
+        // (0,1): (a02, a12)   (0,2): (a01, a12)   (1,2): (a01, a02)
+        float ga = p01 ? a02 : a01, gb = p12 ? a02 : a12;
+        givens(ga, gb, c, s);
+        if (p01) { a01 = 0.0f; a02 = ga; a12 = gb; }
+        else if (p12) { a12 = 0.0f; a01 = ga; a02 = gb; }
+        else { a02 = 0.0f; a01 = ga; a12 = gb; }
+        const float nwk = wk - t, nwl = wl + t;
+        if (p12) w1 = nwk; else w0 = nwk;
+        if (p01) w1 = nwl; else w2 = nwl;
+        // eigenvector rows k and l
+        float rk0 = p12 ? v10 : v00, rk1 = p12 ? v11 : v01, rk2 = p12 ? v12 : v02;
+        float rl0 = p01 ? v10 : v20, rl1 = p01 ? v11 : v21, rl2 = p01 ? v12 : v22;
+        givens(rk0, rl0, c, s);
+        givens(rk1, rl1, c, s);
+        givens(rk2, rl2, c, s);
+        if (p12) { v10 = rk0; v11 = rk1; v12 = rk2; } else { v00 = rk0; v01 = rk1; v02 = rk2; }
+        if (p01) { v10 = rl0; v11 = rl1; v12 = rl2; } else { v20 = rl0; v21 = rl1; v22 = rl2; }
+        // caches of the touched rows / columns: indR[k] (only row 0 has a choice), indC[l] (only column 2)
+        if (k == 0) indR0 = (fabsf(a01) < fabsf(a02)) ? 2 : 1;
+        if (l == 2) indC2 = (fabsf(a02) < fabsf(a12)) ? 1 : 0;
+    }
+    // selection sort, descending, rows of V follow (only the first two values and the first row are used)
+    {
+        int m = 0;
+        if (w0 < w1) m = 1;
+        if ((m == 0 ? w0 : w1) < w2) m = 2;
+        if (m == 1) {
+            float tw = w1; w1 = w0; w0 = tw;
+            float t0 = v10, t1 = v11, t2 = v12; v10 = v00; v11 = v01; v12 = v02; v00 = t0; v01 = t1; v02 = t2;
+        } else if (m == 2) {
+            float tw = w2; w2 = w0; w0 = tw;
+            float t0 = v20, t1 = v21, t2 = v22; v20 = v00; v21 = v01; v22 = v02; v00 = t0; v01 = t1; v02 = t2;
+        }
+        if (w1 < w2) { float tw = w2; w2 = w1; w1 = tw; }
+    }
+    *w_first = w0; *w_second = w1;
+    *vx = v00; *vy = v01; *vz = v02;
+}
+
 // cornerOptimization for one point.  nb = the 5 neighbours (x,y,z), sel = pointSel (map frame).
 // Returns the acceptance flag; coeff = (s*la, s*lb, s*lc, s*ld2).
 __device__ __forceinline__ bool corner_residual(const float (&nbx)[5], const float (&nby)[5],
@@ -145,9 +222,8 @@ __device__ __forceinline__ bool corner_residual(const float (&nbx)[5], const flo
         a33 += az * az;
     }
     a11 /= 5; a12 /= 5; a13 /= 5; a22 /= 5; a23 /= 5; a33 /= 5;
-    float A[9] = {a11, a12, a13, a12, a22, a23, a13, a23, a33};
-    float D[3], V[9];
-    jacobi_eigen<3>(A, D, V);
+    float D[2], V[3];
+    jacobi_eigen3_top(a11, a12, a13, a22, a23, a33, &D[0], &D[1], &V[0], &V[1], &V[2]);
     if (!(D[0] > P.line_eig_ratio * D[1])) return false;
 
     // `cx + 0.1 * v` is evaluated in double in the reference (0.1 is a double literal)

@@ -441,6 +441,37 @@ __global__ void __launch_bounds__(256) knn5_brute_merge_kernel(const u64* __rest
     }
 }
 
+// ---- spatial ordering of the queries -----------------------------------------------------------------
+// The registration kernel stages, per 32-query tile, the box of map cells its queries touch; the tile must be
+// spatially compact for the box to fit in shared memory.  VoxelGrid order (x-fastest voxel rows of the whole
+// scan) is not compact, so the down-sampled scan is additionally ordered by the Morton code of its 2 m cell
+// (8 bits per axis, wrapping every 512 m: aliases only cost efficiency, never correctness).  The order is
+// taken in the sensor frame; a rigid transform keeps a compact tile compact.
+constexpr float kQueryCellInv = 0.5f;
+__device__ __forceinline__ uint32_t spread3_8(uint32_t v) {          // 8 bits -> every third bit
+    v &= 0xffu;
+    v = (v | (v << 8)) & 0x00f00fu;
+    v = (v | (v << 4)) & 0x0c30c3u;
+    v = (v | (v << 2)) & 0x249249u;
+    return v;
+}
+__global__ void __launch_bounds__(256) morton_keys_kernel(const float4* __restrict__ pts, uint32_t n,
+                                                          uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+    const uint32_t i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const float4 p = pts[i];
+    const int cx = (int)floorf(p.x * kQueryCellInv), cy = (int)floorf(p.y * kQueryCellInv), cz = (int)floorf(p.z * kQueryCellInv);
+    keys[i] = spread3_8((uint32_t)cx) | (spread3_8((uint32_t)cy) << 1) | (spread3_8((uint32_t)cz) << 2);
+    vals[i] = i;
+}
+__global__ void __launch_bounds__(256) gather_points_kernel(const float4* __restrict__ pts,
+                                                            const uint32_t* __restrict__ order, uint32_t n,
+                                                            float4* __restrict__ out) {
+    const uint32_t j = blockIdx.x * 256 + threadIdx.x;
+    if (j >= n) return;
+    out[j] = __ldg(pts + order[j]);
+}
+
 // ---- search-grid build ---------------------------------------------------------------------------
 struct GridSpec {
     float ox, oy, oz, inv, cell;

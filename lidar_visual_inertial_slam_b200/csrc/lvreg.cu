@@ -23,6 +23,8 @@
 #include "prims.cuh"
 #include "projection.cuh"
 #include "register.cuh"
+#include "register_staged.cuh"
+#include "register_warm.cuh"
 #include "voxelgrid.cuh"
 
 using namespace lvreg;
@@ -153,12 +155,16 @@ struct lvreg_handle {
     int debug_tiles = 0;          // LVREG_DEBUG_TILES=1: record per-tile durations of iteration 1
     uint32_t debug_ntiles = 0;
     int force_tpq = -1;           // -1 auto, 0 grouped, 1 thread-per-query (LVREG_TPQ)
-    bool reg_occ_is_tpq = false;
+    int reg_variant_env = -1;     // LVREG_REG: -1 auto, 0 grouped, 1 thread-per-query, 2 staged (shared-memory search),
+                                  // 3 warm (thread per query, warm-started radius, static tiles)
+    int reg_occ_variant = -1;
     std::vector<Keyframe*> kfs;
     std::vector<Keyframe*> kf_free;   // keyframes of a cleared session: their device buffers are reused
     Arena kf_arena;                   // backing store of every keyframe cloud
     MapSide map[2];
     DevBuf scan_ds[2];
+    DevBuf scan_sorted[2];        // the same points in Morton order of their 2 m cell: what the registration kernels read
+    bool scan_sorted_ok[2] = {false, false};
     uint32_t n_scan[2] = {0, 0};
     // loop closure: [0] source (cureKeyframeCloud), [1] target (prevKeyframeCloud) + its search grid
     MapSide icp_cloud[2];
@@ -179,6 +185,7 @@ struct lvreg_handle {
     DevBuf feat_pts, feat_range, feat_col, feat_rings, feat_curv, feat_picked, feat_label, feat_flag, feat_ringof,
         feat_cidx, feat_ccnt, feat_pos, feat_cand, feat_spec, feat_idx, feat_pidx, feat_corner, feat_surf;
     uint32_t n_feat[2] = {0, 0};
+    DevBuf stagestats, nnprev[2];
     DevBuf vgout, partials, regout, lmstate, posebuf, tilectr, tilens, qbuf, idxbuf, d2buf, brute_partial, coeffbuf, flagbuf;
     void* pinned = nullptr;       // 64 KB page-locked scratch: lanes use [0, 1 KB), RegOut lives at +4 KB
     cudaEvent_t ev[EV_COUNT];
@@ -690,6 +697,29 @@ int build_map_grids(lvreg_handle* h, VgJob* map_jobs) {
     return LVREG_OK;
 }
 
+// Morton-orders laserCloud{Corner,Surf}LastDS for the registration kernels (knn.cuh) on stream `st`, with the
+// scratch of the scan's lane.  The down-sampled cloud itself keeps PCL's order (it is API-visible and becomes
+// a keyframe).
+int sort_scan_for_search(lvreg_handle* h, int s, cudaStream_t st) {
+    Lane& L = h->lane[LANE_SCAN_CORNER + s];
+    const uint32_t n = h->n_scan[s];
+    h->scan_sorted_ok[s] = false;
+    CK(h->scan_sorted[s].reserve((size_t)(n ? n : 1) * 16));
+    if (n == 0) { h->scan_sorted_ok[s] = true; return LVREG_OK; }
+    CKS(ensure_sort_buffers(h, L, n));
+    morton_keys_kernel<<<nblk(n, 256), 256, 0, st>>>(h->scan_ds[s].as<float4>(), n, L.keys[0].as<uint32_t>(),
+                                                     L.vals[0].as<uint32_t>());
+    launched(h);
+    const int cur = radix_sort_pairs(L.keys[0].as<uint32_t>(), L.vals[0].as<uint32_t>(), L.keys[1].as<uint32_t>(),
+                                     L.vals[1].as<uint32_t>(), n, 24, L.sort_scratch.as<uint32_t>(), st, &h->call_launches);
+    gather_points_kernel<<<nblk(n, 256), 256, 0, st>>>(h->scan_ds[s].as<float4>(), L.vals[cur].as<uint32_t>(), n,
+                                                       h->scan_sorted[s].as<float4>());
+    launched(h);
+    CK(cudaGetLastError());
+    h->scan_sorted_ok[s] = true;
+    return LVREG_OK;
+}
+
 float clampf(float v, float lim) {
     if (v < -lim) v = -lim;
     if (v > lim) v = lim;
@@ -714,14 +744,8 @@ int reg_occupancy(lvreg_handle* h, int* nb) {
     do {                                                                        \
         const int key_ = h->lpq * 100 + h->tile;                                \
         switch (key_) {                                                         \
-            case 408: CKS((FN<4, 8>(__VA_ARGS__))); break;                      \
-            case 416: CKS((FN<4, 16>(__VA_ARGS__))); break;                     \
-            case 432: CKS((FN<4, 32>(__VA_ARGS__))); break;                     \
-            case 808: CKS((FN<8, 8>(__VA_ARGS__))); break;                      \
-            case 832: CKS((FN<8, 32>(__VA_ARGS__))); break;                     \
-            case 1616: CKS((FN<16, 16>(__VA_ARGS__))); break;                   \
-            case 1632: CKS((FN<16, 32>(__VA_ARGS__))); break;                   \
-            default: CKS((FN<8, 16>(__VA_ARGS__))); break;                      \
+            case 816: CKS((FN<8, 16>(__VA_ARGS__))); break;                     \
+            default: CKS((FN<4, 16>(__VA_ARGS__))); break;                      \
         }                                                                       \
     } while (0)
 
@@ -752,7 +776,8 @@ int scan2map_impl(lvreg_handle* h, float pose[6], lvreg_result* res) {
     for (int s = 0; s < 2; ++s) {
         args.grid[s] = grid_view(h->map[s]);
         args.map[s] = h->map[s].ds.as<float4>();
-        args.scan[s] = h->scan_ds[s].as<float4>();
+        if (!h->scan_sorted_ok[s]) CKS(sort_scan_for_search(h, s, h->st));
+        args.scan[s] = h->scan_sorted[s].as<float4>();
         args.n[s] = h->n_scan[s];
     }
     args.prm = reg_params(h);
@@ -760,27 +785,32 @@ int scan2map_impl(lvreg_handle* h, float pose[6], lvreg_result* res) {
     args.out = h->regout.as<RegOut>();
     args.lm = h->lmstate.as<LmState>();
 
-    // thread-per-query when every warp scheduler gets >= 2 warps of queries, else lane groups
-    const bool tpq = h->force_tpq > 0 || (h->force_tpq < 0 &&
-                     (h->n_scan[0] + h->n_scan[1]) / 32 >= (uint32_t)h->num_sms * 8);
-    if (tpq != h->reg_occ_is_tpq) h->reg_max_blocks_per_sm = 0;
-    h->reg_occ_is_tpq = tpq;
-    if (h->reg_max_blocks_per_sm == 0 && tpq) {
-        int nb = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, register_tpq_kernel, kRegThreads, 0));
-        if (nb < 1) return fail(h, LVREG_ERR_CUDA, "register_tpq_kernel does not fit on an SM");
-        h->reg_max_blocks_per_sm = nb;
-    }
+    // kernel variant: 2 = staged (shared-memory search, static tiles; the default), 1 = thread per query with the
+    // global-memory search, 0 = lane groups.  LVREG_REG / LVREG_TPQ override the choice (tests, experiments).
+    int variant = 3;
+    if (h->force_tpq >= 0) variant = h->force_tpq;
+    if (h->reg_variant_env >= 0) variant = h->reg_variant_env;
+    if (variant != h->reg_occ_variant) h->reg_max_blocks_per_sm = 0;
+    h->reg_occ_variant = variant;
     if (h->reg_max_blocks_per_sm == 0) {
         int nb = 0;
-        LVREG_REG_DISPATCH(reg_occupancy, h, &nb);
-        if (nb < 1) return fail(h, LVREG_ERR_CUDA, "register_kernel does not fit on an SM");
+        if (variant == 3) {
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, register_warm_kernel, kRegThreads, 0));
+        } else if (variant == 2) {
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, register_staged_kernel, kRegThreads, register_staged_smem_bytes()));
+        } else if (variant == 1) {
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, register_tpq_kernel, kRegThreads, 0));
+        } else {
+            LVREG_REG_DISPATCH(reg_occupancy, h, &nb);
+        }
+        if (nb < 1) return fail(h, LVREG_ERR_CUDA, "the registration kernel does not fit on an SM");
         h->reg_max_blocks_per_sm = nb;
     }
-    const int tile_q = tpq ? 32 : h->tile;
+    const int tile_q = variant == 0 ? h->tile : 32;
     const uint32_t tiles = nblk(h->n_scan[0], tile_q) + nblk(h->n_scan[1], tile_q);
-    int grid = (int)nblk(tiles, kRegWarps);
     const int max_grid = h->reg_max_blocks_per_sm * h->num_sms;
+    // static tiles: tile t runs on block t % grid, so a small scan spreads over all SMs, one tile per warp
+    int grid = variant >= 2 ? (int)tiles : (int)nblk(tiles, kRegWarps);
     if (grid > max_grid) grid = max_grid;
     if (grid < 1) grid = 1;
     CK(h->partials.reserve((size_t)2 * grid * kRegTerms * sizeof(double)));
@@ -795,7 +825,24 @@ int scan2map_impl(lvreg_handle* h, float pose[6], lvreg_result* res) {
         args.tile_ns = h->tilens.as<uint32_t>();
         h->debug_ntiles = tiles;
     }
-    if (tpq) {
+    args.stage_stats = nullptr;
+    args.nn_prev[0] = args.nn_prev[1] = nullptr;
+    if (variant == 3) {
+        for (int s = 0; s < 2; ++s) {
+            CK(h->nnprev[s].reserve((size_t)(h->n_scan[s] ? h->n_scan[s] : 1) * 5 * sizeof(int32_t)));
+            args.nn_prev[s] = h->nnprev[s].as<int32_t>();
+        }
+        void* kargs[] = {&args};
+        CK(cudaLaunchCooperativeKernel((void*)register_warm_kernel, dim3(grid), dim3(kRegThreads), kargs, 0, h->st));
+    } else if (variant == 2) {
+        if (h->debug_tiles) {
+            CK(cudaMemsetAsync(h->stagestats.p, 0, 8 * sizeof(uint32_t), h->st));
+            args.stage_stats = h->stagestats.as<uint32_t>();
+        }
+        void* kargs[] = {&args};
+        CK(cudaLaunchCooperativeKernel((void*)register_staged_kernel, dim3(grid), dim3(kRegThreads), kargs,
+                                       register_staged_smem_bytes(), h->st));
+    } else if (variant == 1) {
         void* kargs[] = {&args};
         CK(cudaLaunchCooperativeKernel((void*)register_tpq_kernel, dim3(grid), dim3(kRegThreads), kargs, 0, h->st));
     } else {
@@ -927,8 +974,19 @@ int lvreg_create(const lvreg_params* p, int device, void* cuda_stream, lvreg_han
     }
     if (h->regout.reserve(sizeof(RegOut)) != cudaSuccess ||
         h->lmstate.reserve(sizeof(LmState)) != cudaSuccess || h->posebuf.reserve(256) != cudaSuccess ||
-        h->tilectr.reserve(LVREG_MAX_ITERS * sizeof(uint32_t)) != cudaSuccess)
+        h->tilectr.reserve(LVREG_MAX_ITERS * sizeof(uint32_t)) != cudaSuccess ||
+        h->stagestats.reserve(8 * sizeof(uint32_t)) != cudaSuccess)
         return bail(LVREG_ERR_CUDA);
+    cudaMemsetAsync(h->stagestats.p, 0, 8 * sizeof(uint32_t), h->st);
+    // the staged registration kernel keeps a 12.5 KB candidate tile per warp
+    if (cudaFuncSetAttribute(register_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)register_staged_smem_bytes()) != cudaSuccess)
+        return bail(LVREG_ERR_CUDA);
+    cudaFuncSetAttribute(register_staged_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    if (cudaFuncSetAttribute(knn5_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)register_staged_smem_bytes()) != cudaSuccess)
+        return bail(LVREG_ERR_CUDA);
+    cudaFuncSetAttribute(knn5_staged_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     cudaMemsetAsync(h->lmstate.p, 0, sizeof(LmState), h->st);
     // the sort pass keeps 42 KB of staging per block: ask for the large shared-memory carveout
     cudaFuncSetAttribute(rs_onesweep_kernel<kSortThreads>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
@@ -944,10 +1002,17 @@ int lvreg_create(const lvreg_params* p, int device, void* cuda_stream, lvreg_han
     if (e) h->debug_tiles = atoi(e);
     e = getenv("LVREG_TPQ");
     if (e) h->force_tpq = atoi(e) ? 1 : 0;
+    e = getenv("LVREG_REG");
+    if (e) {
+        if (!strcmp(e, "staged")) h->reg_variant_env = 2;
+        else if (!strcmp(e, "warm")) h->reg_variant_env = 3;
+        else if (!strcmp(e, "tpq")) h->reg_variant_env = 1;
+        else if (!strcmp(e, "grouped")) h->reg_variant_env = 0;
+    }
     e = getenv("LVREG_TILE");
     if (e) {
         int v = atoi(e);
-        if (v == 8 || v == 16 || v == 32) h->tile = v;
+        if (v == 16) h->tile = v;
     }
     if (cudaStreamSynchronize(h->st) != cudaSuccess) return bail(LVREG_ERR_CUDA);
     *out = h;
@@ -980,6 +1045,7 @@ void lvreg_destroy(lvreg_handle* h) {
     for (int s = 0; s < 2; ++s) {
         h->map[s].ds.release(); h->map[s].cell_pts.release(); h->map[s].cell_start.release();
         h->scan_ds[s].release();
+        h->scan_sorted[s].release();
         h->icp_cloud[s].ds.release(); h->icp_cloud[s].cell_pts.release(); h->icp_cloud[s].cell_start.release();
     }
     h->icp_coarse.cell_pts.release(); h->icp_coarse.cell_start.release();
@@ -998,7 +1064,7 @@ void lvreg_destroy(lvreg_handle* h) {
     DevBuf* bufs[] = {&h->icp_cur, &h->icp_partials, &h->icp_state, &h->icp_idx, &h->icp_d2, &h->feat_pts, &h->feat_range, &h->feat_col, &h->feat_rings, &h->feat_curv, &h->feat_picked,
                       &h->feat_label, &h->feat_flag, &h->feat_ringof, &h->feat_cidx, &h->feat_ccnt, &h->feat_pos,
                       &h->feat_cand, &h->feat_spec, &h->feat_idx, &h->feat_pidx, &h->feat_corner, &h->feat_surf,
-                      &h->vgout, &h->partials, &h->regout, &h->lmstate, &h->posebuf, &h->tilectr, &h->tilens, &h->qbuf,
+                      &h->stagestats, &h->nnprev[0], &h->nnprev[1], &h->vgout, &h->partials, &h->regout, &h->lmstate, &h->posebuf, &h->tilectr, &h->tilens, &h->qbuf,
                       &h->idxbuf, &h->d2buf, &h->brute_partial, &h->coeffbuf, &h->flagbuf};
     for (DevBuf* b : bufs) b->release();
     h->kf_arena.release_all();
@@ -1044,6 +1110,8 @@ int lvreg_reserve(lvreg_handle* h, size_t map_points_corner, size_t map_points_s
         } else {
             CK(L.raw.reserve(n * 16));
             CK(h->scan_ds[l - 2].reserve(n * 16));
+            CK(h->scan_sorted[l - 2].reserve(n * 16));
+            CK(h->nnprev[l - 2].reserve(n * 5 * sizeof(int32_t)));
         }
     }
     CK(cudaStreamSynchronize(h->st));
@@ -1220,6 +1288,7 @@ int lvreg_downsample_scan(lvreg_handle* h, const lvreg_cloud* corner_raw, const 
     lanes_fork(h, 0xc);
     CKS(prepare_scan_jobs(h, corner_raw, surf_raw, jobs));
     CKS(voxelgrid_batch(h, jobs, 2));
+    for (int s = 0; s < 2; ++s) CKS(sort_scan_for_search(h, s, h->lane[LANE_SCAN_CORNER + s].st));
     lanes_join(h, 0xc);
     mark(h, EV_DS);
     CK(cudaStreamSynchronize(h->st));
@@ -1240,6 +1309,7 @@ int lvreg_set_scan_ds(lvreg_handle* h, const lvreg_cloud* corner_ds, const lvreg
     CK(cudaStreamSynchronize(h->st));
     h->n_scan[0] = (uint32_t)corner_ds->n;
     h->n_scan[1] = (uint32_t)surf_ds->n;
+    h->scan_sorted_ok[0] = h->scan_sorted_ok[1] = false;      // ordered by the next lvreg_scan2map
     end_call(h);
     return LVREG_OK;
 }
@@ -1287,6 +1357,8 @@ int lvreg_register_scan(lvreg_handle* h, const lvreg_cloud* corner_raw, const lv
     CKS(prepare_scan_jobs(h, corner_raw, surf_raw, jobs + nj));
     nj += 2;
     CKS(voxelgrid_batch(h, jobs, nj));
+    // the scan lanes finish long before the map lanes: order the queries for the search there
+    for (int s = 0; s < 2; ++s) CKS(sort_scan_for_search(h, s, h->lane[LANE_SCAN_CORNER + s].st));
     lanes_join(h, mask);
     mark(h, EV_MAP);
     if (ids) {
@@ -1453,6 +1525,19 @@ static int knn5_launch(lvreg_handle* h, int which, const float4* q, uint32_t nq,
                                                                    h->brute_partial.as<u64>());
         knn5_brute_merge_kernel<<<qblocks, 256, 0, h->st>>>(h->brute_partial.as<u64>(), nq, splits, d_idx, d_d2);
         launched(h, 2);
+    } else if (variant == LVREG_KNN_GRID_STAGED) {
+        // the search of the registration kernel (shared-memory tiles filled by bulk copies), materialised
+        const GridView g = grid_view(ms);
+        uint32_t blocks = nblk(nq, 32);
+        if (blocks > (uint32_t)h->num_sms * 2) blocks = (uint32_t)h->num_sms * 2;
+        uint32_t* stats = nullptr;
+        if (h->debug_tiles) {
+            CK(cudaMemsetAsync(h->stagestats.p, 0, 8 * sizeof(uint32_t), h->st));
+            stats = h->stagestats.as<uint32_t>();
+        }
+        knn5_staged_kernel<<<blocks, kRegThreads, register_staged_smem_bytes(), h->st>>>(g, q, nq, h->prm.knn_gate_sq, d_idx,
+                                                                                        d_d2, stats);
+        launched(h);
     } else {
         const GridView g = grid_view(ms);
         const int exact = variant == LVREG_KNN_GRID_EXACT ? 1 : 0;
@@ -1471,7 +1556,7 @@ static int knn5_launch(lvreg_handle* h, int which, const float4* q, uint32_t nq,
 }
 
 int lvreg_knn5(lvreg_handle* h, int which, const lvreg_cloud* queries, int variant, int32_t* idx_out, float* d2_out) {
-    if (!h || which < 0 || which > 1 || !queries || variant < 0 || variant > 2) return LVREG_ERR_INVALID;
+    if (!h || which < 0 || which > 1 || !queries || variant < 0 || variant > 3) return LVREG_ERR_INVALID;
     CK(cudaSetDevice(h->device));
     if (!h->map[which].valid) return fail(h, LVREG_ERR_NO_MAP, "no local map");
     begin_call(h);
@@ -1493,7 +1578,7 @@ int lvreg_knn5(lvreg_handle* h, int which, const lvreg_cloud* queries, int varia
 }
 
 int lvreg_bench_knn5(lvreg_handle* h, int which, const lvreg_cloud* queries, int variant, int repeats, float* ms) {
-    if (!h || which < 0 || which > 1 || !queries || repeats < 1 || variant < 0 || variant > 2) return LVREG_ERR_INVALID;
+    if (!h || which < 0 || which > 1 || !queries || repeats < 1 || variant < 0 || variant > 3) return LVREG_ERR_INVALID;
     CK(cudaSetDevice(h->device));
     if (!h->map[which].valid) return fail(h, LVREG_ERR_NO_MAP, "no local map");
     begin_call(h);
@@ -2525,6 +2610,14 @@ int lvreg_debug_tile_times(lvreg_handle* h, uint32_t* ns_out, size_t cap, size_t
     CK(cudaSetDevice(h->device));
     size_t n = *n_tiles < cap ? *n_tiles : cap;
     CK(cudaMemcpyAsync(ns_out, h->tilens.p, n * 4, cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    return LVREG_OK;
+}
+
+int lvreg_debug_stage_stats(lvreg_handle* h, uint32_t out[8]) {
+    if (!h || !out) return LVREG_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpyAsync(out, h->stagestats.p, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->st));
     CK(cudaStreamSynchronize(h->st));
     return LVREG_OK;
 }

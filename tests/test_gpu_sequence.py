@@ -57,9 +57,9 @@ def test_golden_registration(lv):
     h.close()
 
 
-@pytest.mark.parametrize("tpq", ["0", "1"])
-def test_both_registration_kernels_agree_with_oracle(lv, tpq, monkeypatch):
-    monkeypatch.setenv("LVREG_TPQ", tpq)
+@pytest.mark.parametrize("variant", ["grouped", "tpq", "staged", "warm"])
+def test_all_registration_kernels_agree_with_oracle(lv, variant, monkeypatch):
+    monkeypatch.setenv("LVREG_REG", variant)
     z = np.load(os.path.join(G, "registration.npz"))
     h = lv.Lvreg()
     h.set_local_map(z["corner_map"], z["surf_map"])
