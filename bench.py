@@ -1,17 +1,25 @@
 #!/usr/bin/env python
-"""bench.py -- scan-to-map registrations/s on the BASELINE C3 workload (dense 128-beam scans
-against a ~1M-point local map), one process per GPU.
+"""bench.py -- scan-to-map registrations/s (and kNN queries/s) on the BASELINE configurations, one process per GPU.
 
-    python bench.py --gpus 1 --steps 10 --warmup 3            # our arm (CUDA, through the C ABI)
-    python bench.py --impl reference --steps 3 --warmup 1     # CPU arm: the oracle restatement of
-                                                              # the reference's mapOptimization path
+    python bench.py --gpus 1 --steps 10 --warmup 3             # our arm (CUDA, through the C ABI), workload C3
+    python bench.py --impl reference --steps 3 --warmup 1      # CPU arm: the oracle restatement of the
+                                                               # reference's mapOptimization path
+    python bench.py --workload c1|c2|c3|c4|c5 ...              # the other BASELINE configurations
 
-A "step" is the body of laserCloudInfoHandler (MO:318-322) for ONE incoming scan, exactly the work
-the reference does per scan: extractCloud (transform + concatenate the selected keyframes,
-VoxelGrid corner 0.2 / surf 0.4), kd-tree / search-grid build, downsampleCurrentScan, and the
-<=20-iteration scan2MapOptimization loop.  Keyframes are resident (device / host) in both arms, as
-they are in the reference.  e2e = the same call with the scan's feature clouds in pinned HOST
-memory (PCL 32-byte layout): H2D of the clouds and D2H of pose + result are inside the timed region.
+Workloads (BASELINE.json configs 1-5):
+  c3 (default)  dense 128-beam scans against a ~1 M-point local map; a "step" is the body of
+                laserCloudInfoHandler (MO:318-322) for ONE incoming scan, exactly the work the reference does per
+                scan: extractCloud (transform + concatenate the selected keyframes, VoxelGrid corner 0.2 / surf 0.4),
+                kd-tree / search-grid build, downsampleCurrentScan and the <= 20-iteration scan2MapOptimization loop.
+  c1            the same step on a MID360-like scan against a map from 22 keyframes (latency regime).
+  c2            500-scan MID360 sequence through the C++ mapOptimization mirror: keyframe rule MO:1387-1412,
+                extractNearby, local-map rebuild when the selection changes.  A step is one scan of the sequence.
+  c5            64 independent 100-scan sequences partitioned round-robin over the ranks (no collective).
+  c4            kNN micro-benchmark: a step is one launch of the gated grid search at Nq = 1e5, M = 1e6; the
+                whole Nq x M sweep (grid gated / staged / exact / brute, fused residual) goes into "sweep".
+Keyframes are resident (device / host) in both arms, as they are in the reference.  e2e = the same call with the
+scan's feature clouds in pinned HOST memory (PCL 32-byte layout): H2D of the clouds and D2H of pose + result are
+inside the timed region.
 """
 import argparse
 import json
@@ -28,6 +36,34 @@ sys.path.insert(0, ROOT)
 
 SEED = 0x5EED0000
 N_RING_SCANS = 8            # distinct incoming scans cycled through the steps
+METRIC = "scan-to-map registrations/sec"
+
+WORKLOADS = {
+    "c3": "C3: 128-beam 128x2048 scan (~185k returns -> ~71k DS features) vs ~0.97M-point local map rebuilt from 198 "
+          "resident keyframes (~13M points) per scan",
+    "c1": "C1: MID360-like scan (~20k returns -> ~7.7k DS features) vs ~64k-point local map rebuilt from 22 resident "
+          "keyframes per scan",
+    "c2": "C2: 500-scan MID360 sequence replay through the mapOptimization mirror (keyframe rule, extractNearby, "
+          "local-map rebuild on selection change)",
+    "c5": "C5: 64 independent 100-scan MID360 sequences partitioned over the GPUs (multi-agent replay)",
+    "c4": "C4: kNN micro-benchmark, gated grid search Nq=100000 x M=1000000 (sweep attached)",
+}
+L2_NOTE = {
+    "c3": "inputs larger than L2 (keyframe store + concatenated map + sort buffers > 126 MB per step)",
+    "c1": "working set (~10 MB) fits in L2: latency regime, no flush between steps (the reference's kd-tree is cache "
+          "resident too)",
+    "c2": "working set fits in L2: latency regime, no flush between steps",
+    "c5": "working set fits in L2: latency regime, no flush between steps",
+    "c4": "map (16 MB) fits in L2 by design of the search grid; per-query traffic streams",
+}
+
+
+def workload_config(workload, **extra):
+    """the static description of the workload: identical in both arms (the driver compares the dicts)"""
+    cfg = dict(workload=WORKLOADS[workload], seed="0x%X" % SEED, l2=L2_NOTE[workload],
+               parallelism="independent sequences, 1 per GPU, no collective")
+    cfg.update(extra)
+    return cfg
 
 
 def lattice_poses(workload):
@@ -120,6 +156,28 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append(line.strip())
 
+    def mark(self):
+        return len(self.rows)
+
+    def summary(self, first=0):
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows[first:]:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+                pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    power_w_max=max(pw) if pw else None, reasons=sorted(reasons), samples=len(sm))
+
     def stop(self):
         if not self.proc:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
@@ -128,22 +186,7 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            f = [x.strip() for x in r.split(",")]
-            if len(f) < 7:
-                continue
-            try:
-                sm.append(float(f[0]))
-                mx.append(float(f[1]))
-            except ValueError:
-                continue
-            for n, v in zip(names, f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
-                    reasons=sorted(reasons), samples=len(sm))
+        return self.summary()
 
 
 def measured_peaks():
@@ -154,8 +197,32 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def cpu_arm(ds, n_samples, warmup, threads, log):
-    """the oracle (CPU restatement of the reference) on the same workload; returns (reg/s, per-step ms)"""
+def thread_counts(cores):
+    """all host cores (capped at 64), the reference's shipped numberOfCores = 8 (params_lidar.yaml:59), and 1"""
+    out = []
+    for t in (min(cores, 64), min(8, cores), 1):
+        if t not in out:
+            out.append(t)
+    return out
+
+
+def ncu_traffic(name, pairs):
+    """DRAM bytes per launch of the dominant kernel from a committed `ncu --set full` capture, only when it was
+    taken at this launch size; None otherwise (never a number from another workload)"""
+    tp = os.path.join(ROOT, "profiles", name)
+    if os.path.exists(tp):
+        with open(tp) as f:
+            d = json.load(f)
+        if int(d.get("pairs", -1)) == int(pairs):
+            return d.get("dram_bytes_per_launch")
+    return None
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# C1 / C3: one registration per step, local map rebuilt every step
+# ------------------------------------------------------------------------------------------------------------------
+def cpu_registration_arm(ds, n_samples, warmup, threads, log):
+    """the oracle (CPU restatement of the reference) on the same workload"""
     from oracle import pyoracle as O
     mo = O.MapOptimization(O.default_params(num_threads=threads))
     for i in range(len(ds["kf_pose"])):
@@ -172,64 +239,39 @@ def cpu_arm(ds, n_samples, warmup, threads, log):
             times.append(dt)
         poses.append(pose)
         results.append(res)
-        log("cpu step %d: %.3f s, iterations %d" % (i, dt, res.iterations))
-    return ids, times, poses, results
+        log("cpu step %d (%d threads): %.3f s, iterations %d" % (i, threads, dt, res.iterations))
+    return ids, times, poses[warmup:], results[warmup:]
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c3", choices=["c3", "c1"])
-    ap.add_argument("--cpu-samples", type=int, default=3, help="registrations timed for cpu_baseline")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    args = ap.parse_args()
-
-    from lidar_visual_inertial_slam_b200 import multi
-    rank, world, local_rank = multi.rank_info()
-
-    def log(msg):
-        print("[bench rank %d] %s" % (rank, msg), file=sys.stderr, flush=True)
-
-    wl_name = {"c3": "C3: 128-beam 128x2048 scan (~185k returns -> ~68k features) vs ~0.97M-point local map rebuilt "
-                     "from 198 resident keyframes (~13M points) per scan",
-               "c1": "C1: MID360-like scan (~20k returns) vs local map from 22 keyframes"}[args.workload]
+def registration_reference(args, log):
+    from oracle import pyoracle as O
     cores = os.cpu_count() or 1
+    threads = min(cores, 64)
+    ds = make_dataset(args.workload, SEED, lambda p, leaf: O.voxelgrid(p, leaf)[0], log)
+    ids, times, poses, results = cpu_registration_arm(ds, args.steps, args.warmup, threads, log)
+    ms = 1e3 * float(np.sum(times)) / max(1, len(times))
+    val = 1e3 / ms
+    return dict(metric=METRIC, value=val, unit="registrations/s", n_gpus=int(args.gpus),
+                steps=args.steps, warmup=args.warmup, ms_per_step=ms, higher_is_better=True, scaling="weak",
+                vs_baseline=None, dtype="f32", data="synthetic", impl="reference",
+                config=workload_config(args.workload, keyframes=len(ds["kf_pose"])),
+                cpu_baseline=dict(value=val, unit="registrations/s", cores=threads, kind="port",
+                                  sample="%d full registrations (map rebuild + kd-trees + LM loop) of the same workload" % args.steps),
+                e2e=dict(value=val, unit="registrations/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                gpu_launches=0,
+                note="CPU restatement of the reference's mapOptimization path (oracle/): the reference itself "
+                     "needs ROS 2 + PCL + OpenCV C++ + GTSAM and cannot be built here")
 
-    # ------------------------------------------------------------------ reference (CPU) arm
-    if args.impl == "reference":
-        if rank != 0:
-            return 0
-        from oracle import pyoracle as O
-        threads = min(cores, 64)
-        ds = make_dataset(args.workload, SEED, lambda p, leaf: O.voxelgrid(p, leaf)[0], log)
-        ids, times, poses, results = cpu_arm(ds, args.steps, args.warmup, threads, log)
-        ms = 1e3 * float(np.sum(times)) / max(1, len(times))
-        val = 1e3 / ms
-        line = dict(metric="scan-to-map registrations/sec", value=val, unit="registrations/s", n_gpus=int(args.gpus),
-                    steps=args.steps, warmup=args.warmup, ms_per_step=ms, higher_is_better=True, scaling="weak",
-                    vs_baseline=None, dtype="f32", data="synthetic", impl="reference",
-                    config=dict(workload=wl_name, keyframes=len(ds["kf_pose"]), l2="inputs larger than L2"),
-                    cpu_baseline=dict(value=val, unit="registrations/s", cores=threads, kind="port",
-                                      sample="%d full registrations (map rebuild + kd-trees + LM loop) of the same workload" % args.steps),
-                    e2e=dict(value=val, unit="registrations/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
-                    gpu_launches=0,
-                    note="CPU restatement of the reference's mapOptimization path (oracle/): the reference itself "
-                         "needs ROS 2 + PCL + OpenCV C++ + GTSAM and cannot be built here")
-        print(json.dumps(line), flush=True)
-        return 0
 
-    # ------------------------------------------------------------------ our arm (CUDA)
+def registration_ours(args, log):
     import torch
     import lidar_visual_inertial_slam_b200 as lv
-    from lidar_visual_inertial_slam_b200.binding import to_pcl_layout, device_cloud, Cloud
+    from lidar_visual_inertial_slam_b200 import multi
+    from lidar_visual_inertial_slam_b200.binding import to_pcl_layout, device_cloud
 
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    rank, world, local_rank = multi.rank_info()
+    cores = os.cpu_count() or 1
     torch.cuda.set_device(local_rank)
-    use_dist = world > 1
     multi.init(backend="nccl", device=torch.device("cuda", local_rank))     # barrier + timing reduce only
 
     # the library launches on THIS stream (its four lanes fork from / join into it), and the
@@ -241,7 +283,7 @@ def main():
     ds = make_dataset(args.workload, seed, lambda p, leaf: h.voxelgrid(p, leaf)[0], log)
     for i in range(len(ds["kf_pose"])):
         h.add_keyframe(ds["kf_corner"][i], ds["kf_surf"][i], ds["kf_pose"][i])
-    # keyframe selection = extractNearby through the C++ mirror's logic is exercised in the tests;
+    # keyframe selection = extractNearby through the C++ mirror's logic is exercised in the tests and in c2 / c5;
     # here every keyframe is inside the 50 m radius by construction
     ids = np.arange(len(ds["kf_pose"]), dtype=np.int32)
 
@@ -260,9 +302,9 @@ def main():
         ts = torch.from_numpy(s).cuda()
         keep.append((tc, ts))
         dev_scans.append((device_cloud(tc.data_ptr(), len(c)), device_cloud(ts.data_ptr(), len(s))))
-    d2h_bytes = 2344 + 6 * 4 * 0                                        # the RegOut block (pose, per-iteration log, phase stamps)
+    d2h_bytes = 2344                                                    # the RegOut block (pose, per-iteration log, phase stamps)
 
-    def run_steps(n, first, on_device):
+    def run_steps(n, first, on_device, keep_results=True):
         out = []
         for i in range(first, first + n):
             j = i % N_RING_SCANS
@@ -270,17 +312,18 @@ def main():
             pose, res, st = h.register_scan(c, s, ids, ds["guess"][j])
             if st != lv.OK:
                 raise SystemExit("register_scan failed with status %d" % st)
-            out.append((pose, res, h.timings()))
+            if keep_results:
+                out.append((pose, res, h.timings()))
         return out
 
-    def timed(n, first, on_device):
+    def timed(n, first, on_device, keep_results=True):
         multi.barrier()
         torch.cuda.synchronize()
         l0 = h.launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         e0.record()
-        out = run_steps(n, first, on_device)
+        out = run_steps(n, first, on_device, keep_results)
         e1.record()
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
@@ -289,12 +332,20 @@ def main():
         wall_ms, _ = multi.reduce_timing(wall * 1e3, n, device="cuda")
         return ms, wall_ms / 1e3, out, h.launch_count() - l0
 
-    sampler = ClockSampler(local_rank)        # sampled under load: warm-up + both timed regions
+    sampler = ClockSampler(local_rank)        # sampled under load: warm-up + the timed regions
     sampler.start()
     run_steps(args.warmup, 0, True)
     run_steps(args.warmup, 0, False)
     ms_dev, wall_dev, out_dev, launches = timed(args.steps, args.warmup, True)       # inputs resident in HBM
     ms_e2e, wall_e2e, out_e2e, _ = timed(args.steps, args.warmup, False)              # host buffers
+    # sustained leg: >= sustain-seconds of back-to-back steps (resident inputs), clocks sampled over exactly that region
+    sustained = None
+    if args.sustain_seconds > 0:
+        n_sus = max(args.steps, int(np.ceil(args.sustain_seconds * 1e3 / max(1e-3, ms_dev / args.steps))))
+        mark = sampler.mark()
+        ms_sus, wall_sus, _, _ = timed(n_sus, args.warmup, True, keep_results=False)
+        sustained = dict(value=n_sus * world / (ms_sus * 1e-3), unit="registrations/s", steps=n_sus, seconds=ms_sus * 1e-3,
+                         ms_per_step=ms_sus / n_sus, clocks=sampler.summary(mark))
     clocks = sampler.stop()
 
     # per-stage device time (CUDA events recorded by the library on the launching stream)
@@ -306,26 +357,24 @@ def main():
     mm = res0.n_corner_map + res0.n_surf_map
     hbm_peak, peak_src = measured_peaks()
 
-    def _traffic(name):
-        tp = os.path.join(ROOT, "profiles", name)
-        if os.path.exists(tp):
-            with open(tp) as f:
-                return json.load(f).get("dram_bytes_per_launch")
-        return None
-
     # dominant kernel by share of the (serialised) launch list: rs_onesweep_kernel, one radix-sort pass
-    # of the VoxelGrid replacement (profiles/r01_launches_bench_c3_final_summary.txt).  Inside a step
+    # of the VoxelGrid replacement (profiles/r02_launches_bench_c3_summary.txt).  Inside a step
     # the four lanes overlap, so one pass cannot be bracketed there; it is timed live, alone, on the
     # same stream with the library's CUDA events, at the size of the surf-map sort of this workload.
     # Algorithmic bytes per launch (pass) = 16 B per pair (8 read + 8 written).
     n_sort = int(sum(len(b) for b in ds["kf_surf"]))
+    n_in = int(sum(len(a) + len(b) for a, b in zip(ds["kf_corner"], ds["kf_surf"])))
     sort_ms, sort_passes = h.bench_sort(n_sort, 28, 5)
     pass_ms = sort_ms / sort_passes                     # includes 1/passes of the one histogram kernel
     sort_bytes = 16.0 * n_sort
     sort_gbs = sort_bytes / (pass_ms * 1e-3) / 1e9
-    # second: register_tpq_kernel, ONE cooperative launch per registration (the whole LM loop); its
-    # duration is the library's event pair around the launch inside the timed steps.  Algorithmic
-    # bytes per launch: iterations x (96 B/query + 16 B/map point) + 108 B out.
+    # the whole local-map stage against SURVEY 8d's numerator: 16 B per concatenated keyframe point read + 16 B per
+    # down-sampled map point written, over the stage's device time inside the timed steps (includes the scan lanes)
+    stage_bytes = 16.0 * (n_in + mm)
+    stage_gbs = stage_bytes / (stage["map_build_ms"] * 1e-3) / 1e9 if stage["map_build_ms"] > 0 else 0.0
+    # registration kernel: ONE cooperative launch per registration (the whole LM loop); its duration is the library's
+    # event pair around the launch inside the timed steps.  Algorithmic bytes per launch:
+    # iterations x (96 B/query + 16 B/map point) + 108 B out.
     reg_bytes = float(np.mean([it * (96.0 * nq + 16.0 * mm) + 108.0 for it in iters]))
     reg_s = stage["register_ms"] * 1e-3
     achieved = reg_bytes / reg_s / 1e9 if reg_s > 0 else 0.0
@@ -334,13 +383,12 @@ def main():
     value = n_total_steps / (ms_dev * 1e-3)
     e2e = n_total_steps / (ms_e2e * 1e-3)
 
-    line = dict(metric="scan-to-map registrations/sec", value=value, unit="registrations/s", n_gpus=world,
+    line = dict(metric=METRIC, value=value, unit="registrations/s", n_gpus=world,
                 steps=args.steps, warmup=args.warmup, ms_per_step=ms_dev / args.steps, higher_is_better=True,
                 scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
-                config=dict(workload=wl_name, keyframes=len(ids), queries_per_scan=nq, map_points=mm,
-                            keyframe_points_per_rebuild=int(sum(len(a) + len(b) for a, b in zip(ds["kf_corner"], ds["kf_surf"]))),
-                            lm_iterations_mean=float(np.mean(iters)), parallelism="independent sequences, 1 per GPU, no collective",
-                            l2="inputs larger than L2 (keyframe store + concatenated map + sort buffers > 126 MB per step)"),
+                config=workload_config(args.workload, keyframes=len(ids)),
+                workload_stats=dict(queries_per_scan=nq, map_points=mm, keyframe_points_per_rebuild=n_in,
+                                    lm_iterations_mean=float(np.mean(iters))),
                 e2e=dict(value=e2e, unit="registrations/s", h2d_bytes_per_step=int(np.mean(h2d_bytes)), d2h_bytes_per_step=d2h_bytes,
                          ms_per_step=ms_e2e / args.steps),
                 gpu_launches=int(launches),
@@ -348,28 +396,40 @@ def main():
                 stages_ms=stage,
                 roofline=dict(kernel="rs_onesweep_kernel (one 8-bit radix-sort pass over %d pairs)" % n_sort, bound="hbm",
                               achieved=sort_gbs, peak=hbm_peak, unit="GB/s", frac=sort_gbs / hbm_peak,
-                              traffic=_traffic("r01_sort_kernel_traffic.json"), peak_source=peak_src,
+                              traffic=ncu_traffic("r02_sort_kernel_traffic.json", n_sort), peak_source=peak_src,
                               algorithmic_bytes_per_launch=sort_bytes, launch_ms=pass_ms, passes_per_sort=sort_passes,
                               how="timed alone with CUDA events on the launching stream (the lanes overlap inside a step)"),
-                roofline_register=dict(kernel="register_tpq_kernel (one cooperative launch = the whole LM loop)", bound="hbm",
+                roofline_map_build_stage=dict(what="transform + concatenate + VoxelGrid of the local map (all launches of the "
+                                                   "stage, scan lanes included)", bound="hbm", achieved=stage_gbs, peak=hbm_peak,
+                                              unit="GB/s", frac=stage_gbs / hbm_peak, algorithmic_bytes=stage_bytes,
+                                              stage_ms=stage["map_build_ms"]),
+                roofline_register=dict(kernel="register_warm_kernel (one cooperative launch = the whole LM loop)", bound="hbm",
                                        achieved=achieved, peak=hbm_peak, unit="GB/s", frac=achieved / hbm_peak,
-                                       traffic=_traffic("r01_register_kernel_traffic.json"),
+                                       traffic=ncu_traffic("r02_register_kernel_traffic.json", nq),
                                        algorithmic_bytes_per_launch=reg_bytes, launch_ms=stage["register_ms"],
                                        note="issue/latency-bound, the map stays L2-resident: a few % of HBM peak by construction"),
                 clocks=clocks, wall_s=dict(resident=wall_dev, e2e=wall_e2e))
+    if sustained:
+        line["sustained"] = sustained
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        threads = min(cores, 64)
-        _, times, cposes, cres = cpu_arm(ds, args.cpu_samples, 1, threads, log)
-        cms = 1e3 * float(np.mean(times))
+        by_threads = {}
+        first = None
+        for threads in thread_counts(cores):
+            _, times, cposes, cres = cpu_registration_arm(ds, args.cpu_samples, 1, threads, log)
+            cms = 1e3 * float(np.mean(times))
+            by_threads[str(threads)] = dict(value=1e3 / cms, seconds_per_registration=cms / 1e3)
+            if first is None:
+                first = (threads, cms, len(times), cposes, cres)
+        threads, cms, nsamp, cposes, cres = first
         line["cpu_baseline"] = dict(value=1e3 / cms, unit="registrations/s", cores=threads, kind="port",
-                                    sample="%d full registrations of the same workload (1 warm-up), %.2f s each" % (len(times), cms / 1e3))
-        # parity of the timed GPU results against the oracle on the same inputs
+                                    sample="%d full registrations of the same workload (1 warm-up), %.2f s each" % (nsamp, cms / 1e3),
+                                    by_threads=by_threads)
+        # parity of the timed GPU results against the oracle on the same inputs (sample k = ring scan k)
         perr = rerr = 0.0
         same_iters = True
-        # compare scan j of the ring: GPU step index with the same scan
         for k, (cp, cr) in enumerate(zip(cposes, cres)):
-            j = k % N_RING_SCANS
+            j = (k + 1) % N_RING_SCANS                 # the CPU arm ran one warm-up step first
             for (gp, gr, _), i in zip(out_dev, range(args.warmup, args.warmup + args.steps)):
                 if i % N_RING_SCANS == j:
                     rerr = max(rerr, float(np.abs(gp[:3] - cp[:3]).max()))
@@ -377,12 +437,260 @@ def main():
                     same_iters = same_iters and gr.iterations == cr.iterations
                     break
         line["parity_vs_oracle"] = dict(max_pos_err_m=perr, max_rot_err_rad=rerr, same_iteration_counts=bool(same_iters))
+    h.close()
+    return line
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# C2 / C5: sequence replay through the C++ mapOptimization mirror
+# ------------------------------------------------------------------------------------------------------------------
+def replay_shape(workload):
+    return (1, 500) if workload == "c2" else (64, 100)       # (sequences, scans per sequence)
+
+
+def cpu_replay(seed, n_scans, threads, log, period=0.2):
+    """the oracle doing the per-scan flow of laserCloudInfoHandler (MO:316-326) on one MID360 sequence:
+    extractNearby, local-map rebuild when the selection changed, registration, saveFrame"""
+    from oracle import pyoracle as O
+    from lidar_visual_inertial_slam_b200 import harness as H
+    gen = H.Generator(H.MID360, seed)
+    scans = []
+    for k in range(n_scans):
+        truth = gen.truth_pose(k, period, 1.0)
+        c, s = gen.scan(truth, seed + 1000003 * k, 8)
+        scans.append((truth, gen.guess_pose(k, truth, 0.10, 0.035) if k else truth, c, s))
+    mo = O.MapOptimization(O.default_params(num_threads=threads))
+    last_ids, kf_pose, kf_time, registered = None, None, None, 0
+    t0 = time.perf_counter()
+    for k, (truth, guess, c, s) in enumerate(scans):
+        t = k * period
+        if mo.num_keyframes() > 0:
+            ids = mo.extract_nearby(t)
+            if last_ids is None or not np.array_equal(ids, last_ids):
+                mo.build_local_map(ids)
+                last_ids = ids
+        pose, res, nc, ns = mo.register_scan(c, s, guess)
+        if res.status == 0:
+            registered += 1
+        # saveFrame (MO:1387-1412): Livox -> a keyframe every > 1.0 s, or > 1 m / 0.2 rad of motion
+        add = kf_pose is None or t - kf_time > 1.0 or np.abs(pose[:3] - kf_pose[:3]).max() >= 0.2 or \
+            np.linalg.norm(pose[3:] - kf_pose[3:]) >= 1.0
+        if add:
+            mo.add_keyframe(O.voxelgrid(c, 0.2)[0], O.voxelgrid(s, 0.4)[0], pose, t)
+            kf_pose, kf_time = pose.copy(), t
+    dt = time.perf_counter() - t0
+    log("cpu replay (%d threads): %d scans, %d registered, %.2f s" % (threads, n_scans, registered, dt))
+    return registered, dt
+
+
+def replay_reference(args, log):
+    cores = os.cpu_count() or 1
+    threads = min(cores, 64)
+    n_seq, n_scans = replay_shape(args.workload)
+    n_sample = min(n_scans, 120)
+    reg, dt = cpu_replay(SEED, n_sample, threads, log)
+    val = reg / dt
+    return dict(metric=METRIC, value=val, unit="registrations/s", n_gpus=int(args.gpus), steps=reg, warmup=0,
+                ms_per_step=1e3 * dt / max(1, reg), higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+                data="synthetic", impl="reference", config=workload_config(args.workload, sequences=n_seq, scans_per_sequence=n_scans),
+                cpu_baseline=dict(value=val, unit="registrations/s", cores=threads, kind="port",
+                                  sample="the first %d scans of sequence 0 (per-scan flow of MO:316-326)" % n_sample),
+                e2e=dict(value=val, unit="registrations/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0,
+                note="CPU restatement of the reference's mapOptimization path (oracle/), one sequence on one process")
+
+
+def replay_ours(args, log):
+    import torch
+    from lidar_visual_inertial_slam_b200 import harness as H
+    from lidar_visual_inertial_slam_b200 import multi
+    rank, world, local_rank = multi.rank_info()
+    cores = os.cpu_count() or 1
+    torch.cuda.set_device(local_rank)
+    multi.init(backend="nccl", device=torch.device("cuda", local_rank))
+    n_seq, n_scans = replay_shape(args.workload)
+    mine = multi.partition_sequences(n_seq, rank, world)
+    mo = H.ReplayMirror(H.MID360, device=local_rank)
+    gen_threads = max(1, min(8, cores // max(1, world)))
+    mo.replay(SEED + 7777, 8, gen_threads=gen_threads)                    # untimed warm-up: context, lazy loading
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    multi.barrier()
+    torch.cuda.synchronize()
+    tot = dict(registered=0.0, wall_s=0.0, device_ms=0.0, launches=0.0, iterations=0.0, queries=0.0, keyframes=0.0,
+               converged=0.0, max_pos_err=0.0, max_rot_err=0.0)
+    for q in mine:                                                          # generation is outside the harness' clock
+        r = mo.replay(multi.sequence_seed(SEED, q), n_scans, gen_threads=gen_threads)
+        for k in ("registered", "wall_s", "device_ms", "launches", "iterations", "queries", "keyframes", "converged"):
+            tot[k] += r[k]
+        tot["max_pos_err"] = max(tot["max_pos_err"], r["max_pos_err"])
+        tot["max_rot_err"] = max(tot["max_rot_err"], r["max_rot_err"])
+    torch.cuda.synchronize()
+    multi.barrier()
+    clocks = sampler.stop()
+    # whole job: registrations of all ranks over the slowest rank's replay time (host wall clock around the replay
+    # loops: every scan comes from pinned host memory and the pose goes back to the host, i.e. this IS end to end)
+    wall_ms, regs = multi.reduce_timing(tot["wall_s"] * 1e3, tot["registered"], device="cuda")
+    dev_ms, _ = multi.reduce_timing(tot["device_ms"], tot["registered"], device="cuda")
+    _, launches = multi.reduce_timing(0.0, tot["launches"], device="cuda")
+    e2e = regs / (wall_ms * 1e-3)
+    value = regs / (dev_ms * 1e-3) if dev_ms > 0 else e2e
+    scan_bytes = 20000 * 32                                                  # ~20k feature points x 32 B (PCL layout)
+    line = dict(metric=METRIC, value=value, unit="registrations/s", n_gpus=world, steps=int(tot["registered"]), warmup=8,
+                ms_per_step=dev_ms / max(1.0, tot["registered"]), higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="f32", data="synthetic",
+                config=workload_config(args.workload, sequences=n_seq, scans_per_sequence=n_scans),
+                workload_stats=dict(registrations=int(regs), keyframes_rank0=int(tot["keyframes"]),
+                                    lm_iterations_mean=tot["iterations"] / max(1.0, tot["registered"]),
+                                    converged_rank0=int(tot["converged"]), max_pos_err_vs_truth_m=tot["max_pos_err"],
+                                    max_rot_err_vs_truth_rad=tot["max_rot_err"],
+                                    device_share_of_wall=dev_ms / wall_ms if wall_ms > 0 else None),
+                e2e=dict(value=e2e, unit="registrations/s", h2d_bytes_per_step=scan_bytes, d2h_bytes_per_step=2344,
+                         ms_per_step=wall_ms / max(1.0, tot["registered"]),
+                         how="host wall clock of the replay loops, slowest rank; scans in pinned host memory"),
+                value_how="registrations over the summed device time of their library calls (CUDA events), slowest rank",
+                gpu_launches=int(launches), clocks=clocks,
+                roofline=dict(kernel="whole step (latency regime: ~10 MB working set, launch- and latency-bound)", bound="hbm",
+                              achieved=None, peak=measured_peaks()[0], unit="GB/s", frac=None, traffic=None))
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        by_threads = {}
+        first = None
+        for threads in thread_counts(cores):
+            reg, dt = cpu_replay(SEED, min(n_scans, 120), threads, log)
+            by_threads[str(threads)] = dict(value=reg / dt)
+            if first is None:
+                first = (threads, reg, dt)
+        line["cpu_baseline"] = dict(value=first[1] / first[2], unit="registrations/s", cores=first[0], kind="port",
+                                    sample="the first %d scans of sequence 0, %.2f s" % (min(n_scans, 120), first[2]),
+                                    by_threads=by_threads)
+    mo.close()
+    return line
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# C4: kNN micro-benchmark
+# ------------------------------------------------------------------------------------------------------------------
+def knn_reference(args, log):
+    from oracle import pyoracle as O
+    from benchmarks import knn_sweep as K
+    cores = os.cpu_count() or 1
+    threads = min(cores, 64)
+    rng = np.random.default_rng(4)
+    mp, side = K.make_map(rng, 1000000)
+    q = K.make_queries(rng, mp, side, 100000)
+    tree = O.KdTree(mp)
+    times = []
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        tree.knn(q, 5, num_threads=threads)
+        if i >= args.warmup:
+            times.append(time.perf_counter() - t0)
+    ms = 1e3 * float(np.mean(times))
+    val = len(q) / (ms * 1e-3)
+    return dict(metric="kNN queries/sec", value=val, unit="queries/s", n_gpus=int(args.gpus), steps=args.steps,
+                warmup=args.warmup, ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+                data="synthetic", impl="reference", config=workload_config("c4"),
+                cpu_baseline=dict(value=val, unit="queries/s", cores=threads, kind="port",
+                                  sample="%d x 1e5 exact 5-NN queries on the oracle's kd-tree (tree build excluded)" % args.steps),
+                e2e=dict(value=val, unit="queries/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+
+
+def knn_ours(args, log):
+    import lidar_visual_inertial_slam_b200 as lv
+    from lidar_visual_inertial_slam_b200 import multi
+    from benchmarks import knn_sweep as K
+    import torch
+    rank, world, local_rank = multi.rank_info()
+    torch.cuda.set_device(local_rank)
+    multi.init(backend="nccl", device=torch.device("cuda", local_rank))
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    sweep = K.run_sweep(device=local_rank, quick=args.quick, log=log)
+    hbm_peak, peak_src = measured_peaks()
+    head = [r for r in sweep["rows"] if r["M"] == 1000000 and r["Nq"] == 100000]
+    g = [r for r in head if r["variant"] == "grid_gated"][0]
+    # end to end: host queries in, host indices + distances out (lvreg_knn5)
+    h = lv.Lvreg(device=local_rank)
+    rng = np.random.default_rng(4)
+    mp, side = K.make_map(rng, 1000000)
+    q = K.make_queries(rng, mp, side, 100000)
+    h.set_local_map(mp[:16], mp)
+    for _ in range(3):
+        h.knn5(lv.SURF, q, lv.KNN_GRID_GATED)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        h.knn5(lv.SURF, q, lv.KNN_GRID_GATED)
+    e2e_ms = 1e3 * (time.perf_counter() - t0) / args.steps
+    h.close()
+    clocks = sampler.stop()
+    ms, _ = multi.reduce_timing(g["ms"], 1, device="cuda")
+    line = dict(metric="kNN queries/sec", value=world * 100000 / (ms * 1e-3), unit="queries/s", n_gpus=world, steps=10,
+                warmup=3, ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                config=workload_config("c4"),
+                e2e=dict(value=world * 100000 / (e2e_ms * 1e-3), unit="queries/s", h2d_bytes_per_step=100000 * 16,
+                         d2h_bytes_per_step=100000 * 40, ms_per_step=e2e_ms),
+                gpu_launches=10, clocks=clocks,
+                roofline=dict(kernel="knn5_grid_kernel<8> gated, Nq=1e5, M=1e6", bound="hbm", achieved=g["algorithmic_gbs"],
+                              peak=hbm_peak, unit="GB/s", frac=g["algorithmic_gbs"] / hbm_peak, peak_source=peak_src,
+                              traffic=ncu_traffic("r02_knn_grid_traffic.json", 100000),
+                              note="algorithmic bytes = 56 B per query (query in, 5 indices + 5 distances out); the candidate "
+                                   "cells are L2-resident by design and are reported from ncu, not counted here"),
+                sweep=sweep["rows"])
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import pyoracle as O
+        tree = O.KdTree(mp)
+        cores = os.cpu_count() or 1
+        by_threads = {}
+        for threads in thread_counts(cores):
+            tree.knn(q[:20000], 5, num_threads=threads)
+            t0 = time.perf_counter()
+            tree.knn(q, 5, num_threads=threads)
+            dt = time.perf_counter() - t0
+            by_threads[str(threads)] = dict(value=len(q) / dt)
+        t_all = str(thread_counts(cores)[0])
+        line["cpu_baseline"] = dict(value=by_threads[t_all]["value"], unit="queries/s", cores=int(t_all), kind="port",
+                                    sample="1e5 exact 5-NN queries on the oracle's kd-tree of the 1e6-point map (build excluded)",
+                                    by_threads=by_threads)
+    return line
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c3", choices=["c1", "c2", "c3", "c4", "c5"])
+    ap.add_argument("--cpu-samples", type=int, default=3, help="registrations timed per thread count for cpu_baseline")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sustain-seconds", type=float, default=2.0, help="length of the sustained leg (0 = skip)")
+    ap.add_argument("--quick", action="store_true", help="c4: reduced sweep")
+    args = ap.parse_args()
+
+    from lidar_visual_inertial_slam_b200 import multi
+    rank, world, local_rank = multi.rank_info()
+
+    def log(msg):
+        print("[bench rank %d] %s" % (rank, msg), file=sys.stderr, flush=True)
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        fn = {"c1": registration_reference, "c3": registration_reference, "c2": replay_reference, "c5": replay_reference,
+              "c4": knn_reference}[args.workload]
+        print(json.dumps(fn(args, log)), flush=True)
+        return 0
+
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    fn = {"c1": registration_ours, "c3": registration_ours, "c2": replay_ours, "c5": replay_ours, "c4": knn_ours}[args.workload]
+    line = fn(args, log)
     if rank == 0:
         print(json.dumps(line), flush=True)
-    h.close()
-    if use_dist:
+    if world > 1:
         import torch.distributed as dist
-        dist.destroy_process_group()
+        if dist.is_initialized():
+            dist.destroy_process_group()
     return 0
 
 

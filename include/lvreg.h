@@ -136,6 +136,10 @@ int         lvreg_version(void);
 /* page-locked host memory for callers that want full-speed uploads */
 void*       lvreg_host_alloc(size_t bytes);
 void        lvreg_host_free(void* p);
+/* page-lock / unlock memory the caller already owns (e.g. the points of a pcl::PointCloud): uploads from it are
+ * then asynchronous DMA transfers instead of staged copies */
+int         lvreg_host_register(void* p, size_t bytes);
+int         lvreg_host_unregister(void* p);
 
 /* ---- keyframe store: cornerCloudKeyFrames / surfCloudKeyFrames / cloudKeyPoses6D (MO:83-87) -- */
 /* saveKeyFramesAndFactor's push_back of the DS feature clouds + pose (MO:1600-1610). */

@@ -749,6 +749,16 @@ int reg_occupancy(lvreg_handle* h, int* nb) {
         }                                                                       \
     } while (0)
 
+// kernel variant: 3 = warm (thread per query, warm-started search radius, static dealt tiles; the default),
+// 2 = staged (shared-memory search), 1 = thread per query with dynamic tiles, 0 = lane groups.
+// LVREG_REG / LVREG_TPQ override the choice (tests, experiments).
+int reg_variant(const lvreg_handle* h) {
+    int variant = 3;
+    if (h->force_tpq >= 0) variant = h->force_tpq;
+    if (h->reg_variant_env >= 0) variant = h->reg_variant_env;
+    return variant;
+}
+
 int scan2map_impl(lvreg_handle* h, float pose[6], lvreg_result* res) {
     if (res) {
         memset(res, 0, sizeof(*res));
@@ -776,20 +786,21 @@ int scan2map_impl(lvreg_handle* h, float pose[6], lvreg_result* res) {
     for (int s = 0; s < 2; ++s) {
         args.grid[s] = grid_view(h->map[s]);
         args.map[s] = h->map[s].ds.as<float4>();
-        if (!h->scan_sorted_ok[s]) CKS(sort_scan_for_search(h, s, h->st));
-        args.scan[s] = h->scan_sorted[s].as<float4>();
+        args.scan[s] = h->scan_ds[s].as<float4>();
         args.n[s] = h->n_scan[s];
     }
+    args.dealt = getenv("LVREG_DEALT") ? 1 : 0;
+    if (reg_variant(h) >= 2 && !args.dealt)     // spatially compact tiles: similar paths, shared cache lines
+        for (int s = 0; s < 2; ++s) {
+            if (!h->scan_sorted_ok[s]) CKS(sort_scan_for_search(h, s, h->st));
+            args.scan[s] = h->scan_sorted[s].as<float4>();
+        }
     args.prm = reg_params(h);
     args.pose_in = h->posebuf.as<float>();
     args.out = h->regout.as<RegOut>();
     args.lm = h->lmstate.as<LmState>();
 
-    // kernel variant: 2 = staged (shared-memory search, static tiles; the default), 1 = thread per query with the
-    // global-memory search, 0 = lane groups.  LVREG_REG / LVREG_TPQ override the choice (tests, experiments).
-    int variant = 3;
-    if (h->force_tpq >= 0) variant = h->force_tpq;
-    if (h->reg_variant_env >= 0) variant = h->reg_variant_env;
+    const int variant = reg_variant(h);
     if (variant != h->reg_occ_variant) h->reg_max_blocks_per_sm = 0;
     h->reg_occ_variant = variant;
     if (h->reg_max_blocks_per_sm == 0) {
@@ -829,7 +840,7 @@ int scan2map_impl(lvreg_handle* h, float pose[6], lvreg_result* res) {
     args.nn_prev[0] = args.nn_prev[1] = nullptr;
     if (variant == 3) {
         for (int s = 0; s < 2; ++s) {
-            CK(h->nnprev[s].reserve((size_t)(h->n_scan[s] ? h->n_scan[s] : 1) * 5 * sizeof(int32_t)));
+            CK(h->nnprev[s].reserve((size_t)(nblk(h->n_scan[s], 32) + 1) * 32 * 5 * sizeof(int32_t)));
             args.nn_prev[s] = h->nnprev[s].as<int32_t>();
         }
         void* kargs[] = {&args};
@@ -931,6 +942,15 @@ void* lvreg_host_alloc(size_t bytes) {
 }
 void lvreg_host_free(void* p) {
     if (p) cudaFreeHost(p);
+}
+
+int lvreg_host_register(void* p, size_t bytes) {
+    if (!p || !bytes) return LVREG_ERR_INVALID;
+    return cudaHostRegister(p, bytes, cudaHostRegisterDefault) == cudaSuccess ? LVREG_OK : LVREG_ERR_CUDA;
+}
+int lvreg_host_unregister(void* p) {
+    if (!p) return LVREG_ERR_INVALID;
+    return cudaHostUnregister(p) == cudaSuccess ? LVREG_OK : LVREG_ERR_CUDA;
 }
 
 int lvreg_create(const lvreg_params* p, int device, void* cuda_stream, lvreg_handle** out) {
@@ -1111,7 +1131,7 @@ int lvreg_reserve(lvreg_handle* h, size_t map_points_corner, size_t map_points_s
             CK(L.raw.reserve(n * 16));
             CK(h->scan_ds[l - 2].reserve(n * 16));
             CK(h->scan_sorted[l - 2].reserve(n * 16));
-            CK(h->nnprev[l - 2].reserve(n * 5 * sizeof(int32_t)));
+            CK(h->nnprev[l - 2].reserve((n / 32 + 2) * 32 * 5 * sizeof(int32_t)));
         }
     }
     CK(cudaStreamSynchronize(h->st));
@@ -1288,7 +1308,9 @@ int lvreg_downsample_scan(lvreg_handle* h, const lvreg_cloud* corner_raw, const 
     lanes_fork(h, 0xc);
     CKS(prepare_scan_jobs(h, corner_raw, surf_raw, jobs));
     CKS(voxelgrid_batch(h, jobs, 2));
-    for (int s = 0; s < 2; ++s) CKS(sort_scan_for_search(h, s, h->lane[LANE_SCAN_CORNER + s].st));
+    h->scan_sorted_ok[0] = h->scan_sorted_ok[1] = false;
+    if (reg_variant(h) >= 2)
+        for (int s = 0; s < 2; ++s) CKS(sort_scan_for_search(h, s, h->lane[LANE_SCAN_CORNER + s].st));
     lanes_join(h, 0xc);
     mark(h, EV_DS);
     CK(cudaStreamSynchronize(h->st));
@@ -1357,8 +1379,10 @@ int lvreg_register_scan(lvreg_handle* h, const lvreg_cloud* corner_raw, const lv
     CKS(prepare_scan_jobs(h, corner_raw, surf_raw, jobs + nj));
     nj += 2;
     CKS(voxelgrid_batch(h, jobs, nj));
-    // the scan lanes finish long before the map lanes: order the queries for the search there
-    for (int s = 0; s < 2; ++s) CKS(sort_scan_for_search(h, s, h->lane[LANE_SCAN_CORNER + s].st));
+    // staged variant: the scan lanes finish long before the map lanes, order the queries for the search there
+    h->scan_sorted_ok[0] = h->scan_sorted_ok[1] = false;
+    if (reg_variant(h) >= 2)
+        for (int s = 0; s < 2; ++s) CKS(sort_scan_for_search(h, s, h->lane[LANE_SCAN_CORNER + s].st));
     lanes_join(h, mask);
     mark(h, EV_MAP);
     if (ids) {
@@ -1736,15 +1760,23 @@ int lvreg_extract_features(lvreg_handle* h, const lvreg_cloud* deskewed, const l
     CK(h->feat_corner.reserve((size_t)ns * kFeCornerStride * 16));
     if (n == 0) return LVREG_OK;
     // shared-memory budget of the per-ring kernel from the ring / sector lengths
+    // A ring is processed when end - start >= 1 (cloudExtraction, imageProjection.cpp:617-640, writes
+    // start = first + 4, end = last - 5: a ring of fewer than 11 points has end < start and is skipped).  A processed
+    // ring indexes [start - 5, end + 4] clipped to the cloud, its sectors [start, end]: both ends must lie inside the
+    // cloud, and processed rings must be disjoint and ascending (each block owns its ring's labels and flags).
     int cap = 16, max_sector = 1;
+    long long prev_end = -1;
     for (int r = 0; r < ns; ++r) {
-        const int a = info->start_ring_index[r], b = info->end_ring_index[r];
-        if (a < -1000000 || b > (int)n + 1000000) return fail(h, LVREG_ERR_INVALID, "ring index out of range");
-        int lo = a - 5, hi = b + 4;
+        const long long a = info->start_ring_index[r], b = info->end_ring_index[r];
+        if (b - a < 1) continue;
+        if (a < 0 || b > (long long)n - 1) return fail(h, LVREG_ERR_INVALID, "ring index out of range");
+        if (a <= prev_end) return fail(h, LVREG_ERR_INVALID, "rings overlap or are not ascending");
+        prev_end = b;
+        long long lo = a - 5, hi = b + 4;
         if (lo < 0) lo = 0;
-        if (hi > (int)n - 1) hi = (int)n - 1;
-        if (hi - lo + 1 > cap) cap = hi - lo + 1;
-        if ((b - a) / 6 + 2 > max_sector) max_sector = (b - a) / 6 + 2;
+        if (hi > (long long)n - 1) hi = (long long)n - 1;
+        if (hi - lo + 1 > cap) cap = (int)(hi - lo + 1);
+        if ((b - a) / 6 + 2 > max_sector) max_sector = (int)((b - a) / 6 + 2);
     }
     int sort_cap = 2;
     while (sort_cap < max_sector) sort_cap <<= 1;

@@ -54,6 +54,7 @@ struct RegArgs {
     double* partials;                    // [2][gridDim.x][kRegTerms]
     uint32_t* tile_counter;              // [LVREG max iters] zeroed by the host before the launch
     uint32_t* tile_ns;                   // optional diagnostics: duration of every tile in iteration 1 (ns)
+    int dealt;                           // register_warm_kernel: deal the queries out over the tiles (experiment)
     int32_t* nn_prev[2];                 // register_warm_kernel: the 5 neighbours of the previous iteration, [5][n]
     uint32_t* stage_stats;               // optional diagnostics of register_staged_kernel: tiles staged whole / as
                                          // halves / as quarters, lanes on the global-memory search, barrier time-outs

@@ -8,11 +8,18 @@
 //     the top-5 insertion -- the divergent part of the scan (ncu: a quarter of all issued instructions at 7
 //     active lanes).  The candidate set is a superset of the true 5-NN (ties at the radius included, the
 //     (d2, index) key order decides as before), so neighbours, coefficients and poses do not change.
-//   * STATIC TILES.  Tile t runs on block t % gridDim, warp t / gridDim, every iteration; warps add their tiles
-//     in tile order, blocks their warps in warp order, the grid its blocks in block order.  The fp64 sums of
-//     MO:1257-1259 therefore have one fixed order: results are bit-reproducible run to run.
+//   * STATIC TILES.  Tile t runs on block t % gridDim, warp t / gridDim, every iteration; warps add their
+//     tiles in tile order, blocks their warps in warp order, the grid its blocks in block order.  The fp64 sums
+//     of MO:1257-1259 therefore have one fixed order: results are bit-reproducible run to run.  A tile is 32
+//     consecutive queries of the Morton-ordered scan (neighbours in space: similar paths through the search,
+//     shared cache lines).  Dealing the queries out instead (lane l of tile t takes query l * tiles + t, every
+//     tile a uniform sample of the scan; RegArgs::dealt) balances the tiles perfectly but every tile then
+//     costs as much as the slowest one did: measured 0.46 ms against 0.42 ms per C3 registration.
 //   The row loop is rolled (one copy of the scan + insertion code instead of nine) to keep the hot loop inside
-//   the instruction cache.
+//   the instruction cache, and a candidate batch is tested against the radius in fp32 before any 64-bit key is
+//   formed.  Tried and dropped (measured on C3, results unchanged): draining the insertions of a whole row in
+//   warp-aligned rounds from per-lane shared-memory stacks (0.444 ms against 0.425 ms: the stack traffic and
+//   the extra warp reduction per row cost what the aligned insertions save).
 #pragma once
 
 #include <cooperative_groups.h>
@@ -129,33 +136,33 @@ __global__ void __launch_bounds__(kRegThreads, 2) register_warm_kernel(RegArgs a
         for (uint32_t tile = first_tile; tile < tiles; tile += tile_stride) {
             const unsigned long long tile_t0 = (a.tile_ns && iter == 1) ? gtimer() : 0ull;
             const int cls = tile < tiles_c ? 0 : 1;
-            const uint32_t base = (cls == 0 ? tile : tile - tiles_c) * TILE;
-            const uint32_t qi = base + lane;
-            const uint32_t ncls = a.n[cls];
-            const bool valid = qi < ncls;
+            const uint32_t tl = cls == 0 ? tile : tile - tiles_c, tcls = cls == 0 ? tiles_c : tiles_s;
+            const uint32_t qi = a.dealt ? (uint32_t)lane * tcls + tl : tl * TILE + lane;
+            const uint32_t ncls = tcls * TILE;                        // slots of the neighbour cache
+            const bool valid = qi < a.n[cls];
             const float4* __restrict__ map = a.map[cls];
-            int32_t* __restrict__ nnp = a.nn_prev[cls];              // [5][n], coalesced
+            int32_t* __restrict__ nnp = a.nn_prev[cls] + (size_t)tl * TILE + lane - qi;   // [5][tiles * 32], tile-major
             float4 ori = valid ? __ldg(a.scan[cls] + qi) : make_float4(0.f, 0.f, 0.f, 0.f);
             const float3 sel = apply_affine(T, ori.x, ori.y, ori.z);
             float row[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             bool ok = false;
-            if (valid) {
-                // search radius: the previous iteration's 5 neighbours bound the new 5th distance
-                float tau_le = gate_le;
-                if (iter > 0) {
-                    int pn[5];
+            // search radius: the previous iteration's 5 neighbours bound the new 5th distance
+            float tau_le = gate_le;
+            if (valid && iter > 0) {
+                int pn[5];
 #pragma unroll
-                    for (int i = 0; i < 5; ++i) pn[i] = nnp[(size_t)i * ncls + qi];
-                    if (pn[4] >= 0) {
-                        float dm = 0.f;
+                for (int i = 0; i < 5; ++i) pn[i] = nnp[(size_t)i * ncls + qi];
+                if (pn[4] >= 0) {
+                    float dm = 0.f;
 #pragma unroll
-                        for (int i = 0; i < 5; ++i) {
-                            const float4 p = __ldg(map + pn[i]);
-                            dm = fmaxf(dm, sqdist(sel.x, sel.y, sel.z, p.x, p.y, p.z));
-                        }
-                        tau_le = fminf(tau_le, dm);
+                    for (int i = 0; i < 5; ++i) {
+                        const float4 p = __ldg(map + pn[i]);
+                        dm = fmaxf(dm, sqdist(sel.x, sel.y, sel.z, p.x, p.y, p.z));
                     }
+                    tau_le = fminf(tau_le, dm);
                 }
+            }
+            if (valid) {
                 u64 best[5];
                 thread_knn5_radius(a.grid[cls], sel.x, sel.y, sel.z, tau_le, best);
                 int nn[5];

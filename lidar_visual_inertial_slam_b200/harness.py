@@ -152,6 +152,48 @@ class MapOptimizationMirror:
             pass
 
 
+class ReplayMirror:
+    """one long-lived C++ mapOptimization mirror with pre-sized device buffers; sequences are replayed on it one
+    after the other (reset in between), as lvreg_replay does per GPU"""
+    KEYS = ["scans", "registered", "keyframes", "converged", "iterations", "queries", "wall_s", "device_ms",
+            "max_pos_err", "max_rot_err", "launches"]
+
+    def __init__(self, sensor, device=0):
+        self.L = lib()
+        self.sensor = sensor
+        if sensor == BEAM128:
+            rv = (3000000, 12000000, 65536, 400000, 1 << 25)
+        else:
+            rv = (200000, 800000, 20000, 60000, 1 << 22)
+        arr = (C.c_size_t * 5)(*rv)
+        self.L.lvh_mo_create_reserved.restype = C.c_void_p
+        self.L.lvh_mo_create_reserved.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        self.L.lvh_replay_on.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_int, C.c_double, C.c_double, C.c_float,
+                                         C.c_float, C.c_int, C.c_void_p]
+        self.mo = C.c_void_p(self.L.lvh_mo_create_reserved(None, device, arr))
+        if not self.mo:
+            raise RuntimeError(self.L.lvh_last_error().decode())
+
+    def replay(self, seed, n_scans, period=0.2, speed=1.0, guess_trans=0.10, guess_rot=0.035, gen_threads=8):
+        out = (C.c_double * 11)()
+        st = self.L.lvh_replay_on(self.mo, self.sensor, C.c_uint64(seed), n_scans, C.c_double(period), C.c_double(speed),
+                                  C.c_float(guess_trans), C.c_float(guess_rot), gen_threads, out)
+        if st != 0:
+            raise RuntimeError(self.L.lvh_last_error().decode())
+        return dict(zip(self.KEYS, list(out)))
+
+    def close(self):
+        if self.mo:
+            self.L.lvh_mo_destroy(self.mo)
+            self.mo = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def replay(sensor, seed, n_scans, device=0, period=0.2, speed=1.0, guess_trans=0.10, guess_rot=0.035, gen_threads=8):
     out = (C.c_double * 10)()
     L = lib()

@@ -65,6 +65,22 @@ void* lvh_mo_create(const lvreg_params* p, int device) {
         return nullptr;
     }
 }
+// the same with capacity hints {map corner, map surf, scan corner, scan surf points, grid cells}: every per-call
+// device buffer is sized up front (lvreg_reserve), so that no call of a timed replay allocates
+void* lvh_mo_create_reserved(const lvreg_params* p, int device, const size_t reserve[5]) {
+    try {
+        ParamServer ps;
+        if (p) ps.lv = *p;
+        if (reserve) {
+            ps.reserveMapCorner = reserve[0]; ps.reserveMapSurf = reserve[1]; ps.reserveScanCorner = reserve[2];
+            ps.reserveScanSurf = reserve[3]; ps.reserveGridCells = reserve[4];
+        }
+        return new mapOptimization(ps, device);
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return nullptr;
+    }
+}
 void lvh_mo_destroy(void* mo) { delete (mapOptimization*)mo; }
 
 // laserCloudInfoHandler for one scan (packed rows).  Returns the lvreg status of scan2map, or -1
@@ -165,6 +181,22 @@ int lvh_replay(int sensor, uint64_t seed, int n_scans, double period, double spe
         out[0] = st.scans; out[1] = st.registered; out[2] = st.keyframes; out[3] = st.converged;
         out[4] = (double)st.iterations; out[5] = (double)st.queries; out[6] = st.wall_s; out[7] = st.device_ms;
         out[8] = st.max_pos_err; out[9] = st.max_rot_err;
+        return 0;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return -2;
+    }
+}
+
+// replay of one sequence on an existing mirror (reset() first): what lvreg_replay does per sequence and GPU
+int lvh_replay_on(void* mo, int sensor, uint64_t seed, int n_scans, double period, double speed, float gt, float gr,
+                  int gen_threads, double* out /*11 doubles*/) {
+    try {
+        SequenceSpec s{sensor, seed, n_scans, period, speed, gt, gr};
+        ReplayStats st = replay_sequence(s, 0, gen_threads, (mapOptimization*)mo);
+        out[0] = st.scans; out[1] = st.registered; out[2] = st.keyframes; out[3] = st.converged;
+        out[4] = (double)st.iterations; out[5] = (double)st.queries; out[6] = st.wall_s; out[7] = st.device_ms;
+        out[8] = st.max_pos_err; out[9] = st.max_rot_err; out[10] = (double)st.launches;
         return 0;
     } catch (const std::exception& e) {
         g_err = e.what();

@@ -409,10 +409,30 @@ Cloud mapOptimization::getLaserCloudFromMapDS(int which) {
     return c;
 }
 
+mapOptimization::PinnedCloud::~PinnedCloud() {
+    if (p) lvreg_host_free(p);
+}
+void mapOptimization::PinnedCloud::assign(const Cloud& c) {
+    if (c.size() > cap) {
+        if (p) lvreg_host_free(p);
+        cap = c.size() + c.size() / 2 + 1024;
+        p = (PointType*)lvreg_host_alloc(cap * sizeof(PointType));
+        if (!p) { cap = 0; throw std::runtime_error("lvreg_host_alloc failed"); }
+    }
+    n = c.size();
+    if (n) std::memcpy(p, c.data(), n * sizeof(PointType));
+}
+
 bool mapOptimization::laserCloudInfoHandler(const Cloud& corner, const Cloud& surf, double stamp, const float* guess) {
     timeLaserInfoCur = stamp;
-    laserCloudCornerLast = corner;
-    laserCloudSurfLast = surf;
+    const bool fused = fusedHandler && !cloudKeyPoses3D.empty();
+    if (fused) {                          // the one copy of the message (pcl::fromROSMsg, MO:305-307) lands in pinned memory
+        pinCorner_.assign(corner);
+        pinSurf_.assign(surf);
+    } else {
+        laserCloudCornerLast = corner;
+        laserCloudSurfLast = surf;
+    }
     if (!(timeLaserInfoCur - timeLastProcessing_ >= P_.mappingProcessInterval)) return false;   // MO:311-314
     timeLastProcessing_ = timeLaserInfoCur;
     std::memset(&lastTimings, 0, sizeof(lastTimings));
@@ -429,7 +449,10 @@ bool mapOptimization::laserCloudInfoHandler(const Cloud& corner, const Cloud& su
     // down-sampling run concurrently on the device and share their host synchronisations
     std::vector<int32_t> ids = extractNearby();
     const bool rebuild = mapDirty_ || ids != lastIds_;
-    lvreg_cloud c = as_lvreg_cloud(laserCloudCornerLast), s = as_lvreg_cloud(laserCloudSurfLast);
+    lvreg_cloud c, s;
+    c.data = pinCorner_.p; c.n = pinCorner_.n; c.stride = sizeof(PointType); c.intensity_offset = 16; c.on_device = 0; c.reserved = 0;
+    s = c;
+    s.data = pinSurf_.p; s.n = pinSurf_.n;
     lastStatus = lvreg_register_scan(h_, &c, &s, rebuild ? ids.data() : nullptr, ids.size(), transformTobeMapped, &lastResult);
     if (lastStatus != LVREG_OK && lastStatus != LVREG_ERR_NOT_ENOUGH_FEATURES)
         throw std::runtime_error(std::string("lvreg_register_scan: ") + lvreg_last_error(h_));

@@ -123,6 +123,15 @@ class mapOptimization {
     std::vector<int32_t> extractNearby();
 
   private:
+    // page-locked landing buffers of the incoming feature clouds: pcl::fromROSMsg (MO:305-307) copies the message
+    // into laserCloud*Last anyway; copying into pinned memory instead makes the upload an asynchronous DMA transfer
+    struct PinnedCloud {
+        PointType* p = nullptr;
+        size_t cap = 0, n = 0;
+        ~PinnedCloud();
+        void assign(const Cloud& c);
+    };
+    PinnedCloud pinCorner_, pinSurf_;
     ParamServer P_;
     lvreg_handle* h_ = nullptr;
     std::vector<int32_t> lastIds_;

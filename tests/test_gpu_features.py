@@ -89,3 +89,27 @@ def test_features_feed_registration_on_device(lv):
         assert res.iterations == rres.iterations
         assert np.abs(pose[:3] - rpose[:3]).max() <= 1e-5 and np.abs(pose[3:] - rpose[3:]).max() <= 1e-4
     h.close()
+
+
+def test_extract_features_rejects_malformed_ring_indices(lv):
+    """start / end ring indices come from the caller (CloudInfo): a processed ring must lie inside the cloud and
+    the rings must be disjoint and ascending; anything else is LVREG_ERR_INVALID, not device memory corruption"""
+    rng = np.random.default_rng(6)
+    pts, rg, col, sr, er = ring_scan(rng, 4, 400)
+    h = lv.Lvreg()
+    ref = h.extract_features(pts, rg, col, sr, er)
+    bad = []
+    s2 = sr.copy(); s2[0] = -3; bad.append((s2, er))                        # start before the cloud
+    e2 = er.copy(); e2[-1] = len(pts) + 7; bad.append((sr, e2))             # end past the cloud
+    s3 = sr.copy(); s3[2] = sr[1]; bad.append((s3, er))                     # ring 2 overlaps ring 1
+    s4, e4 = sr[::-1].copy(), er[::-1].copy(); bad.append((s4, e4))         # descending rings
+    s5 = sr.copy(); s5[1] = -(2 ** 31) + 2; bad.append((s5, er))            # overflow bait
+    for s_, e_ in bad:
+        with pytest.raises(lv.LvregError) as ei:
+            h.extract_features(pts, rg, col, s_, e_)
+        assert ei.value.status == lv.ERR_INVALID
+    # the handle is still usable and gives the same answer
+    again = h.extract_features(pts, rg, col, sr, er)
+    for a, b in zip(ref, again):
+        assert np.array_equal(a, b)
+    h.close()
