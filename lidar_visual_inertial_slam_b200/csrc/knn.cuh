@@ -478,10 +478,14 @@ struct GridSpec {
     int dx, dy, dz;
 };
 
-__global__ void __launch_bounds__(256) cell_keys_kernel(const float4* __restrict__ pts, uint32_t m,
-                                                        GridSpec gs, uint32_t* __restrict__ keys,
-                                                        uint32_t* __restrict__ vals,
-                                                        uint32_t* __restrict__ counts) {
+// Counting-sort build of the search grid: the atomic that counts a cell's points also hands every point its rank
+// inside the cell, so the points can be scattered to cell_start[cell] + rank right after the scan of the counts:
+// two passes over the map and one scan instead of a radix sort by cell key.  The order of the points INSIDE a
+// cell is the arrival order of the atomics; the search keeps the 5 smallest (d2, index) keys, which do not depend
+// on the order in which a cell's points are visited, so results are unaffected.
+__global__ void __launch_bounds__(256) cell_count_kernel(const float4* __restrict__ pts, uint32_t m, GridSpec gs,
+                                                         uint32_t* __restrict__ keys, uint32_t* __restrict__ ranks,
+                                                         uint32_t* __restrict__ counts) {
     uint32_t i = blockIdx.x * 256 + threadIdx.x;
     if (i >= m) return;
     float4 p = pts[i];
@@ -491,8 +495,18 @@ __global__ void __launch_bounds__(256) cell_keys_kernel(const float4* __restrict
     int cz = cell_coord(p.z, gs.oz, gs.inv, gs.dz, &u);
     uint32_t key = ((uint32_t)cz * gs.dy + cy) * gs.dx + cx;
     keys[i] = key;
-    vals[i] = i;
-    atomicAdd(&counts[key], 1u);
+    ranks[i] = atomicAdd(&counts[key], 1u);
+}
+
+__global__ void __launch_bounds__(256) cell_scatter_kernel(const float4* __restrict__ pts,
+                                                           const uint32_t* __restrict__ keys,
+                                                           const uint32_t* __restrict__ ranks,
+                                                           const uint32_t* __restrict__ cell_start, uint32_t m,
+                                                           float4* __restrict__ out) {
+    uint32_t i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= m) return;
+    float4 p = pts[i];
+    out[__ldg(cell_start + keys[i]) + ranks[i]] = make_float4(p.x, p.y, p.z, __uint_as_float(i));
 }
 
 struct CountIn {
@@ -515,15 +529,5 @@ struct StartOut {
         *reinterpret_cast<uint4*>(s + i + 4) = b;
     }
 };
-
-__global__ void __launch_bounds__(256) cell_gather_kernel(const float4* __restrict__ pts,
-                                                          const uint32_t* __restrict__ sorted_vals,
-                                                          uint32_t m, float4* __restrict__ out) {
-    uint32_t j = blockIdx.x * 256 + threadIdx.x;
-    if (j >= m) return;
-    uint32_t i = sorted_vals[j];
-    float4 p = __ldg(pts + i);
-    out[j] = make_float4(p.x, p.y, p.z, __uint_as_float(i));
-}
 
 }  // namespace lvreg

@@ -563,17 +563,15 @@ int build_grid(lvreg_handle* h, Lane& L, MapSide& ms, const float* bb_min, const
     CK(ms.cell_start.reserve((size_t)(ncells + 9) * 4));
     CK(ms.cell_pts.reserve((size_t)m * 16));
     CK(L.scan_temp.reserve((size_t)(scan_num_tiles(ncells + 1) + 2) * 4));
+    // counting sort by cell: count (the atomic also ranks the point inside its cell), scan, scatter
     CK(cudaMemsetAsync(L.scan_in.p, 0, (size_t)(ncells + 1) * 4, L.st));
-    cell_keys_kernel<<<nblk(m, 256), 256, 0, L.st>>>(pts, m, gs, L.keys[0].as<uint32_t>(),
-                                                     L.vals[0].as<uint32_t>(), L.scan_in.as<uint32_t>());
+    cell_count_kernel<<<nblk(m, 256), 256, 0, L.st>>>(pts, m, gs, L.keys[0].as<uint32_t>(), L.vals[0].as<uint32_t>(),
+                                                      L.scan_in.as<uint32_t>());
     launched(h);
     exclusive_scan(CountIn{L.scan_in.as<uint32_t>()}, StartOut{ms.cell_start.as<uint32_t>()}, ncells + 1,
                    L.scan_temp.as<uint32_t>(), L.small.as<uint32_t>() + SM_TOTAL, L.st, &h->call_launches);
-    int cur = radix_sort_pairs(L.keys[0].as<uint32_t>(), L.vals[0].as<uint32_t>(), L.keys[1].as<uint32_t>(),
-                               L.vals[1].as<uint32_t>(), m, bits_for(ncells - 1), L.sort_scratch.as<uint32_t>(),
-                               L.st, &h->call_launches);
-    cell_gather_kernel<<<nblk(m, 256), 256, 0, L.st>>>(pts, L.vals[cur].as<uint32_t>(), m,
-                                                       ms.cell_pts.as<float4>());
+    cell_scatter_kernel<<<nblk(m, 256), 256, 0, L.st>>>(pts, L.keys[0].as<uint32_t>(), L.vals[0].as<uint32_t>(),
+                                                        ms.cell_start.as<uint32_t>(), m, ms.cell_pts.as<float4>());
     launched(h);
     CK(cudaGetLastError());
     ms.gs = gs;
@@ -749,7 +747,16 @@ int reg_occupancy(lvreg_handle* h, int* nb) {
         }                                                                       \
     } while (0)
 
-// kernel variant: 3 = warm (thread per query, warm-started search radius, static dealt tiles; the default),
+// Morton-ordering the queries pays when there are several tiles per SM to balance (C3: 2200 tiles); on a small
+// scan its ~16 extra launches cost more than the ordering returns (C1: 240 tiles, launch-bound).  The staged
+// search always needs compact tiles.
+int reg_variant(const lvreg_handle* h);
+bool want_sorted_scan(const lvreg_handle* h, int variant) {
+    if (variant == 2) return true;
+    return variant == 3 && h->n_scan[0] + h->n_scan[1] >= 32768u;
+}
+
+// kernel variant: 3 = warm (thread per query, warm-started search radius, static tiles; the default),
 // 2 = staged (shared-memory search), 1 = thread per query with dynamic tiles, 0 = lane groups.
 // LVREG_REG / LVREG_TPQ override the choice (tests, experiments).
 int reg_variant(const lvreg_handle* h) {
@@ -790,7 +797,7 @@ int scan2map_impl(lvreg_handle* h, float pose[6], lvreg_result* res) {
         args.n[s] = h->n_scan[s];
     }
     args.dealt = getenv("LVREG_DEALT") ? 1 : 0;
-    if (reg_variant(h) >= 2 && !args.dealt)     // spatially compact tiles: similar paths, shared cache lines
+    if (want_sorted_scan(h, reg_variant(h)) && !args.dealt)     // spatially compact tiles: similar paths, shared cache lines
         for (int s = 0; s < 2; ++s) {
             if (!h->scan_sorted_ok[s]) CKS(sort_scan_for_search(h, s, h->st));
             args.scan[s] = h->scan_sorted[s].as<float4>();
@@ -1309,7 +1316,7 @@ int lvreg_downsample_scan(lvreg_handle* h, const lvreg_cloud* corner_raw, const 
     CKS(prepare_scan_jobs(h, corner_raw, surf_raw, jobs));
     CKS(voxelgrid_batch(h, jobs, 2));
     h->scan_sorted_ok[0] = h->scan_sorted_ok[1] = false;
-    if (reg_variant(h) >= 2)
+    if (want_sorted_scan(h, reg_variant(h)))
         for (int s = 0; s < 2; ++s) CKS(sort_scan_for_search(h, s, h->lane[LANE_SCAN_CORNER + s].st));
     lanes_join(h, 0xc);
     mark(h, EV_DS);
@@ -1381,7 +1388,7 @@ int lvreg_register_scan(lvreg_handle* h, const lvreg_cloud* corner_raw, const lv
     CKS(voxelgrid_batch(h, jobs, nj));
     // staged variant: the scan lanes finish long before the map lanes, order the queries for the search there
     h->scan_sorted_ok[0] = h->scan_sorted_ok[1] = false;
-    if (reg_variant(h) >= 2)
+    if (want_sorted_scan(h, reg_variant(h)))
         for (int s = 0; s < 2; ++s) CKS(sort_scan_for_search(h, s, h->lane[LANE_SCAN_CORNER + s].st));
     lanes_join(h, mask);
     mark(h, EV_MAP);
