@@ -553,6 +553,7 @@ __device__ inline bool clearly_well_conditioned(const float* AtA, float threshol
 struct LmState {            // isDegenerate (MO:131) and matP (MO:132) persist across scans
     int is_degenerate;
     float matP[36];
+    int last_path;          // diagnostics: how iteration 0 decided degeneracy (1 = Cholesky shortcut, 2 = 6x6 Jacobi)
 };
 
 // LMOptimization from the solve onward (MO:1260-1311).  AtA/Atb are the fp32 normal equations.
@@ -567,7 +568,9 @@ __device__ inline bool lm_solve(const float* AtA, const float* Atb, int iter, fl
         // every eigenvalue is provably above the threshold: cv::eigen would report the same
         // (isDegenerate = false, matP unused), so the 6x6 Jacobi sweep is skipped
         st->is_degenerate = 0;
+        st->last_path = 1;
     } else if (iter == 0) {
+        st->last_path = 2;
         float A[36], E[6], V[36], V2[36];
         for (int i = 0; i < 36; ++i) A[i] = AtA[i];
         jacobi_eigen<6>(A, E, V);

@@ -5,7 +5,9 @@
 // Structure (built once per local map):
 //   cell_pts[m]        float4 {x, y, z, bits(original index)} sorted by cell key (x fastest), so
 //                      the 3 x-adjacent cells of a row are ONE contiguous, coalesced float4 run
-//   cell_start[nc+1]   exclusive prefix of the per-cell counts (dense array)
+//   cell_start[nc+1]   exclusive prefix of the per-cell counts: a DENSE directory while it is small next to
+//                      the map (cells <= max(2^24, 16 M)), else an open-addressing HASH of the occupied cells
+//                      (memory proportional to the map; a sparse map spread over kilometres keeps the 1 m cell)
 //   cell edge          gate radius * (1 + 1/128): any point closer than the gate (sqrt(1.0 m^2),
 //                      MO:1025/1121) lies in the 3x3x3 block around the query's cell, with margin
 //                      for the fp32 rounding of the cell coordinate (dims are capped at 2048/axis)
@@ -30,7 +32,10 @@ constexpr u64 kKeyNone = 0xffffffffffffffffull;
 
 struct GridView {
     const float4* pts;           // cell-sorted points, w = original index bits
-    const uint32_t* cell_start;  // ncells + 1
+    const uint32_t* cell_start;  // dense: ncells + 1 prefix; hashed: hmask + 2 prefix over the table slots
+    const unsigned long long* hkeys;   // hashed: linear cell id of every table slot (kHashEmpty = free)
+    uint32_t hmask;              // hashed: table size - 1 (power of two)
+    int hashed;                  // 0 = dense cell directory, 1 = open-addressing hash of the occupied cells
     float ox, oy, oz;            // grid origin (bbox min of the map)
     float inv;                   // 1 / cell
     float cell;
@@ -105,6 +110,99 @@ __device__ __forceinline__ void scan_range_le(const GridView& g, uint32_t s, uin
     }
 }
 
+// ---- hashed directory ------------------------------------------------------------------------------
+constexpr unsigned long long kHashEmpty = 0xffffffffffffffffull;
+__host__ __device__ __forceinline__ uint32_t cell_hash(unsigned long long k) {
+    k ^= k >> 33;
+    k *= 0xff51afd7ed558ccdull;
+    k ^= k >> 29;
+    return (uint32_t)k;
+}
+// points of cell (x, y, z): [*s, *e) in g.pts; false when the cell is empty
+__device__ __forceinline__ bool hash_cell_range(const GridView& g, int x, int y, int z, uint32_t* s, uint32_t* e) {
+    const unsigned long long key = ((unsigned long long)z * (unsigned long long)g.dy + (unsigned long long)y) *
+                                   (unsigned long long)g.dx + (unsigned long long)x;
+    uint32_t slot = cell_hash(key) & g.hmask;
+    for (;;) {
+        const unsigned long long k = __ldg(g.hkeys + slot);
+        if (k == key) {
+            *s = __ldg(g.cell_start + slot);
+            *e = __ldg(g.cell_start + slot + 1);
+            return true;
+        }
+        if (k == kHashEmpty) return false;
+        slot = (slot + 1) & g.hmask;
+    }
+}
+
+// The search over a hashed directory (maps whose dense directory would dwarf them).  Same semantics as
+// group_knn5 / group_knn5_gated: Chebyshev shells of cells around the query's cell, one hash probe per cell,
+// until the 5th neighbour is provably inside the searched cube (exact) or after the 3x3x3 block (gated).
+template <int LPQ>
+__device__ __noinline__ void group_knn5_hashed(const GridView& g, float qx, float qy, float qz, int gl, unsigned gmask,
+                                               bool exact, float gate_sq, u64* best_out) {
+    u64 t[5] = {kKeyNone, kKeyNone, kKeyNone, kKeyNone, kKeyNone};
+    u64 best[5] = {kKeyNone, kKeyNone, kKeyNone, kKeyNone, kKeyNone};
+    float ux, uy, uz;
+    const int cx = cell_coord(qx, g.ox, g.inv, g.dx, &ux);
+    const int cy = cell_coord(qy, g.oy, g.inv, g.dy, &uy);
+    const int cz = cell_coord(qz, g.oz, g.inv, g.dz, &uz);
+    const float skip = exact ? __int_as_float(0x7f800000) : gate_sq;
+    const bool far = !exact && (ux < -1.f || uy < -1.f || uz < -1.f || ux > (float)g.dx + 1.f ||
+                                uy > (float)g.dy + 1.f || uz > (float)g.dz + 1.f);
+    const float sl_x = 0.002f + 4e-7f * fabsf(ux), sl_y = 0.002f + 4e-7f * fabsf(uy), sl_z = 0.002f + 4e-7f * fabsf(uz);
+    for (int rr = 1; !far; ++rr) {
+        // shell rr: the cells at Chebyshev distance rr (rr == 1: the whole 3x3x3 block)
+        for (int dzz = -rr; dzz <= rr; ++dzz) {
+            const int zz = cz + dzz;
+            if (zz < 0 || zz >= g.dz) continue;
+            for (int dyy = -rr; dyy <= rr; ++dyy) {
+                const int yy = cy + dyy;
+                if (yy < 0 || yy >= g.dy) continue;
+                const bool full = rr == 1 || dzz == -rr || dzz == rr || dyy == -rr || dyy == rr;
+                const int step = full ? 1 : 2 * rr;
+                for (int xx = cx - rr; xx <= cx + rr; xx += step) {
+                    if (xx < 0 || xx >= g.dx) continue;
+                    uint32_t s, e;
+                    if (hash_cell_range(g, xx, yy, zz, &s, &e)) scan_range<LPQ>(g, s, e, gl, qx, qy, qz, skip, t);
+                }
+            }
+        }
+        group_merge<LPQ>(gmask, t, best);
+        if (!exact) break;
+        const int r = rr;          // cells within Chebyshev distance r are done: same stopping rule as group_knn5
+        float bound = 3.0e38f;
+        bool open = false;
+        if (cx - r > 0)        { bound = fminf(bound, ux - (float)(cx - r) - sl_x); open = true; }
+        if (cx + r < g.dx - 1) { bound = fminf(bound, (float)(cx + r + 1) - ux - sl_x); open = true; }
+        if (cy - r > 0)        { bound = fminf(bound, uy - (float)(cy - r) - sl_y); open = true; }
+        if (cy + r < g.dy - 1) { bound = fminf(bound, (float)(cy + r + 1) - uy - sl_y); open = true; }
+        if (cz - r > 0)        { bound = fminf(bound, uz - (float)(cz - r) - sl_z); open = true; }
+        if (cz + r < g.dz - 1) { bound = fminf(bound, (float)(cz + r + 1) - uz - sl_z); open = true; }
+        if (!open) break;
+        if (best[4] != kKeyNone && bound > 0.f) {
+            const float bm = bound * g.cell;
+            if (key_d2(best[4]) <= bm * bm * 0.9999f) break;
+        }
+        if (r >= 16) {             // far from any structure: finish with an exhaustive scan (still exact)
+#pragma unroll
+            for (int i = 0; i < 5; ++i) t[i] = kKeyNone;
+            scan_range<LPQ>(g, 0, g.m, gl, qx, qy, qz, skip, t);
+            group_merge<LPQ>(gmask, t, best);
+            break;
+        }
+#pragma unroll
+        for (int i = 0; i < 5; ++i) t[i] = gl == 0 ? best[i] : kKeyNone;
+    }
+    if (!exact) {
+#pragma unroll
+        for (int i = 0; i < 5; ++i)
+            if (best[i] != kKeyNone && !(key_d2(best[i]) < gate_sq)) best[i] = kKeyNone;
+    }
+#pragma unroll
+    for (int i = 0; i < 5; ++i) best_out[i] = best[i];
+}
+
 // GATED search with geometric pruning.  The centre row (3 x-cells) is scanned first and merged;
 // its 5th distance (or the gate) becomes tau.  A remaining row / x-cell is visited only when its
 // lower-bound distance to the query (gap to the cell slab, minus a rounding slack) does not
@@ -118,6 +216,13 @@ __device__ __forceinline__ void group_knn5_gated(const GridView& g, float qx, fl
     const int cy = cell_coord(qy, g.oy, g.inv, g.dy, &uy);
     const int cz = cell_coord(qz, g.oz, g.inv, g.dz, &uz);
     const int lane_base = (threadIdx.x & 31) - gl;
+    if (g.hashed) {                 // its address escapes into the out-of-line search; `best` stays in registers
+        u64 hb[5];
+        group_knn5_hashed<LPQ>(g, qx, qy, qz, gl, gmask, false, gate_sq, hb);
+#pragma unroll
+        for (int i = 0; i < 5; ++i) best[i] = hb[i];
+        return;
+    }
 #pragma unroll
     for (int i = 0; i < 5; ++i) best[i] = kKeyNone;
     const bool far = ux < -1.f || uy < -1.f || uz < -1.f || ux > (float)g.dx + 1.f ||
@@ -211,6 +316,13 @@ __device__ __forceinline__ void thread_scan(const GridView& g, uint32_t s, uint3
 
 __device__ __forceinline__ void thread_knn5_gated(const GridView& g, float qx, float qy, float qz,
                                                   float gate_sq, u64 (&t)[5]) {
+    if (g.hashed) {
+        u64 hb[5];
+        group_knn5_hashed<1>(g, qx, qy, qz, 0, 1u << (threadIdx.x & 31), false, gate_sq, hb);
+#pragma unroll
+        for (int i = 0; i < 5; ++i) t[i] = hb[i];
+        return;
+    }
 #pragma unroll
     for (int i = 0; i < 5; ++i) t[i] = kKeyNone;
     float ux, uy, uz;
@@ -271,6 +383,13 @@ __device__ __forceinline__ void group_knn5(const GridView& g, float qx, float qy
     const int cz = cell_coord(qz, g.oz, g.inv, g.dz, &uz);
     const float skip = exact ? __int_as_float(0x7f800000) : gate_sq;
     const int lane_base = (threadIdx.x & 31) - gl;
+    if (g.hashed) {
+        u64 hb[5];
+        group_knn5_hashed<LPQ>(g, qx, qy, qz, gl, gmask, exact, gate_sq, hb);
+#pragma unroll
+        for (int i = 0; i < 5; ++i) best[i] = hb[i];
+        return;
+    }
 
     if (!exact) {
         // a query more than one cell outside the grid has nothing within the gate
@@ -496,6 +615,30 @@ __global__ void __launch_bounds__(256) cell_count_kernel(const float4* __restric
     uint32_t key = ((uint32_t)cz * gs.dy + cy) * gs.dx + cx;
     keys[i] = key;
     ranks[i] = atomicAdd(&counts[key], 1u);
+}
+
+// the same count + rank step over a hashed directory: the cell's slot is found (or claimed) by linear probing
+__global__ void __launch_bounds__(256) hash_count_kernel(const float4* __restrict__ pts, uint32_t m, GridSpec gs,
+                                                         unsigned long long* __restrict__ hkeys, uint32_t hmask,
+                                                         uint32_t* __restrict__ slots, uint32_t* __restrict__ ranks,
+                                                         uint32_t* __restrict__ counts) {
+    uint32_t i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= m) return;
+    float4 p = pts[i];
+    float u;
+    const int cx = cell_coord(p.x, gs.ox, gs.inv, gs.dx, &u);
+    const int cy = cell_coord(p.y, gs.oy, gs.inv, gs.dy, &u);
+    const int cz = cell_coord(p.z, gs.oz, gs.inv, gs.dz, &u);
+    const unsigned long long key = ((unsigned long long)cz * (unsigned long long)gs.dy + (unsigned long long)cy) *
+                                   (unsigned long long)gs.dx + (unsigned long long)cx;
+    uint32_t slot = cell_hash(key) & hmask;
+    for (;;) {
+        const unsigned long long prev = atomicCAS(hkeys + slot, kHashEmpty, key);
+        if (prev == kHashEmpty || prev == key) break;
+        slot = (slot + 1) & hmask;
+    }
+    slots[i] = slot;
+    ranks[i] = atomicAdd(&counts[slot], 1u);
 }
 
 __global__ void __launch_bounds__(256) cell_scatter_kernel(const float4* __restrict__ pts,

@@ -117,7 +117,9 @@ struct DepthEntry {            // one entry of cloudQueue / timeQueue (feature_t
 
 struct MapSide {
     DevBuf ds;                // laserCloud*FromMapDS, float4, VoxelGrid (ascending idx) order
-    DevBuf cell_pts, cell_start;
+    DevBuf cell_pts, cell_start, hkeys;
+    bool hashed = false;      // cell directory: dense prefix array, or an open-addressing hash of the occupied cells
+    uint32_t hmask = 0;
     uint32_t m = 0;
     uint64_t n_in = 0;
     GridSpec gs{};
@@ -504,7 +506,7 @@ int voxelgrid_batch(lvreg_handle* h, VgJob* jobs, int nj) {
 
 // ---- search-grid build (on a lane stream; no host synchronisation when the bbox is known) --------
 int build_grid(lvreg_handle* h, Lane& L, MapSide& ms, const float* bb_min, const float* bb_max,
-               float cell_override = 0.f, const float4* pts_override = nullptr) {
+               float cell_override = 0.f, const float4* pts_override = nullptr, bool allow_hash = false) {
     const uint32_t m = ms.m;
     const float4* pts = pts_override ? pts_override : ms.ds.as<float4>();
     GridSpec gs;
@@ -515,6 +517,7 @@ int build_grid(lvreg_handle* h, Lane& L, MapSide& ms, const float* bb_min, const
         gs.cell = cell;
         gs.inv = 1.0f / cell;
         gs.dx = gs.dy = gs.dz = 1;
+        ms.hashed = false;
         CK(ms.cell_start.reserve(2 * 4));
         CK(cudaMemsetAsync(ms.cell_start.p, 0, 8, L.st));
         CK(ms.cell_pts.reserve(16));
@@ -539,6 +542,10 @@ int build_grid(lvreg_handle* h, Lane& L, MapSide& ms, const float* bb_min, const
             mx[a] = ordered_to_float(L.pinned[3 + a]);
         }
     }
+    // Directory: dense while it is small next to the map (cells <= max(2^24, 16 m): memory stays O(m) above a fixed
+    // 64 MB floor), else a hash of the occupied cells.  Only a map wider than 2048 cells per axis gets coarser cells
+    // (the fp32 error bound of the cell coordinate assumes dims <= 2048; coarser cells stay exact).
+    ms.hashed = false;
     for (;;) {
         const float inv = 1.0f / cell;
         int64_t dims[3];
@@ -547,21 +554,53 @@ int build_grid(lvreg_handle* h, Lane& L, MapSide& ms, const float* bb_min, const
             dims[a] = (int64_t)floorf((mx[a] - mn[a]) * inv) + 1;
             if (dims[a] > 2048 || dims[a] < 1) ok = false;
         }
-        if (ok && dims[0] * dims[1] * dims[2] <= (int64_t)(1 << 26)) {
-            gs.ox = mn[0]; gs.oy = mn[1]; gs.oz = mn[2];
-            gs.cell = cell;
-            gs.inv = inv;
-            gs.dx = (int)dims[0]; gs.dy = (int)dims[1]; gs.dz = (int)dims[2];
-            break;
+        if (ok) {
+            const int64_t nc = dims[0] * dims[1] * dims[2];
+            int64_t dense_cap = (int64_t)16 * (int64_t)m;
+            if (dense_cap < ((int64_t)1 << 24)) dense_cap = (int64_t)1 << 24;
+            if (dense_cap > ((int64_t)1 << 28)) dense_cap = (int64_t)1 << 28;
+            if (!allow_hash) dense_cap = (int64_t)1 << 26;
+            if (nc <= dense_cap || allow_hash) {
+                ms.hashed = nc > dense_cap;
+                gs.ox = mn[0]; gs.oy = mn[1]; gs.oz = mn[2];
+                gs.cell = cell;
+                gs.inv = inv;
+                gs.dx = (int)dims[0]; gs.dy = (int)dims[1]; gs.dz = (int)dims[2];
+                break;
+            }
         }
         cell *= 2.0f;       // coarser cells stay exact, they only add candidates
         if (!(cell < 1e30f)) return fail(h, LVREG_ERR_INVALID, "map extent is not finite");
     }
+    CK(ms.cell_pts.reserve((size_t)m * 16));
+    CK(L.keys[0].reserve((size_t)m * 4));
+    CK(L.vals[0].reserve((size_t)m * 4));
+    if (ms.hashed) {
+        uint32_t tsize = 1024;
+        while (tsize < 2u * m) tsize <<= 1;
+        ms.hmask = tsize - 1;
+        CK(ms.hkeys.reserve((size_t)tsize * 8));
+        CK(L.scan_in.reserve((size_t)(tsize + 9) * 4));
+        CK(ms.cell_start.reserve((size_t)(tsize + 9) * 4));
+        CK(L.scan_temp.reserve((size_t)(scan_num_tiles(tsize + 1) + 2) * 4));
+        CK(cudaMemsetAsync(ms.hkeys.p, 0xff, (size_t)tsize * 8, L.st));
+        CK(cudaMemsetAsync(L.scan_in.p, 0, (size_t)(tsize + 1) * 4, L.st));
+        hash_count_kernel<<<nblk(m, 256), 256, 0, L.st>>>(pts, m, gs, ms.hkeys.as<unsigned long long>(), ms.hmask,
+                                                          L.keys[0].as<uint32_t>(), L.vals[0].as<uint32_t>(),
+                                                          L.scan_in.as<uint32_t>());
+        launched(h);
+        exclusive_scan(CountIn{L.scan_in.as<uint32_t>()}, StartOut{ms.cell_start.as<uint32_t>()}, tsize + 1,
+                       L.scan_temp.as<uint32_t>(), L.small.as<uint32_t>() + SM_TOTAL, L.st, &h->call_launches);
+        cell_scatter_kernel<<<nblk(m, 256), 256, 0, L.st>>>(pts, L.keys[0].as<uint32_t>(), L.vals[0].as<uint32_t>(),
+                                                            ms.cell_start.as<uint32_t>(), m, ms.cell_pts.as<float4>());
+        launched(h);
+        CK(cudaGetLastError());
+        ms.gs = gs;
+        return LVREG_OK;
+    }
     const uint32_t ncells = (uint32_t)gs.dx * gs.dy * gs.dz;
-    CKS(ensure_sort_buffers(h, L, m));
     CK(L.scan_in.reserve((size_t)(ncells + 9) * 4));
     CK(ms.cell_start.reserve((size_t)(ncells + 9) * 4));
-    CK(ms.cell_pts.reserve((size_t)m * 16));
     CK(L.scan_temp.reserve((size_t)(scan_num_tiles(ncells + 1) + 2) * 4));
     // counting sort by cell: count (the atomic also ranks the point inside its cell), scan, scatter
     CK(cudaMemsetAsync(L.scan_in.p, 0, (size_t)(ncells + 1) * 4, L.st));
@@ -582,6 +621,9 @@ GridView grid_view(const MapSide& ms) {
     GridView g;
     g.pts = ms.cell_pts.as<float4>();
     g.cell_start = ms.cell_start.as<uint32_t>();
+    g.hkeys = ms.hkeys.as<unsigned long long>();
+    g.hmask = ms.hmask;
+    g.hashed = ms.hashed ? 1 : 0;
     g.ox = ms.gs.ox; g.oy = ms.gs.oy; g.oz = ms.gs.oz;
     g.inv = ms.gs.inv;
     g.cell = ms.gs.cell;
@@ -689,7 +731,8 @@ int prepare_scan_jobs(lvreg_handle* h, const lvreg_cloud* corner_raw, const lvre
 int build_map_grids(lvreg_handle* h, VgJob* map_jobs) {
     for (int s = 0; s < 2; ++s) {
         const bool have_bb = map_jobs && map_jobs[s].n > 0;
-        CKS(build_grid(h, h->lane[s], h->map[s], have_bb ? map_jobs[s].mn : nullptr, have_bb ? map_jobs[s].mx : nullptr));
+        CKS(build_grid(h, h->lane[s], h->map[s], have_bb ? map_jobs[s].mn : nullptr, have_bb ? map_jobs[s].mx : nullptr,
+                       0.f, nullptr, true));
         h->map[s].valid = true;
     }
     return LVREG_OK;
@@ -1070,7 +1113,7 @@ void lvreg_destroy(lvreg_handle* h) {
         if (L.st) cudaStreamDestroy(L.st);
     }
     for (int s = 0; s < 2; ++s) {
-        h->map[s].ds.release(); h->map[s].cell_pts.release(); h->map[s].cell_start.release();
+        h->map[s].ds.release(); h->map[s].cell_pts.release(); h->map[s].cell_start.release(); h->map[s].hkeys.release();
         h->scan_ds[s].release();
         h->scan_sorted[s].release();
         h->icp_cloud[s].ds.release(); h->icp_cloud[s].cell_pts.release(); h->icp_cloud[s].cell_start.release();
@@ -2658,6 +2701,7 @@ int lvreg_debug_stage_stats(lvreg_handle* h, uint32_t out[8]) {
     CK(cudaSetDevice(h->device));
     CK(cudaMemcpyAsync(out, h->stagestats.p, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->st));
     CK(cudaStreamSynchronize(h->st));
+    out[5] = (uint32_t)((const RegOut*)((const char*)h->pinned + 4096))->pad;   // 1 = Cholesky shortcut, 2 = 6x6 Jacobi
     return LVREG_OK;
 }
 

@@ -281,6 +281,7 @@ __global__ void __launch_bounds__(kRegThreads, 2) register_kernel(RegArgs a) {
         a.out->iterations = iter;
         a.out->converged = converged;
         a.out->degenerate = sLm.is_degenerate;
+        a.out->pad = sLm.last_path;
         for (int i = 0; i < 6; ++i) a.out->pose[i] = sPose[i];
         *a.lm = sLm;
     }
@@ -439,6 +440,7 @@ __global__ void __launch_bounds__(kRegThreads, 2) register_tpq_kernel(RegArgs a)
         a.out->iterations = iter;
         a.out->converged = converged;
         a.out->degenerate = sLm.is_degenerate;
+        a.out->pad = sLm.last_path;
         for (int i = 0; i < 6; ++i) a.out->pose[i] = sPose[i];
         *a.lm = sLm;
     }

@@ -131,6 +131,7 @@ __device__ __forceinline__ bool stage_and_search(const GridView& g, StWarp& S, u
                                                  int cx, int cy, int cz, float ux, float uy, float uz, float qx, float qy,
                                                  float qz, float gate_sq, u64 (&best)[5], int* err) {
     const unsigned full = 0xffffffffu;
+    if (g.hashed) return false;                                // hashed directory: rows are not contiguous runs
     const bool in = (seg >> lane) & 1u;
     const int big = 0x7fffffff;
     const int xmin = __reduce_min_sync(full, in ? cx : big), xmax = __reduce_max_sync(full, in ? cx : -1);
@@ -434,6 +435,7 @@ __global__ void __launch_bounds__(kRegThreads, 2) register_staged_kernel(RegArgs
         a.out->iterations = iter;
         a.out->converged = converged;
         a.out->degenerate = sLm.is_degenerate;
+        a.out->pad = sLm.last_path;
         for (int i = 0; i < 6; ++i) a.out->pose[i] = sPose[i];
         *a.lm = sLm;
     }

@@ -38,7 +38,14 @@ __device__ __forceinline__ float float_below(float x) { return __uint_as_float(_
 // (the caller guarantees that, or passes float_below(gate)).  Same visiting order, pruning rule and key order
 // as thread_knn5_gated.
 __device__ __forceinline__ void thread_knn5_radius(const GridView& g, float qx, float qy, float qz, float tau_le,
-                                                   u64 (&t)[5]) {
+                                                   float gate_sq, u64 (&t)[5]) {
+    if (g.hashed) {                 // hashed directory (huge sparse extents): the plain gated search, still exact
+        u64 hb[5];
+        group_knn5_hashed<1>(g, qx, qy, qz, 0, 1u << (threadIdx.x & 31), false, gate_sq, hb);
+#pragma unroll
+        for (int i = 0; i < 5; ++i) t[i] = hb[i];
+        return;
+    }
 #pragma unroll
     for (int i = 0; i < 5; ++i) t[i] = kKeyNone;
     float ux, uy, uz;
@@ -164,7 +171,7 @@ __global__ void __launch_bounds__(kRegThreads, 2) register_warm_kernel(RegArgs a
             }
             if (valid) {
                 u64 best[5];
-                thread_knn5_radius(a.grid[cls], sel.x, sel.y, sel.z, tau_le, best);
+                thread_knn5_radius(a.grid[cls], sel.x, sel.y, sel.z, tau_le, P.knn_gate_sq, best);
                 int nn[5];
 #pragma unroll
                 for (int i = 0; i < 5; ++i) {
@@ -266,6 +273,7 @@ __global__ void __launch_bounds__(kRegThreads, 2) register_warm_kernel(RegArgs a
         a.out->iterations = iter;
         a.out->converged = converged;
         a.out->degenerate = sLm.is_degenerate;
+        a.out->pad = sLm.last_path;
         for (int i = 0; i < 6; ++i) a.out->pose[i] = sPose[i];
         *a.lm = sLm;
     }

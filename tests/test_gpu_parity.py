@@ -448,3 +448,51 @@ def test_two_handles_are_independent(lv, room):
     assert np.abs(pb - rpb).max() <= 1e-4 and not np.array_equal(pa, pb)
     a.close()
     b.close()
+
+
+def test_hashed_cell_directory_sparse_kilometre_map(lv):
+    """A sparse map spread over > 2^26 search cells (two blocks of structure 1.6 km apart): the directory becomes
+    a hash of the occupied cells, the cell keeps its 1 m edge (no coarsening), and every search variant and the
+    registration kernels still equal the oracle."""
+    rng = np.random.default_rng(77)
+    cw, sw = room_world(rng, n_surf=20000, n_corner=4000)
+    off = np.array([1600.0, 1500.0, 40.0, 0.0], np.float32)
+    surf_map = np.concatenate([sw, sw + off]).astype(np.float32)
+    corner_map = np.concatenate([cw, cw + off]).astype(np.float32)
+    h = lv.Lvreg()
+    info = h.set_local_map(corner_map, surf_map)
+    dims = np.array(info.grid_dims[1][:], np.int64)
+    assert dims.prod() > (1 << 26)                          # a dense directory would need > 2^26 cells ...
+    assert abs(info.grid_cell[1] - 1.0078125) < 1e-6       # ... and the cell was NOT coarsened
+    q = np.concatenate([surf_map[rng.integers(0, len(surf_map), 3000)],
+                        rng.uniform(-20, 1650, (300, 4)).astype(np.float32)]).astype(np.float32)
+    q[:3000, :3] += rng.normal(0, 0.05, (3000, 3)).astype(np.float32)
+    tree = O.KdTree(surf_map)
+    oidx, od2 = tree.knn(q, 5)
+    eidx, ed2 = h.knn5(lv.SURF, q, lv.KNN_GRID_EXACT)
+    assert np.array_equal(eidx, oidx) and np.array_equal(ed2, od2)
+    inside = od2[:, 4] < 1.0
+    assert inside.sum() > 2000
+    for variant in (lv.KNN_GRID_GATED, lv.KNN_GRID_STAGED):
+        gidx, gd2 = h.knn5(lv.SURF, q, variant)
+        assert np.array_equal(gidx[inside], oidx[inside]) and np.array_equal(gd2[inside], od2[inside])
+    # registration in the far block, every kernel variant
+    truth = np.array([0.01, -0.02, 0.2, 1600.5, 1499.0, 40.1], np.float32)
+    c, s = scan_from_world(rng, cw + off, sw + off, truth, 1200, 4000)
+    guess = truth + np.array([0.01, -0.01, 0.02, 0.08, -0.05, 0.03], np.float32)
+    cds, sds = O.voxelgrid(c, 0.2)[0], O.voxelgrid(s, 0.4)[0]
+    opose, ores = O.scan2map(corner_map, surf_map, cds, sds, guess)[:2]
+    h.close()
+    import os
+    for variant in ("warm", "tpq", "grouped", "staged"):
+        os.environ["LVREG_REG"] = variant
+        try:
+            h = lv.Lvreg()
+            h.set_local_map(corner_map, surf_map)
+            h.set_scan_ds(cds, sds)
+            pose, res, st = h.scan2map(guess)
+            assert st == lv.OK and res.iterations == ores.iterations
+            assert np.abs(pose[:3] - opose[:3]).max() <= 1e-5 and np.abs(pose[3:] - opose[3:]).max() <= 1e-4
+            h.close()
+        finally:
+            os.environ.pop("LVREG_REG", None)
