@@ -306,7 +306,8 @@ int lvreg_loop_find_near_keyframes(lvreg_handle* h, int key, int search_num, int
 /* Global map for visualisation / saving (publishGlobalMap MO:493-508; saveMapService MO:199-231): the
  * clouds selected by `which` (1 corner, 2 surf, 3 corner then surf of each keyframe) of the listed
  * keyframes under their stored poses, concatenated in list order, then one VoxelGrid with `leaf`
- * (globalMapVisualizationLeafSize / the service's resolution).  The result replaces slot 0; read it back
+ * (globalMapVisualizationLeafSize / the service's resolution; leaf = 0: no VoxelGrid, the concatenation itself,
+ * as saveMapService does for resolution 0).  The result replaces slot 0; read it back
  * with lvreg_icp_get_cloud(h, 0, ...).  The key-pose selection (radius search + pose-density VoxelGrid,
  * MO:476-491) is host logic over a few hundred poses. */
 int lvreg_build_global_map(lvreg_handle* h, const int32_t* ids, size_t n_ids, int which, float leaf, size_t* n_out);

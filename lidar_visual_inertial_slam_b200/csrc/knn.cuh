@@ -514,32 +514,66 @@ __global__ void __launch_bounds__(256) knn5_grid_kernel(GridView g, const float4
 // ---- brute force (FP32-pipe bound variant of the micro-benchmark) -----------------------------
 // thread per query, map staged through shared memory in tiles; blockIdx.y splits the map.
 constexpr int kBruteTile = 1024;
+constexpr int kBruteQpt = 2;                 // queries per thread: one shared-memory read serves two distance evaluations
+constexpr int kBruteQpb = 256 * kBruteQpt;   // queries per block
+// Per pair: 3 subtractions, 3 multiplications, 2 additions (no FMA: FLANN's L2_Simple rounds every operation), one
+// fp32 compare against the query's current 5th distance; the 64-bit (d2, index) key is only formed for the few
+// candidates that pass it.
 __global__ void __launch_bounds__(256) knn5_brute_kernel(const float4* __restrict__ map, uint32_t m,
                                                          const float4* __restrict__ queries,
                                                          uint32_t nq, uint32_t chunk,
                                                          u64* __restrict__ partial) {
     __shared__ float4 tile[kBruteTile];
-    const uint32_t q = blockIdx.x * 256 + threadIdx.x;
-    float4 qp = q < nq ? queries[q] : make_float4(0, 0, 0, 0);
-    u64 t[5] = {kKeyNone, kKeyNone, kKeyNone, kKeyNone, kKeyNone};
+    const uint32_t q0 = blockIdx.x * kBruteQpb + threadIdx.x, q1 = q0 + 256;
+    const float4 a = q0 < nq ? queries[q0] : make_float4(0, 0, 0, 0);
+    const float4 b = q1 < nq ? queries[q1] : make_float4(0, 0, 0, 0);
+    u64 ta[5] = {kKeyNone, kKeyNone, kKeyNone, kKeyNone, kKeyNone};
+    u64 tb[5] = {kKeyNone, kKeyNone, kKeyNone, kKeyNone, kKeyNone};
+    float wa = __int_as_float(0x7f800000), wb = wa;          // current 5th distance (inf while the list is short)
     const uint32_t begin = blockIdx.y * chunk;
     const uint32_t end = min(m, begin + chunk);
     for (uint32_t base = begin; base < end; base += kBruteTile) {
         const uint32_t cnt = min((uint32_t)kBruteTile, end - base);
         __syncthreads();
-        for (uint32_t i = threadIdx.x; i < cnt; i += 256) tile[i] = ld_stream(map + base + i);
+        for (uint32_t i = threadIdx.x; i < kBruteTile; i += 256)
+            tile[i] = i < cnt ? ld_stream(map + base + i) : make_float4(3.0e19f, 3.0e19f, 3.0e19f, 0.f);
         __syncthreads();
-#pragma unroll 4
-        for (uint32_t i = 0; i < cnt; ++i) {
-            float4 p = tile[i];
-            float d = sqdist(qp.x, qp.y, qp.z, p.x, p.y, p.z);
-            u64 key = ((u64)__float_as_uint(d) << 32) | (u64)(base + i);
-            top5_insert(t, key);
+        // eight candidates per step: 16 distances and their two minima, ONE branch; the (rare) step in which some
+        // candidate beats a current 5th distance is redone candidate by candidate by a single rolled copy of the
+        // insertion code (the distances are recomputed from shared memory: same inputs, same bits)
+        for (uint32_t i0 = 0; i0 < cnt; i0 += 8) {
+            float ma = __int_as_float(0x7f800000), mb = ma;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const float4 p = tile[i0 + k];                 // rows past cnt hold points at infinity
+                ma = fminf(ma, sqdist(a.x, a.y, a.z, p.x, p.y, p.z));
+                mb = fminf(mb, sqdist(b.x, b.y, b.z, p.x, p.y, p.z));
+            }
+            if (ma <= wa || mb <= wb) {
+#pragma unroll 1
+                for (uint32_t i = i0; i < min(i0 + 8, cnt); ++i) {
+                    const float4 p = tile[i];
+                    const float da = sqdist(a.x, a.y, a.z, p.x, p.y, p.z);
+                    const float db = sqdist(b.x, b.y, b.z, p.x, p.y, p.z);
+                    if (da <= wa) {
+                        top5_insert(ta, ((u64)__float_as_uint(da) << 32) | (u64)(base + i));
+                        if (ta[4] != kKeyNone) wa = key_d2(ta[4]);
+                    }
+                    if (db <= wb) {
+                        top5_insert(tb, ((u64)__float_as_uint(db) << 32) | (u64)(base + i));
+                        if (tb[4] != kKeyNone) wb = key_d2(tb[4]);
+                    }
+                }
+            }
         }
     }
-    if (q < nq) {
+    if (q0 < nq) {
 #pragma unroll
-        for (int i = 0; i < 5; ++i) partial[((size_t)blockIdx.y * nq + q) * 5 + i] = t[i];
+        for (int i = 0; i < 5; ++i) partial[((size_t)blockIdx.y * nq + q0) * 5 + i] = ta[i];
+    }
+    if (q1 < nq) {
+#pragma unroll
+        for (int i = 0; i < 5; ++i) partial[((size_t)blockIdx.y * nq + q1) * 5 + i] = tb[i];
     }
 }
 

@@ -1586,8 +1586,9 @@ static int knn5_launch(lvreg_handle* h, int which, const float4* q, uint32_t nq,
                        float* d_d2) {
     const MapSide& ms = h->map[which];
     if (variant == LVREG_KNN_BRUTE) {
-        const uint32_t qblocks = nblk(nq, 256);
-        uint32_t splits = (uint32_t)(2 * h->num_sms) / (qblocks ? qblocks : 1);
+        const uint32_t qblocks = nblk(nq, kBruteQpb);
+        const uint32_t mblocks = nblk(nq, 256);
+        uint32_t splits = (uint32_t)(4 * h->num_sms) / (qblocks ? qblocks : 1);
         if (splits < 1) splits = 1;
         uint32_t max_splits = nblk(ms.m ? ms.m : 1, kBruteTile);
         if (splits > max_splits) splits = max_splits;
@@ -1597,7 +1598,7 @@ static int knn5_launch(lvreg_handle* h, int which, const float4* q, uint32_t nq,
         CK(h->brute_partial.reserve((size_t)splits * nq * 5 * sizeof(u64)));
         knn5_brute_kernel<<<dim3(qblocks, splits), 256, 0, h->st>>>(ms.ds.as<float4>(), ms.m, q, nq, chunk,
                                                                    h->brute_partial.as<u64>());
-        knn5_brute_merge_kernel<<<qblocks, 256, 0, h->st>>>(h->brute_partial.as<u64>(), nq, splits, d_idx, d_d2);
+        knn5_brute_merge_kernel<<<mblocks, 256, 0, h->st>>>(h->brute_partial.as<u64>(), nq, splits, d_idx, d_d2);
         launched(h, 2);
     } else if (variant == LVREG_KNN_GRID_STAGED) {
         // the search of the registration kernel (shared-memory tiles filled by bulk copies), materialised
@@ -2203,13 +2204,33 @@ int lvreg_loop_find_near_keyframes(lvreg_handle* h, int key, int search_num, int
 // global map for visualisation / saving (publishGlobalMap MO:493-508, saveMapService MO:199-231): the selected
 // clouds of the listed keyframes under their stored poses, concatenated in list order, then one VoxelGrid
 int lvreg_build_global_map(lvreg_handle* h, const int32_t* ids, size_t n_ids, int which, float leaf, size_t* n_out) {
-    if (!h || (!ids && n_ids) || which < 1 || which > 3 || !(leaf > 0.f)) return LVREG_ERR_INVALID;
+    if (!h || (!ids && n_ids) || which < 1 || which > 3 || !(leaf >= 0.f)) return LVREG_ERR_INVALID;
     CK(cudaSetDevice(h->device));
     if (h->kfs.empty()) return fail(h, LVREG_ERR_NO_KEYFRAMES, "no keyframes");
     begin_call(h);
     mark(h, EV_BEGIN);
     VgJob J;
-    CKS(prepare_submap_job(h, ids, n_ids, which, leaf, 0, J));
+    CKS(prepare_submap_job(h, ids, n_ids, which, leaf > 0.f ? leaf : 1.0f, 0, J));
+    if (leaf == 0.f) {
+        // saveMapService with resolution 0 (MO:219-225): the transformed clouds, concatenated, no VoxelGrid
+        Lane& L = h->lane[0];
+        MapSide& ms = h->icp_cloud[0];
+        CK(ms.ds.reserve((size_t)(J.n ? J.n : 1) * 16));
+        if (J.n) {
+            uint32_t* mm = L.small.as<uint32_t>() + SM_MM;
+            CK(L.segs.reserve(L.seg_host.size() * sizeof(Segment)));
+            CK(cudaMemcpyAsync(L.segs.p, L.seg_host.data(), L.seg_host.size() * sizeof(Segment), cudaMemcpyHostToDevice, h->st));
+            transform_concat_kernel<<<min(nblk(J.n, 256), (uint32_t)h->num_sms * 16), 256, 0, h->st>>>(
+                L.segs.as<Segment>(), (uint32_t)L.seg_host.size(), J.n, ms.ds.as<float4>(), mm);
+            launched(h);
+        }
+        CK(cudaStreamSynchronize(h->st));
+        ms.m = J.n;
+        ms.valid = true;
+        end_call(h);
+        if (n_out) *n_out = ms.m;
+        return LVREG_OK;
+    }
     lanes_fork(h, 0x1);
     CKS(voxelgrid_batch(h, &J, 1));
     lanes_join(h, 0x1);

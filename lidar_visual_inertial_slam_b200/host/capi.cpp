@@ -7,6 +7,7 @@
 
 #include "front_end.hpp"
 #include "harness.hpp"
+#include "wire_formats.hpp"
 
 using namespace lvreg_host;
 
@@ -186,6 +187,83 @@ int lvh_replay(int sensor, uint64_t seed, int n_scans, double period, double spe
         g_err = e.what();
         return -2;
     }
+}
+
+// ---- wire / disk formats ----
+// CloudInfo from flat arrays -> CDR bytes.  Returns the size of the message; writes it when it fits in `cap`.
+// scalars_i = {imu_available, odom_available, odom_reset_id}; scalars_f = {imu_roll_init, imu_pitch_init,
+// imu_yaw_init, initial_guess_x, y, z, roll, pitch, yaw}; clouds as packed {x,y,z,intensity} rows.
+size_t lvh_cloudinfo_serialize(double stamp, const char* frame_id, const int32_t* start_ring, const int32_t* end_ring,
+                               size_t n_ring, const int32_t* col, const float* range, size_t n_pts,
+                               const int64_t scalars_i[3], const float scalars_f[9], const float* deskewed, size_t nd,
+                               const float* corner, size_t nc, const float* surf, size_t ns, uint8_t* out, size_t cap) {
+    CloudInfo m;
+    m.stamp = stamp;
+    m.start_ring_index.assign(start_ring, start_ring + n_ring);
+    m.end_ring_index.assign(end_ring, end_ring + n_ring);
+    m.point_col_ind.assign(col, col + n_pts);
+    m.point_range.assign(range, range + n_pts);
+    m.imu_available = scalars_i[0]; m.odom_available = scalars_i[1]; m.odom_reset_id = scalars_i[2];
+    m.imu_roll_init = scalars_f[0]; m.imu_pitch_init = scalars_f[1]; m.imu_yaw_init = scalars_f[2];
+    m.initial_guess_x = scalars_f[3]; m.initial_guess_y = scalars_f[4]; m.initial_guess_z = scalars_f[5];
+    m.initial_guess_roll = scalars_f[6]; m.initial_guess_pitch = scalars_f[7]; m.initial_guess_yaw = scalars_f[8];
+    m.cloud_deskewed = cloud_from_xyzi(deskewed, nd);
+    m.cloud_corner = cloud_from_xyzi(corner, nc);
+    m.cloud_surface = cloud_from_xyzi(surf, ns);
+    const std::vector<uint8_t> b = serialize_cloud_info(m, frame_id ? frame_id : "");
+    if (out && b.size() <= cap) std::memcpy(out, b.data(), b.size());
+    return b.size();
+}
+
+// CDR bytes -> CloudInfo -> CDR bytes (must reproduce the input); summary = {stamp, rings, points, imu_available,
+// odom_available, odom_reset_id, 9 floats, n_deskewed, n_corner, n_surface, sum of all cloud coordinates}.
+// Returns the re-serialised size, 0 on a malformed message (lvh_last_error says why).
+size_t lvh_cloudinfo_roundtrip(const uint8_t* in, size_t len, uint8_t* out, size_t cap, double summary[19]) {
+    try {
+        std::string frame;
+        const CloudInfo m = deserialize_cloud_info(in, len, &frame);
+        if (summary) {
+            summary[0] = m.stamp; summary[1] = (double)m.start_ring_index.size(); summary[2] = (double)m.point_range.size();
+            summary[3] = (double)m.imu_available; summary[4] = (double)m.odom_available; summary[5] = (double)m.odom_reset_id;
+            const float f[9] = {m.imu_roll_init, m.imu_pitch_init, m.imu_yaw_init, m.initial_guess_x, m.initial_guess_y,
+                                m.initial_guess_z, m.initial_guess_roll, m.initial_guess_pitch, m.initial_guess_yaw};
+            for (int i = 0; i < 9; ++i) summary[6 + i] = f[i];
+            summary[15] = (double)m.cloud_deskewed.size(); summary[16] = (double)m.cloud_corner.size();
+            summary[17] = (double)m.cloud_surface.size();
+            double sum = 0;
+            for (const Cloud* c : {&m.cloud_deskewed, &m.cloud_corner, &m.cloud_surface})
+                for (const PointType& p : *c) sum += (double)p.x + (double)p.y + (double)p.z + (double)p.intensity;
+            summary[18] = sum;
+        }
+        const std::vector<uint8_t> b = serialize_cloud_info(m, frame);
+        if (out && b.size() <= cap) std::memcpy(out, b.data(), b.size());
+        return b.size();
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return 0;
+    }
+}
+
+// saveMapService (MO:179-236) on the mirror: trajectory / transformations / CornerMap / SurfMap / GlobalMap .pcd
+// into `directory` (must exist).  Returns 1 on success, 0 on an I/O failure, -2 on exception.
+int lvh_mo_save_map(void* p, const char* directory, float resolution) {
+    try {
+        return ((mapOptimization*)p)->saveMap(directory, resolution) ? 1 : 0;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return -2;
+    }
+}
+
+// binary PCD (x y z intensity ...) -> packed rows; returns the number of points, or -1
+long long lvh_load_pcd_xyzi(const char* path, float* out, size_t cap_points) {
+    Cloud c;
+    if (!load_pcd_binary_xyzi(path, &c)) return -1;
+    if (out)
+        for (size_t i = 0; i < c.size() && i < cap_points; ++i) {
+            out[4 * i] = c[i].x; out[4 * i + 1] = c[i].y; out[4 * i + 2] = c[i].z; out[4 * i + 3] = c[i].intensity;
+        }
+    return (long long)c.size();
 }
 
 // replay of one sequence on an existing mirror (reset() first): what lvreg_replay does per sequence and GPU

@@ -1,6 +1,7 @@
 // map_optimization.cpp -- see map_optimization.hpp.  Host logic only (keyframe selection,
 // bookkeeping); all point-level work is done by liblvreg on the GPU.
 #include "map_optimization.hpp"
+#include "wire_formats.hpp"
 
 #include <algorithm>
 #include <cmath>
@@ -199,6 +200,36 @@ bool mapOptimization::performLoopClosure() {
 
 // publishGlobalMap, MO:460-510: key poses within the visualisation radius, thinned by a pose-density
 // VoxelGrid, their corner + surf clouds under the stored poses, one VoxelGrid -- all point work on the device
+bool mapOptimization::saveMap(const std::string& directory, float resolution) {
+    std::vector<int32_t> ids(cloudKeyPoses3D.size());
+    for (size_t i = 0; i < ids.size(); ++i) ids[i] = (int32_t)i;
+    auto device_map = [&](int which, float leaf) {                 // all keyframes, list order, under their stored poses
+        Cloud out;
+        if (ids.empty()) return out;
+        size_t n = 0;
+        if (lvreg_build_global_map(h_, ids.data(), ids.size(), which, leaf, &n) != LVREG_OK)
+            throw std::runtime_error(std::string("lvreg_build_global_map: ") + lvreg_last_error(h_));
+        out.resize(n);
+        lvreg_cloud_out o = as_lvreg_out(out);
+        if (n && lvreg_icp_get_cloud(h_, 0, &o, &n) != LVREG_OK)
+            throw std::runtime_error(std::string("lvreg_icp_get_cloud: ") + lvreg_last_error(h_));
+        return out;
+    };
+    bool ok = save_pcd_binary(directory + "/trajectory.pcd", cloudKeyPoses3D);            // MO:192
+    ok = save_pcd_binary(directory + "/transformations.pcd", cloudKeyPoses6D) && ok;     // MO:193
+    const Cloud globalCornerCloud = device_map(1, 0.f), globalSurfCloud = device_map(2, 0.f);      // MO:200-205
+    if (resolution != 0.f) {                                                              // MO:206-218
+        ok = save_pcd_binary(directory + "/CornerMap.pcd", device_map(1, resolution)) && ok;
+        ok = save_pcd_binary(directory + "/SurfMap.pcd", device_map(2, resolution)) && ok;
+    } else {                                                                              // MO:219-225
+        ok = save_pcd_binary(directory + "/CornerMap.pcd", globalCornerCloud) && ok;
+        ok = save_pcd_binary(directory + "/SurfMap.pcd", globalSurfCloud) && ok;
+    }
+    Cloud globalMapCloud = globalCornerCloud;                                             // MO:227-229
+    globalMapCloud.insert(globalMapCloud.end(), globalSurfCloud.begin(), globalSurfCloud.end());
+    return save_pcd_binary(directory + "/GlobalMap.pcd", globalMapCloud) && ok;
+}
+
 Cloud mapOptimization::publishGlobalMap() {
     Cloud out;
     const size_t K = cloudKeyPoses3D.size();

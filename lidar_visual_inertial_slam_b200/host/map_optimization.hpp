@@ -11,6 +11,7 @@
 
 #include <cstdint>
 #include <map>
+#include <string>
 #include <vector>
 
 #include "../../include/lvreg.h"
@@ -112,6 +113,11 @@ class mapOptimization {
 
     // publishGlobalMap (MO:460-510) without the ROS publisher: returns globalMapKeyFramesDS
     Cloud publishGlobalMap();
+    // the lio_sam/save_map service (MO:179-236): trajectory.pcd, transformations.pcd, CornerMap.pcd, SurfMap.pcd and
+    // GlobalMap.pcd (binary PCD v0.7, as pcl::io::savePCDFileBinary writes them) into `directory`, which must exist;
+    // resolution != 0 down-samples the corner / surf maps with that leaf (MO:206-218).  The transform + concatenate
+    // (+ VoxelGrid) of all keyframe clouds runs on the device.
+    bool saveMap(const std::string& directory, float resolution);
 
     // read-backs of device-resident clouds (laserCloud*LastDS / *FromMapDS)
     Cloud getLaserCloudLastDS(int which);
