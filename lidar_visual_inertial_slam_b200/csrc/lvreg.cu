@@ -26,6 +26,7 @@
 #include "register_staged.cuh"
 #include "register_warm.cuh"
 #include "voxelgrid.cuh"
+#include "voxelgrid_mid.cuh"
 
 using namespace lvreg;
 
@@ -154,6 +155,7 @@ struct lvreg_handle {
     int num_sms = kNumSMs;
     int lpq = 4;
     int tile = 16;
+    bool vg_mid_enabled = true;   // LVREG_VG_MID=0 disables the cooperative single-launch VoxelGrid (experiments)
     int debug_tiles = 0;          // LVREG_DEBUG_TILES=1: record per-tile durations of iteration 1
     uint32_t debug_ntiles = 0;
     int force_tpq = -1;           // -1 auto, 0 grouped, 1 thread-per-query (LVREG_TPQ)
@@ -359,6 +361,7 @@ struct VgJob {
     bool want_out_keys = false;        // per-voxel idx into Lane::vox_keys
     uint32_t* d_point_keys = nullptr;  // optional device array (n): per-point idx
     bool small = false;                // internal: handled by the single-block kernel
+    bool mid = false;                  // internal: handled by the cooperative single-launch kernel
     // results
     float mn[3] = {0, 0, 0}, mx[3] = {0, 0, 0};   // bbox of the input cloud
     int passthrough = 0;
@@ -392,6 +395,55 @@ int voxelgrid_batch(lvreg_handle* h, VgJob* jobs, int nj) {
         }
         if (!(J.leaf > 0.f)) return fail(h, LVREG_ERR_INVALID, "leaf size must be positive");
         J.small = !J.from_segments && J.n <= (uint32_t)kVgSmallMax;
+        J.mid = !J.small && J.n <= (uint32_t)kVgMidMax && h->vg_mid_enabled;
+        if (J.mid) {
+            // the whole filter in one cooperative launch (voxelgrid_mid.cuh): no host round trip until the shared
+            // final synchronisation, one launch instead of ~15
+            VgMidArgs a;
+            a.n = J.n;
+            a.leaf = J.leaf;
+            a.pts = J.pts;
+            a.segs = nullptr;
+            a.nseg = 0;
+            a.world = nullptr;
+            if (J.from_segments) {
+                CK(L.segs.reserve(L.seg_host.size() * sizeof(Segment)));
+                CK(cudaMemcpyAsync(L.segs.p, L.seg_host.data(), L.seg_host.size() * sizeof(Segment), cudaMemcpyHostToDevice, L.st));
+                CK(L.concat.reserve((size_t)J.n * 16));
+                a.segs = L.segs.as<Segment>();
+                a.nseg = (uint32_t)L.seg_host.size();
+                a.world = L.concat.as<float4>();
+                a.pts = nullptr;
+            }
+            for (int i = 0; i < 2; ++i) {
+                CK(L.keys[i].reserve((size_t)J.n * 4));
+                CK(L.vals[i].reserve((size_t)J.n * 4));
+            }
+            CK(L.sort_scratch.reserve((vg_mid_hist_words() + vg_mid_bb_floats()) * 4));
+            CK(L.vox_start.reserve((size_t)J.n * 4));
+            CK(J.out->reserve((size_t)J.n * 16));
+            a.k0 = L.keys[0].as<uint32_t>(); a.v0 = L.vals[0].as<uint32_t>();
+            a.k1 = L.keys[1].as<uint32_t>(); a.v1 = L.vals[1].as<uint32_t>();
+            a.tile_hist = L.sort_scratch.as<uint32_t>();
+            a.tile_bb = reinterpret_cast<float*>(L.sort_scratch.as<uint32_t>() + vg_mid_hist_words());
+            a.vstart = L.vox_start.as<uint32_t>();
+            a.out = J.out->as<float4>();
+            a.out_keys = nullptr;
+            if (J.want_out_keys) {
+                CK(L.vox_keys.reserve((size_t)J.n * 4));
+                a.out_keys = L.vox_keys.as<uint32_t>();
+            }
+            a.point_keys = J.d_point_keys;
+            VgSmallInfo* d_info = reinterpret_cast<VgSmallInfo*>(L.small.as<uint32_t>() + SM_SMALLVG);
+            a.info = d_info;
+            void* kargs[] = {&a};
+            CK(cudaLaunchCooperativeKernel((void*)voxelgrid_mid_kernel, dim3(nblk(J.n, kVgMidTile)), dim3(kVgMidThreads), kargs, 0, L.st));
+            launched(h);
+            CK(cudaMemcpyAsync(L.pinned + 32, d_info, sizeof(VgSmallInfo), cudaMemcpyDeviceToHost, L.st));
+            if (J.from_segments) J.pts = L.concat.as<float4>();
+            J.small = true;                    // from here on it is handled like the single-block path
+            continue;
+        }
         if (J.small) {
             // the whole filter in one block, no host round trip until the shared final synchronisation
             CK(J.out->reserve((size_t)J.n * 16));
@@ -1068,6 +1120,8 @@ int lvreg_create(const lvreg_params* p, int device, void* cuda_stream, lvreg_han
         int v = atoi(e);
         if (v == 4 || v == 8 || v == 16 || v == 32) h->lpq = v;
     }
+    e = getenv("LVREG_VG_MID");
+    if (e) h->vg_mid_enabled = atoi(e) != 0;
     e = getenv("LVREG_DEBUG_TILES");
     if (e) h->debug_tiles = atoi(e);
     e = getenv("LVREG_TPQ");
