@@ -521,30 +521,35 @@ __device__ inline bool lu_solve6(const float* Ain, const float* Bin, float* X) {
     return true;
 }
 
-// Rigorous shortcut for the degeneracy test (MO:1262-1281): if JtJ - mu*I admits a Cholesky
-// factorisation (fp64) with mu = threshold + a bound on the fp32 Jacobi eigenvalue error
-// (64 * eps * trace, far above the backward error of the sweep), then lambda_min > mu and the
-// Jacobi result would have every eigenvalue >= threshold.  Returns false when in doubt.
+// Shortcut for the degeneracy test (MO:1262-1281).  If JtJ - mu*I admits a Cholesky factorisation, then
+// lambda_min(JtJ) > mu - |E|, |E| <= 7 eps |JtJ| being the backward error of a 6x6 fp32 Cholesky.  With
+// mu = 1.01 * threshold + 128 eps * trace this leaves lambda_min > threshold + 121 eps * trace, far above the error
+// of the fp32 Jacobi sweep cv::eigen would run (a few eps * |JtJ|): its eigenvalues would all be >= threshold,
+// i.e. isDegenerate = false and matP unused -- the sweep can be skipped.  Returns false when in doubt.  (fp32 on
+// purpose: the fp64 version was ~2500 instructions of DDIV / DSQRT expansions executed once per registration, i.e.
+// always from a cold instruction cache: 12 us at C3.)
 __device__ inline bool clearly_well_conditioned(const float* AtA, float threshold) {
-    double tr = 0.0;
-    for (int i = 0; i < 6; ++i) tr += (double)AtA[i * 6 + i];
-    if (!(tr > 0.0) || !(tr < 1e30)) return false;
-    const double mu = (double)threshold * 1.01 + 64.0 * 1.1920929e-07 * tr;
-    double L[6][6];
-#pragma unroll
+    float tr = 0.0f;
+    for (int i = 0; i < 6; ++i) tr += AtA[i * 6 + i];
+    if (!(tr > 0.0f) || !(tr < 1e30f)) return false;
+    const float mu = threshold * 1.01f + 128.0f * 1.1920929e-07f * tr;
+    // rolled on purpose: this runs once per registration, i.e. from a cold instruction cache, where the cost is the
+    // number of instruction lines fetched (an unrolled version measured 12 us at C3), not the number executed
+    float L[36];
+#pragma unroll 1
     for (int j = 0; j < 6; ++j) {
-        double d = (double)AtA[j * 6 + j] - mu;
-#pragma unroll
-        for (int k = 0; k < j; ++k) d -= L[j][k] * L[j][k];
-        if (!(d > 1e-12 * tr)) return false;
-        const double ljj = sqrt(d);
-        L[j][j] = ljj;
-#pragma unroll
+        float d = AtA[j * 6 + j] - mu;
+#pragma unroll 1
+        for (int k = 0; k < j; ++k) d -= L[j * 6 + k] * L[j * 6 + k];
+        if (!(d > 1e-5f * tr)) return false;
+        const float ljj = sqrtf(d);
+        L[j * 6 + j] = ljj;
+#pragma unroll 1
         for (int i = j + 1; i < 6; ++i) {
-            double v = 0.5 * ((double)AtA[i * 6 + j] + (double)AtA[j * 6 + i]);
-#pragma unroll
-            for (int k = 0; k < j; ++k) v -= L[i][k] * L[j][k];
-            L[i][j] = v / ljj;
+            float v = 0.5f * (AtA[i * 6 + j] + AtA[j * 6 + i]);
+#pragma unroll 1
+            for (int k = 0; k < j; ++k) v -= L[i * 6 + k] * L[j * 6 + k];
+            L[i * 6 + j] = v / ljj;
         }
     }
     return true;
@@ -624,6 +629,29 @@ __device__ inline void pose_to_affine_dev(const float* pose, Affine* T, Trig* g)
     T->m[8] = -D;     T->m[9] = C * F;           T->m[10] = C * E;           T->m[11] = pose[5];
     // MO:1202-1207: srx = sin(pitch), sry = sin(yaw), srz = sin(roll)
     g->srx = D; g->crx = C; g->sry = B; g->cry = A; g->srz = F; g->crz = E;
+}
+
+// The same, by the first six lanes of a warp: lane i evaluates one of the six sin / cos values (a double-precision
+// sin or cos is ~150 dependent instructions; one after the other they cost ~2 us at the head of every LM
+// iteration), lane 0 assembles the matrix.  Identical values: every lane runs the same scalar routine on the same
+// argument as pose_to_affine_dev.  Call with the full warp converged.
+__device__ inline void pose_to_affine_warp(const float* pose, Affine* T, Trig* g) {
+    const int lane = threadIdx.x & 31;
+    float v = 0.f;
+    if (lane < 6) {
+        const double ang = (double)pose[2 - (lane >> 1)];          // lanes 0,1: yaw; 2,3: pitch; 4,5: roll
+        v = (lane & 1) ? (float)sin(ang) : (float)cos(ang);
+    }
+    const float A = __shfl_sync(0xffffffffu, v, 0), B = __shfl_sync(0xffffffffu, v, 1);
+    const float C = __shfl_sync(0xffffffffu, v, 2), D = __shfl_sync(0xffffffffu, v, 3);
+    const float E = __shfl_sync(0xffffffffu, v, 4), F = __shfl_sync(0xffffffffu, v, 5);
+    if (lane == 0) {
+        const float DE = D * E, DF = D * F;
+        T->m[0] = A * C;  T->m[1] = A * DF - B * E;  T->m[2]  = B * F + A * DE;  T->m[3]  = pose[3];
+        T->m[4] = B * C;  T->m[5] = A * E + B * DF;  T->m[6]  = B * DE - A * F;  T->m[7]  = pose[4];
+        T->m[8] = -D;     T->m[9] = C * F;           T->m[10] = C * E;           T->m[11] = pose[5];
+        g->srx = D; g->crx = C; g->sry = B; g->cry = A; g->srz = F; g->crz = E;
+    }
 }
 
 }  // namespace lvreg

@@ -23,7 +23,10 @@
 // inside the searched cube (or the whole grid was visited).
 #pragma once
 
+#include <cooperative_groups.h>
+
 #include "common.cuh"
+#include "prims.cuh"
 
 namespace lvreg {
 
@@ -684,6 +687,83 @@ __global__ void __launch_bounds__(256) cell_scatter_kernel(const float4* __restr
     if (i >= m) return;
     float4 p = pts[i];
     out[__ldg(cell_start + keys[i]) + ranks[i]] = make_float4(p.x, p.y, p.z, __uint_as_float(i));
+}
+
+// The whole dense-directory build for small maps as ONE cooperative launch: count + rank, exclusive scan of the
+// cell counts (block chunk sums -> grid barrier -> every block adds the chunks before its own), scatter.  Six
+// launches of a few microseconds each become one (C1 / C2 / C5: the grid build is pure launch latency).
+constexpr int kGridMidThreads = 256;
+constexpr uint32_t kGridMidMaxPoints = 1u << 18, kGridMidMaxCells = 1u << 20;
+__global__ void __launch_bounds__(kGridMidThreads) grid_build_mid_kernel(const float4* __restrict__ pts, uint32_t m, GridSpec gs,
+                                                                         uint32_t ncells, uint32_t* __restrict__ keys,
+                                                                         uint32_t* __restrict__ ranks,
+                                                                         uint32_t* __restrict__ counts /* zeroed, ncells + 1 */,
+                                                                         uint32_t* __restrict__ chunk_sums /* gridDim.x */,
+                                                                         uint32_t* __restrict__ cell_start /* ncells + 1 */,
+                                                                         float4* __restrict__ out) {
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    __shared__ uint32_t red[kGridMidThreads / 32];
+    __shared__ uint32_t before_s;
+    const uint32_t nthreads = gridDim.x * kGridMidThreads, gtid = blockIdx.x * kGridMidThreads + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (uint32_t i = gtid; i < m; i += nthreads) {
+        const float4 p = pts[i];
+        float u;
+        const int cx = cell_coord(p.x, gs.ox, gs.inv, gs.dx, &u);
+        const int cy = cell_coord(p.y, gs.oy, gs.inv, gs.dy, &u);
+        const int cz = cell_coord(p.z, gs.oz, gs.inv, gs.dz, &u);
+        const uint32_t key = ((uint32_t)cz * gs.dy + cy) * gs.dx + cx;
+        keys[i] = key;
+        ranks[i] = atomicAdd(&counts[key], 1u);
+    }
+    __threadfence();
+    grid.sync();
+    // block b scans the contiguous chunk [b * per, (b + 1) * per) of the ncells + 1 counts
+    const uint32_t total = ncells + 1;
+    const uint32_t per = (total + gridDim.x - 1) / gridDim.x;
+    const uint32_t c0 = min(blockIdx.x * per, total), c1 = min(c0 + per, total);
+    uint32_t s = 0;
+    for (uint32_t i = c0 + threadIdx.x; i < c1; i += kGridMidThreads) s += counts[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) red[warp] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int w = 0; w < kGridMidThreads / 32; ++w) t += red[w];
+        chunk_sums[blockIdx.x] = t;
+    }
+    __threadfence();
+    grid.sync();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (uint32_t b = 0; b < blockIdx.x; ++b) t += chunk_sums[b];
+        before_s = t;
+    }
+    __syncthreads();
+    // exclusive scan of the chunk, 256 cells per step, carried in index order
+    uint32_t carry = before_s;
+    for (uint32_t i0 = c0; i0 < c1; i0 += kGridMidThreads) {
+        const uint32_t i = i0 + threadIdx.x;
+        const uint32_t v = i < c1 ? counts[i] : 0u;
+        uint32_t inc = warp_inclusive_scan(v, lane);
+        __syncthreads();
+        if (lane == 31) red[warp] = inc;
+        __syncthreads();
+        uint32_t wpre = 0, all = 0;
+        for (int w = 0; w < kGridMidThreads / 32; ++w) {
+            if (w < warp) wpre += red[w];
+            all += red[w];
+        }
+        if (i < c1) cell_start[i] = carry + wpre + inc - v;
+        carry += all;
+    }
+    __threadfence();
+    grid.sync();
+    for (uint32_t i = gtid; i < m; i += nthreads) {
+        const float4 p = pts[i];
+        out[cell_start[keys[i]] + ranks[i]] = make_float4(p.x, p.y, p.z, __uint_as_float(i));
+    }
 }
 
 struct CountIn {

@@ -656,6 +656,26 @@ int build_grid(lvreg_handle* h, Lane& L, MapSide& ms, const float* bb_min, const
     CK(L.scan_temp.reserve((size_t)(scan_num_tiles(ncells + 1) + 2) * 4));
     // counting sort by cell: count (the atomic also ranks the point inside its cell), scan, scatter
     CK(cudaMemsetAsync(L.scan_in.p, 0, (size_t)(ncells + 1) * 4, L.st));
+    if (m <= kGridMidMaxPoints && ncells <= kGridMidMaxCells && h->vg_mid_enabled) {       // small map: one cooperative launch
+        uint32_t blocks = nblk(m > ncells ? m : ncells, kGridMidThreads * 4);
+        if (blocks > (uint32_t)h->num_sms) blocks = (uint32_t)h->num_sms;
+        if (blocks < 1) blocks = 1;
+        CK(L.scan_temp.reserve((size_t)(blocks + 2) * 4 + (size_t)(scan_num_tiles(ncells + 1) + 2) * 4));
+        const float4* pts_c = pts;
+        uint32_t* keys_p = L.keys[0].as<uint32_t>();
+        uint32_t* ranks_p = L.vals[0].as<uint32_t>();
+        uint32_t* counts_p = L.scan_in.as<uint32_t>();
+        uint32_t* chunk_p = L.scan_temp.as<uint32_t>();
+        uint32_t* start_p = ms.cell_start.as<uint32_t>();
+        float4* out_p = ms.cell_pts.as<float4>();
+        uint32_t m_c = m, nc_c = ncells;
+        void* kargs[] = {&pts_c, &m_c, &gs, &nc_c, &keys_p, &ranks_p, &counts_p, &chunk_p, &start_p, &out_p};
+        CK(cudaLaunchCooperativeKernel((void*)grid_build_mid_kernel, dim3(blocks), dim3(kGridMidThreads), kargs, 0, L.st));
+        launched(h);
+        CK(cudaGetLastError());
+        ms.gs = gs;
+        return LVREG_OK;
+    }
     cell_count_kernel<<<nblk(m, 256), 256, 0, L.st>>>(pts, m, gs, L.keys[0].as<uint32_t>(), L.vals[0].as<uint32_t>(),
                                                       L.scan_in.as<uint32_t>());
     launched(h);

@@ -131,10 +131,8 @@ __global__ void __launch_bounds__(kRegThreads, 2) register_warm_kernel(RegArgs a
     int iter = 0;
     int converged = 0;
     for (; iter < P.max_iters; ++iter) {
-        if (threadIdx.x == 0) {
-            if (blockIdx.x == 0) a.out->stamp[iter][0] = gtimer();
-            pose_to_affine_dev(sPose, &sT, &sTrig);
-        }
+        if (blockIdx.x == 0 && threadIdx.x == 0) a.out->stamp[iter][0] = gtimer();
+        if (warp == 0) pose_to_affine_warp(sPose, &sT, &sTrig);
         __syncthreads();
         const Affine T = sT;
         const Trig trig = sTrig;
@@ -214,10 +212,22 @@ __global__ void __launch_bounds__(kRegThreads, 2) register_warm_kernel(RegArgs a
         if (blockIdx.x == 0 && threadIdx.x == 0) a.out->stamp[iter][2] = gtimer();
         {
             const double* all = a.partials + (size_t)(iter & 1) * gridDim.x * kRegTerms;
+            // 8 chains per term, each with 4 independent accumulators (loads in flight instead of one dependent
+            // add per L2 round trip); every partial keeps a fixed place in a fixed order
             const int t = threadIdx.x % 32, chain = threadIdx.x / 32;
             double s = 0.0;
-            if (t < kRegTerms)
-                for (uint32_t b = chain; b < gridDim.x; b += kRegWarps) s += all[(size_t)b * kRegTerms + t];
+            if (t < kRegTerms) {
+                double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+                uint32_t b = chain;
+                for (; b + 3 * kRegWarps < gridDim.x; b += 4 * kRegWarps) {
+                    s0 += all[(size_t)b * kRegTerms + t];
+                    s1 += all[(size_t)(b + kRegWarps) * kRegTerms + t];
+                    s2 += all[(size_t)(b + 2 * kRegWarps) * kRegTerms + t];
+                    s3 += all[(size_t)(b + 3 * kRegWarps) * kRegTerms + t];
+                }
+                for (; b < gridDim.x; b += kRegWarps) s0 += all[(size_t)b * kRegTerms + t];
+                s = (s0 + s1) + (s2 + s3);
+            }
             __syncthreads();
             if (t < kRegTerms) sRed[chain][t] = s;
             __syncthreads();

@@ -365,7 +365,7 @@ def test_local_map_build_and_register_scan_vs_oracle(lv, room):
     assert res.iterations == rres.iterations and res.converged == rres.converged
     assert _pose_close(pose, rpose)
     t = hd.timings()
-    assert t.kernel_launches > 10 and t.register_ms > 0 and t.map_build_ms > 0
+    assert t.kernel_launches >= 4 and t.register_ms > 0 and t.map_build_ms > 0      # a handful of fused launches
     # after a pose correction (loop closure) the map must be rebuilt
     hd.update_keyframe_poses(np.array(poses) + np.float32(0.001))
     _, _, st = hd.scan2map(guess)
