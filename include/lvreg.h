@@ -190,9 +190,14 @@ int lvreg_scan2map(lvreg_handle* h, float pose_rpyxyz[6], lvreg_result* res);
  * scan2MapOptimization, i.e. the body of laserCloudInfoHandler MO:318-322. */
 int lvreg_register_scan(lvreg_handle* h, const lvreg_cloud* corner_raw, const lvreg_cloud* surf_raw,
                         const int32_t* ids, size_t n_ids, float pose_rpyxyz[6], lvreg_result* res);
-/* transformUpdate (MO:1345-1375): optional IMU roll/pitch slerp + clamps.  Host arithmetic. */
+/* transformUpdate (MO:1345-1375) as a stand-alone stage: optional IMU roll/pitch slerp, THEN the clamps of
+ * roll / pitch / z (the reference's order).  Host arithmetic. */
 int lvreg_transform_update(const lvreg_handle* h, float pose_rpyxyz[6], int imu_available,
                            float imu_roll_init, float imu_pitch_init);
+/* cloudInfo.imu_available / imu_roll_init / imu_pitch_init of the scan about to be registered (MO:1347-1366).
+ * lvreg_scan2map / lvreg_register_scan end with transformUpdate exactly like scan2MapOptimization (MO:1339): blend
+ * towards this IMU attitude when available, then clamp once.  Sticky until changed; default: not available. */
+int lvreg_set_imu_prior(lvreg_handle* h, int imu_available, float imu_roll_init, float imu_pitch_init);
 /* isDegenerate (MO:131) persists across scans in the reference; read / reset it here. */
 int lvreg_get_degenerate(const lvreg_handle* h, int* is_degenerate);
 int lvreg_reset_lm_state(lvreg_handle* h);

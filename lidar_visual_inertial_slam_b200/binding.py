@@ -356,6 +356,9 @@ class Lvreg:
                                                C.c_float(imu_roll), C.c_float(imu_pitch)))
         return pose
 
+    def set_imu_prior(self, imu_available, imu_roll=0.0, imu_pitch=0.0):
+        self._ck(self.L.lvreg_set_imu_prior(self.h, int(bool(imu_available)), C.c_float(imu_roll), C.c_float(imu_pitch)))
+
     def get_degenerate(self):
         v = C.c_int(0)
         self._ck(self.L.lvreg_get_degenerate(self.h, C.byref(v)))

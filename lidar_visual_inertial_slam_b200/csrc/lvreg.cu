@@ -38,18 +38,27 @@ static thread_local int g_alloc_calls = 0;
 // bump allocator over large slabs: keyframe clouds come from here, so adding a keyframe does not call
 // cudaMalloc (one slab holds hundreds of keyframes); everything is returned when the handle is destroyed
 struct Arena {
-    std::vector<void*> slabs;
+    struct Slab { void* p; size_t bytes; };
+    std::vector<Slab> slabs;
+    size_t next_slab = 0;            // slabs[0 .. next_slab) are in use, the rest is free for re-use after reset()
     char* cur = nullptr;
     size_t left = 0;
     size_t slab_bytes = (size_t)64 << 20;
     cudaError_t alloc(size_t bytes, void** out) {
         bytes = (bytes + 255) & ~(size_t)255;
-        if (bytes > left) {
+        while (bytes > left) {
+            if (next_slab < slabs.size()) {                 // a slab kept from an earlier session
+                cur = (char*)slabs[next_slab].p;
+                left = slabs[next_slab].bytes;
+                ++next_slab;
+                continue;
+            }
             const size_t sz = bytes > slab_bytes ? bytes : slab_bytes;
             void* p = nullptr;
             cudaError_t e = cudaMalloc(&p, sz);
             if (e != cudaSuccess) return e;
-            slabs.push_back(p);
+            slabs.push_back({p, sz});
+            next_slab = slabs.size();
             cur = (char*)p;
             left = sz;
         }
@@ -58,11 +67,17 @@ struct Arena {
         left -= bytes;
         return cudaSuccess;
     }
-    void release_all() {
-        for (void* p : slabs) cudaFree(p);
-        slabs.clear();
+    // every block is handed back at once (no keyframe is live): the slabs stay allocated and are filled again from
+    // the start, so repeated sessions on one handle do not grow device memory
+    void reset() {
+        next_slab = 0;
         cur = nullptr;
         left = 0;
+    }
+    void release_all() {
+        for (const Slab& sl : slabs) cudaFree(sl.p);
+        slabs.clear();
+        reset();
     }
 };
 
@@ -155,6 +170,8 @@ struct lvreg_handle {
     int num_sms = kNumSMs;
     int lpq = 4;
     int tile = 16;
+    int imu_available = 0;        // cloudInfo.imu_available / imu_roll_init / imu_pitch_init of the current scan (MO:1347-1366)
+    float imu_roll = 0.f, imu_pitch = 0.f;
     bool vg_mid_enabled = true;   // LVREG_VG_MID=0 disables the cooperative single-launch VoxelGrid (experiments)
     int debug_tiles = 0;          // LVREG_DEBUG_TILES=1: record per-tile durations of iteration 1
     uint32_t debug_ntiles = 0;
@@ -269,6 +286,29 @@ inline cudaError_t lanes_sync(lvreg_handle* h, unsigned mask) {   // ONE host wa
     lanes_join(h, mask);
     return cudaStreamSynchronize(h->st);
 }
+
+// A failing call must not leave half-built state behind: unless commit() is reached, the lanes are joined and
+// drained and whatever the call was rebuilding is marked empty / invalid, so that a later lvreg_scan2map cannot run
+// on counts and data that do not belong together.
+struct CallGuard {
+    lvreg_handle* h;
+    bool scan, map;
+    bool ok = false;
+    CallGuard(lvreg_handle* h_, bool touches_scan, bool touches_map) : h(h_), scan(touches_scan), map(touches_map) {}
+    void commit() { ok = true; }
+    ~CallGuard() {
+        if (ok) return;
+        lanes_join(h, (1u << kLanes) - 1u);
+        cudaStreamSynchronize(h->st);
+        cudaGetLastError();
+        if (scan) {
+            h->n_scan[0] = h->n_scan[1] = 0;
+            h->scan_sorted_ok[0] = h->scan_sorted_ok[1] = false;
+        }
+        if (map) h->map[0].valid = h->map[1].valid = false;
+        h->total_launches += (uint64_t)h->call_launches;
+    }
+};
 
 // ---- cloud transfer ----------------------------------------------------------------------------
 int check_cloud(lvreg_handle* h, const lvreg_cloud* c) {
@@ -839,6 +879,25 @@ float clampf(float v, float lim) {
     return v;
 }
 
+// transformUpdate (MO:1345-1375) in the reference's order: the IMU blend of roll and pitch first, then ONE clamp of
+// roll, pitch and z (constraintTransformation, MO:1377-1385)
+void transform_update_host(const lvreg_params& prm, float pose[6], int imu_available, float imu_roll, float imu_pitch) {
+    if (imu_available && fabs((double)imu_pitch) < 1.4) {
+        // tf2 slerp of two rotations about one axis == interpolation of the angle along the
+        // shortest arc (MO:1349-1366), evaluated in double like tf2
+        const double w = prm.imu_rpy_weight;
+        auto slerp_angle = [](double a, double b, double t) {
+            double d = remainder(b - a, 2.0 * M_PI);
+            return remainder(a + t * d, 2.0 * M_PI);
+        };
+        pose[0] = (float)slerp_angle(pose[0], imu_roll, w);
+        pose[1] = (float)slerp_angle(pose[1], imu_pitch, w);
+    }
+    pose[0] = clampf(pose[0], prm.rotation_tolerance);
+    pose[1] = clampf(pose[1], prm.rotation_tolerance);
+    pose[5] = clampf(pose[5], prm.z_tolerance);
+}
+
 template <int LPQ, int TILE>
 int launch_register(lvreg_handle* h, RegArgs& args, int grid) {
     void* kargs[] = {&args};
@@ -987,10 +1046,8 @@ int scan2map_impl(lvreg_handle* h, float pose[6], lvreg_result* res) {
     mark(h, EV_REG);
     CK(cudaStreamSynchronize(h->st));
     for (int i = 0; i < 6; ++i) pose[i] = ho->pose[i];
-    // transformUpdate's clamps (MO:1370-1372); the IMU slerp is lvreg_transform_update
-    pose[0] = clampf(pose[0], h->prm.rotation_tolerance);
-    pose[1] = clampf(pose[1], h->prm.rotation_tolerance);
-    pose[5] = clampf(pose[5], h->prm.z_tolerance);
+    // transformUpdate (MO:1339): IMU blend (lvreg_set_imu_prior) first, then the clamps, as the reference orders them
+    transform_update_host(h->prm, pose, h->imu_available, h->imu_roll, h->imu_pitch);
     if (res) {
         res->iterations = ho->iterations;
         res->converged = ho->converged;
@@ -1318,7 +1375,8 @@ int lvreg_add_keyframe_from_scan(lvreg_handle* h, const float pose[6], int32_t* 
         }
         kf->n[s] = n;
     }
-    CK(cudaStreamSynchronize(h->st));
+    // no host synchronisation: every later use of the keyframe is ordered behind these copies on the handle's stream
+    // (the lanes fork from it)
     memcpy(kf->pose, pose, sizeof(kf->pose));
     h->kfs.push_back(kf);
     if (id_out) *id_out = (int32_t)h->kfs.size() - 1;
@@ -1345,15 +1403,19 @@ int lvreg_clear_keyframes(lvreg_handle* h) {
     if (!h) return LVREG_ERR_INVALID;
     CK(cudaSetDevice(h->device));
     CK(cudaStreamSynchronize(h->st));
-    // keep the buffers for the next session (bounded: a long session is not pinned in memory for ever)
+    // no keyframe stays live: hand every cloud back to the arena at once (its slabs are kept and refilled from the
+    // start, so replaying session after session on one handle neither allocates nor grows) and recycle the objects
     for (Keyframe* kf : h->kfs) {
+        kf->cloud[0].p = kf->cloud[1].p = nullptr;
+        kf->cloud[0].cap = kf->cloud[1].cap = 0;
         if (h->kf_free.size() < 4096) h->kf_free.push_back(kf);
-        else {
-            kf->cloud[0].release();
-            kf->cloud[1].release();
-            delete kf;
-        }
+        else delete kf;
     }
+    for (Keyframe* kf : h->kf_free) {
+        kf->cloud[0].p = kf->cloud[1].p = nullptr;
+        kf->cloud[0].cap = kf->cloud[1].cap = 0;
+    }
+    h->kf_arena.reset();
     h->kfs.clear();
     h->map[0].valid = h->map[1].valid = false;
     return LVREG_OK;
@@ -1366,6 +1428,7 @@ int lvreg_build_local_map(lvreg_handle* h, const int32_t* ids, size_t n, lvreg_m
     begin_call(h);
     mark(h, EV_BEGIN);
     VgJob jobs[2];
+    CallGuard guard(h, false, true);
     CKS(prepare_map_jobs(h, ids, n, jobs));
     lanes_fork(h, 0x3);
     CKS(voxelgrid_batch(h, jobs, 2));
@@ -1375,6 +1438,7 @@ int lvreg_build_local_map(lvreg_handle* h, const int32_t* ids, size_t n, lvreg_m
     lanes_join(h, 0x3);
     mark(h, EV_GRID);
     CK(cudaStreamSynchronize(h->st));
+    guard.commit();
     h->last.map_build_ms = span(h, EV_BEGIN, EV_MAP);
     h->last.grid_build_ms = span(h, EV_MAP, EV_GRID);
     finish_timings(h);
@@ -1390,6 +1454,7 @@ int lvreg_set_local_map(lvreg_handle* h, const lvreg_cloud* corner_ds, const lvr
     begin_call(h);
     mark(h, EV_BEGIN);
     const lvreg_cloud* c[2] = {corner_ds, surf_ds};
+    CallGuard guard(h, false, true);
     lanes_fork(h, 0x3);
     for (int s = 0; s < 2; ++s) {
         Lane& L = h->lane[s];
@@ -1404,6 +1469,7 @@ int lvreg_set_local_map(lvreg_handle* h, const lvreg_cloud* corner_ds, const lvr
     lanes_join(h, 0x3);
     mark(h, EV_GRID);
     CK(cudaStreamSynchronize(h->st));
+    guard.commit();
     h->last.upload_ms = span(h, EV_BEGIN, EV_MAP);
     h->last.grid_build_ms = span(h, EV_MAP, EV_GRID);
     finish_timings(h);
@@ -1429,6 +1495,7 @@ int lvreg_downsample_scan(lvreg_handle* h, const lvreg_cloud* corner_raw, const 
     begin_call(h);
     mark(h, EV_BEGIN);
     VgJob jobs[2];
+    CallGuard guard(h, true, false);
     lanes_fork(h, 0xc);
     CKS(prepare_scan_jobs(h, corner_raw, surf_raw, jobs));
     CKS(voxelgrid_batch(h, jobs, 2));
@@ -1438,6 +1505,7 @@ int lvreg_downsample_scan(lvreg_handle* h, const lvreg_cloud* corner_raw, const 
     lanes_join(h, 0xc);
     mark(h, EV_DS);
     CK(cudaStreamSynchronize(h->st));
+    guard.commit();
     h->last.downsample_ms = span(h, EV_BEGIN, EV_DS);      // includes the H2D + pack of the two clouds
     finish_timings(h);
     end_call(h);
@@ -1450,9 +1518,11 @@ int lvreg_set_scan_ds(lvreg_handle* h, const lvreg_cloud* corner_ds, const lvreg
     if (!h) return LVREG_ERR_INVALID;
     CK(cudaSetDevice(h->device));
     begin_call(h);
+    CallGuard guard(h, true, false);
     CKS(upload_cloud(h, corner_ds, h->scan_ds[0], h->lane[LANE_SCAN_CORNER].stage, h->st));
     CKS(upload_cloud(h, surf_ds, h->scan_ds[1], h->lane[LANE_SCAN_SURF].stage, h->st));
     CK(cudaStreamSynchronize(h->st));
+    guard.commit();
     h->n_scan[0] = (uint32_t)corner_ds->n;
     h->n_scan[1] = (uint32_t)surf_ds->n;
     h->scan_sorted_ok[0] = h->scan_sorted_ok[1] = false;      // ordered by the next lvreg_scan2map
@@ -1494,6 +1564,7 @@ int lvreg_register_scan(lvreg_handle* h, const lvreg_cloud* corner_raw, const lv
     VgJob jobs[4];
     int nj = 0;
     unsigned mask = 0xc;
+    CallGuard guard(h, true, ids != nullptr);
     if (ids) {
         CKS(prepare_map_jobs(h, ids, n_ids, jobs));
         nj = 2;
@@ -1519,6 +1590,7 @@ int lvreg_register_scan(lvreg_handle* h, const lvreg_cloud* corner_raw, const lv
                 g_alloc_bytes / 1048576.0, g_alloc_ms);
         g_alloc_ms = 0.0; g_alloc_bytes = 0; g_alloc_calls = 0;
     }
+    guard.commit();                                            // scan and map are consistent from here on
     int s = scan2map_impl(h, pose, res);                      // scan2MapOptimization MO:322
     if (s == LVREG_OK || s == LVREG_ERR_NOT_ENOUGH_FEATURES) {
         CK(cudaStreamSynchronize(h->st));
@@ -1536,20 +1608,15 @@ int lvreg_register_scan(lvreg_handle* h, const lvreg_cloud* corner_raw, const lv
 int lvreg_transform_update(const lvreg_handle* h, float pose[6], int imu_available, float imu_roll,
                            float imu_pitch) {
     if (!h || !pose) return LVREG_ERR_INVALID;
-    if (imu_available && fabs((double)imu_pitch) < 1.4) {
-        // tf2 slerp of two rotations about one axis == interpolation of the angle along the
-        // shortest arc (MO:1349-1366), evaluated in double like tf2
-        const double w = h->prm.imu_rpy_weight;
-        auto slerp_angle = [](double a, double b, double t) {
-            double d = remainder(b - a, 2.0 * M_PI);
-            return remainder(a + t * d, 2.0 * M_PI);
-        };
-        pose[0] = (float)slerp_angle(pose[0], imu_roll, w);
-        pose[1] = (float)slerp_angle(pose[1], imu_pitch, w);
-    }
-    pose[0] = clampf(pose[0], h->prm.rotation_tolerance);
-    pose[1] = clampf(pose[1], h->prm.rotation_tolerance);
-    pose[5] = clampf(pose[5], h->prm.z_tolerance);
+    transform_update_host(h->prm, pose, imu_available, imu_roll, imu_pitch);
+    return LVREG_OK;
+}
+
+int lvreg_set_imu_prior(lvreg_handle* h, int imu_available, float imu_roll, float imu_pitch) {
+    if (!h) return LVREG_ERR_INVALID;
+    h->imu_available = imu_available ? 1 : 0;
+    h->imu_roll = imu_roll;
+    h->imu_pitch = imu_pitch;
     return LVREG_OK;
 }
 

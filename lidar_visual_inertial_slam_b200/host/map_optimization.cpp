@@ -85,6 +85,50 @@ static inline float pointDistance(const PointType& a, const PointType& b) {
     return std::sqrt((a.x - b.x) * (a.x - b.x) + (a.y - b.y) * (a.y - b.y) + (a.z - b.z) * (a.z - b.z));
 }
 
+// pcl::VoxelGrid over a few hundred KEY POSES (downSizeFilterSurroundingKeyPoses MO:910-911,
+// downSizeFilterGlobalMapKeyPoses MO:484-486): keyframe-selection logic, host-side by design.  Same
+// algorithm as the device filter: PCL's fp32 bounds and idx arithmetic, a stable order inside a voxel,
+// one output per voxel in ascending idx with sequential fp32 sums and a true division; "leaf too small" returns
+// the input.  A device call here would cost a launch sequence and a host synchronisation per incoming scan.
+static void voxelgrid_key_poses(const Cloud& in, float leaf, Cloud* out) {
+    out->clear();
+    if (in.empty()) return;
+    float mn[3] = {in[0].x, in[0].y, in[0].z}, mx[3] = {in[0].x, in[0].y, in[0].z};
+    for (const PointType& p : in) {
+        mn[0] = std::fmin(mn[0], p.x); mn[1] = std::fmin(mn[1], p.y); mn[2] = std::fmin(mn[2], p.z);
+        mx[0] = std::fmax(mx[0], p.x); mx[1] = std::fmax(mx[1], p.y); mx[2] = std::fmax(mx[2], p.z);
+    }
+    const float inv = 1.0f / leaf;
+    int64_t d[3];
+    for (int a = 0; a < 3; ++a) d[a] = (int64_t)((mx[a] - mn[a]) * inv) + 1;
+    if (d[0] * d[1] * d[2] > (int64_t)INT32_MAX) { *out = in; return; }
+    int min_b[3], div_b[3];
+    for (int a = 0; a < 3; ++a) {
+        min_b[a] = (int)std::floor(mn[a] * inv);
+        div_b[a] = (int)std::floor(mx[a] * inv) - min_b[a] + 1;
+    }
+    const int mul[3] = {1, div_b[0], div_b[0] * div_b[1]};
+    std::vector<std::pair<uint32_t, uint32_t>> keyed(in.size());
+    for (size_t i = 0; i < in.size(); ++i) {
+        const int ix = (int)(std::floor(in[i].x * inv) - (float)min_b[0]);
+        const int iy = (int)(std::floor(in[i].y * inv) - (float)min_b[1]);
+        const int iz = (int)(std::floor(in[i].z * inv) - (float)min_b[2]);
+        keyed[i] = {(uint32_t)(ix * mul[0] + iy * mul[1] + iz * mul[2]), (uint32_t)i};
+    }
+    std::sort(keyed.begin(), keyed.end());               // (idx, input index): the stable order
+    for (size_t b = 0; b < keyed.size();) {
+        size_t e = b;
+        float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
+        for (; e < keyed.size() && keyed[e].first == keyed[b].first; ++e) {
+            const PointType& p = in[keyed[e].second];
+            sx += p.x; sy += p.y; sz += p.z; si += p.intensity;
+        }
+        const float c = (float)(e - b);
+        out->push_back(make_point(sx / c, sy / c, sz / c, si / c));
+        b = e;
+    }
+}
+
 std::vector<int32_t> mapOptimization::extractNearby() {
     std::vector<int32_t> ids;
     const size_t K = cloudKeyPoses3D.size();
@@ -104,17 +148,9 @@ std::vector<int32_t> mapOptimization::extractNearby() {
     std::sort(hits.begin(), hits.end());
     Cloud surroundingKeyPoses(hits.size());
     for (size_t i = 0; i < hits.size(); ++i) surroundingKeyPoses[i] = cloudKeyPoses3D[hits[i].second];
-    // downSizeFilterSurroundingKeyPoses (2.0 m VoxelGrid) MO:910-911 -- on the GPU, same kernels
-    Cloud surroundingKeyPosesDS(surroundingKeyPoses.size());
-    size_t nds = 0;
-    {
-        lvreg_cloud in = as_lvreg_cloud(surroundingKeyPoses);
-        lvreg_cloud_out out = as_lvreg_out(surroundingKeyPosesDS);
-        int pt = 0;
-        int st = lvreg_voxelgrid(h_, &in, P_.surroundingKeyframeDensity, &out, &nds, nullptr, &pt);
-        if (st != LVREG_OK) throw std::runtime_error(std::string("lvreg_voxelgrid: ") + lvreg_last_error(h_));
-    }
-    surroundingKeyPosesDS.resize(nds);
+    // downSizeFilterSurroundingKeyPoses (2.0 m VoxelGrid) MO:910-911
+    Cloud surroundingKeyPosesDS;
+    voxelgrid_key_poses(surroundingKeyPoses, P_.surroundingKeyframeDensity, &surroundingKeyPosesDS);
     // 1-NN back to a real key pose to recover the integer id (MO:912-916)
     for (PointType& pt : surroundingKeyPosesDS) {
         float best = INFINITY;
@@ -324,6 +360,7 @@ void mapOptimization::scan2MapOptimization() {
         lastStatus = LVREG_ERR_NO_KEYFRAMES;
         return;
     }
+    lvreg_set_imu_prior(h_, imuAvailable ? 1 : 0, imuRollInit, imuPitchInit);      // consumed by transformUpdate, MO:1339
     lastStatus = lvreg_scan2map(h_, transformTobeMapped, &lastResult);
     if (lastStatus == LVREG_ERR_NOT_ENOUGH_FEATURES) {
         std::fprintf(stderr, "Not enough features! Only %d edge and %d planar features available.\n",
@@ -331,9 +368,7 @@ void mapOptimization::scan2MapOptimization() {
         return;
     }
     if (lastStatus != LVREG_OK) throw std::runtime_error(std::string("lvreg_scan2map: ") + lvreg_last_error(h_));
-    isDegenerate = lastResult.degenerate != 0;
-    // transformUpdate (MO:1345-1375): the clamps were applied by lvreg_scan2map; IMU slerp here
-    if (imuAvailable) lvreg_transform_update(h_, transformTobeMapped, 1, imuRollInit, imuPitchInit);
+    isDegenerate = lastResult.degenerate != 0;        // transformUpdate (MO:1345-1375) ran inside lvreg_scan2map
     lvreg_timings t;
     lvreg_get_timings(h_, &t);
     lastTimings.register_ms = t.register_ms;
@@ -480,6 +515,7 @@ bool mapOptimization::laserCloudInfoHandler(const Cloud& corner, const Cloud& su
     // down-sampling run concurrently on the device and share their host synchronisations
     std::vector<int32_t> ids = extractNearby();
     const bool rebuild = mapDirty_ || ids != lastIds_;
+    lvreg_set_imu_prior(h_, imuAvailable ? 1 : 0, imuRollInit, imuPitchInit);
     lvreg_cloud c, s;
     c.data = pinCorner_.p; c.n = pinCorner_.n; c.stride = sizeof(PointType); c.intensity_offset = 16; c.on_device = 0; c.reserved = 0;
     s = c;
@@ -503,8 +539,7 @@ bool mapOptimization::laserCloudInfoHandler(const Cloud& corner, const Cloud& su
         std::fprintf(stderr, "Not enough features! Only %d edge and %d planar features available.\n",
                      laserCloudCornerLastDSNum, laserCloudSurfLastDSNum);          // MO:1341
     } else {
-        isDegenerate = lastResult.degenerate != 0;
-        if (imuAvailable) lvreg_transform_update(h_, transformTobeMapped, 1, imuRollInit, imuPitchInit);
+        isDegenerate = lastResult.degenerate != 0;        // transformUpdate (MO:1339) ran inside the call (IMU prior set above)
     }
     saveKeyFramesAndFactor();
     return true;

@@ -381,6 +381,36 @@ def test_transform_update(lv, h):
     assert np.allclose(a, b, atol=1e-6)
 
 
+def test_transform_update_order_inside_scan2map(lv, room):
+    """MO:1345-1372: the IMU blend comes first, the clamp once after it.  With a tight rotation tolerance the two
+    orders differ (clamp -> blend -> clamp pulls the clamped angle towards the IMU value; blend -> clamp clamps the
+    blended angle): the registration call must give the reference's."""
+    prm = lv.default_params()
+    prm.rotation_tolerance = 0.015
+    prm.z_tolerance = 0.15
+    prm.imu_rpy_weight = 0.5
+    hd = lv.Lvreg(prm)
+    hd.set_local_map(room["cm"], room["sm"])
+    hd.set_scan_ds(room["cds"], room["sds"])
+    imu_roll, imu_pitch = -0.02, 0.03          # pulls the (out-of-tolerance) LM angles back inside the tolerance
+    hd.set_imu_prior(True, imu_roll, imu_pitch)
+    pose, res, st = hd.scan2map(room["guess"])
+    assert st == lv.OK
+    raw = np.array(res.pose_iter)[res.iterations - 1].astype(np.float32)       # transformTobeMapped before transformUpdate
+    op = O.default_params(rotation_tolerance=0.015, z_tolerance=0.15)
+    want = O.transform_update(raw, True, imu_roll, imu_pitch, 0.5, op)
+    assert np.allclose(pose, want, atol=1e-6)
+    # the other order would have given something else
+    wrong = O.transform_update(O.transform_update(raw, False, 0, 0, 0.5, op), True, imu_roll, imu_pitch, 0.5, op)
+    assert np.abs(raw[:2]).max() > 0.015 and np.abs(wrong - want).max() > 1e-3
+    # without a prior: clamps only
+    hd.set_imu_prior(False)
+    hd.reset_lm_state()
+    pose2, _, _ = hd.scan2map(room["guess"])
+    assert np.allclose(pose2, O.transform_update(raw, False, 0, 0, 0.5, op), atol=1e-6)
+    hd.close()
+
+
 # ---- ragged / degenerate inputs ---------------------------------------------------------------------
 def test_ragged_inputs_through_the_scan_path(lv, room):
     hd = lv.Lvreg()
@@ -496,3 +526,62 @@ def test_hashed_cell_directory_sparse_kilometre_map(lv):
             h.close()
         finally:
             os.environ.pop("LVREG_REG", None)
+
+
+def test_failed_call_leaves_a_consistent_handle(lv, room):
+    """a call that fails half way (bad keyframe id, malformed second cloud) must not leave counts and data of
+    different scans / maps behind: the next registration reports 'no map' / 'not enough features'"""
+    hd = lv.Lvreg()
+    hd.add_keyframe(room["cm"], room["sm"], np.zeros(6, np.float32))
+    hd.build_local_map([0])
+    pose, res, st = hd.register_scan(room["c"], room["s"], None, room["guess"])
+    assert st == lv.OK
+    with pytest.raises(lv.LvregError):
+        hd.register_scan(room["c"], room["s"], np.array([5], np.int32), room["guess"])      # id out of range
+    _, _, st = hd.scan2map(room["guess"])
+    assert st in (lv.ERR_NO_MAP, lv.ERR_NOT_ENOUGH_FEATURES)
+    # malformed second cloud in set_scan_ds: the first upload already happened, the counts must not survive
+    hd.build_local_map([0])
+    hd.set_scan_ds(room["cds"], room["sds"])
+    from lidar_visual_inertial_slam_b200.binding import Cloud, _cloud
+    import ctypes as C
+    good, keep = _cloud(room["cds"])
+    bad = Cloud()
+    bad.data = None
+    bad.n = 10
+    bad.stride = 16
+    bad.intensity_offset = 12
+    assert hd.L.lvreg_set_scan_ds(hd.h, C.byref(good), C.byref(bad)) == lv.ERR_INVALID
+    _, _, st = hd.scan2map(room["guess"])
+    assert st == lv.ERR_NOT_ENOUGH_FEATURES
+    # and the handle still works
+    pose2, res2, st = hd.register_scan(room["c"], room["s"], np.array([0], np.int32), room["guess"])
+    assert st == lv.OK and np.array_equal(pose2, pose)
+    hd.close()
+
+
+def test_repeated_sessions_do_not_grow_device_memory(lv, room):
+    """lvreg_clear_keyframes hands the keyframe arena back: replaying session after session on one handle must
+    not allocate more and more device memory (keyframe clouds of changing sizes used to abandon their blocks)"""
+    import torch
+    hd = lv.Lvreg()
+    rng = np.random.default_rng(8)
+
+    def session(scale):
+        for k in range(24):
+            nc = int(len(room["cm"]) * scale * rng.uniform(0.5, 1.0))
+            ns = int(len(room["sm"]) * scale * rng.uniform(0.5, 1.0))
+            hd.add_keyframe(room["cm"][:nc], room["sm"][:ns], np.array([0, 0, 0, 0.01 * k, 0, 0], np.float32))
+        hd.build_local_map(np.arange(24, dtype=np.int32))
+        hd.clear_keyframes()
+
+    session(1.0)
+    session(1.0)
+    torch.cuda.synchronize()
+    free0 = torch.cuda.mem_get_info()[0]
+    for i in range(12):
+        session(0.3 + 0.7 * ((i * 7) % 10) / 10.0)
+    torch.cuda.synchronize()
+    free1 = torch.cuda.mem_get_info()[0]
+    assert free0 - free1 < (64 << 20), "device memory grew by %.1f MB over 12 sessions" % ((free0 - free1) / 1048576.0)
+    hd.close()
