@@ -9,6 +9,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <chrono>
 #include <deque>
 #include <string>
@@ -123,6 +124,11 @@ struct Keyframe {
     DevBuf cloud[2];          // sensor-frame corner / surf, float4
     uint32_t n[2] = {0, 0};
     float pose[6] = {0, 0, 0, 0, 0, 0};
+    // laserCloudMapContainer (MO:106, 942-954): the clouds under the keyframe's current pose, filled on first use and
+    // dropped when the poses are corrected (MO:1623), + their bounding boxes (exact: union of them = bbox of any map)
+    DevBuf world[2];
+    bool world_ok = false;
+    float wmn[2][3] = {{0, 0, 0}, {0, 0, 0}}, wmx[2][3] = {{0, 0, 0}, {0, 0, 0}};
 };
 
 struct DepthEntry {            // one entry of cloudQueue / timeQueue (feature_tracker_node.cpp:343-344)
@@ -172,6 +178,9 @@ struct lvreg_handle {
     int tile = 16;
     int imu_available = 0;        // cloudInfo.imu_available / imu_roll_init / imu_pitch_init of the current scan (MO:1347-1366)
     float imu_roll = 0.f, imu_pitch = 0.f;
+    int warm_tile = 32;
+    bool kf_cache_enabled = true; // LVREG_KF_CACHE=0: transform the keyframe clouds on every map build (experiments)
+    DevBuf kfmm;                  // bounding-box slots of the keyframe clouds being cached
     bool vg_mid_enabled = true;   // LVREG_VG_MID=0 disables the cooperative single-launch VoxelGrid (experiments)
     int debug_tiles = 0;          // LVREG_DEBUG_TILES=1: record per-tile durations of iteration 1
     uint32_t debug_ntiles = 0;
@@ -395,6 +404,7 @@ struct VgJob {
     const float4* pts = nullptr;       // device input (ignored when from_segments)
     uint32_t n = 0;
     bool from_segments = false;        // input = Lane::seg_host, transformed + concatenated into Lane::concat
+    bool cached = false;               // segments point at cached WORLD-frame clouds; mn / mx hold their exact bbox
     float leaf = 0.f;
     DevBuf* out = nullptr;
     uint32_t* n_out = nullptr;
@@ -498,6 +508,11 @@ int voxelgrid_batch(lvreg_handle* h, VgJob* jobs, int nj) {
             CK(cudaMemcpyAsync(L.pinned + 32, d_info, sizeof(VgSmallInfo), cudaMemcpyDeviceToHost, L.st));
             continue;
         }
+        if (J.cached) {                                // world-frame clouds and their exact bbox are already known
+            CK(L.segs.reserve(L.seg_host.size() * sizeof(Segment)));
+            CK(cudaMemcpyAsync(L.segs.p, L.seg_host.data(), L.seg_host.size() * sizeof(Segment), cudaMemcpyHostToDevice, L.st));
+            continue;
+        }
         uint32_t* mm = L.small.as<uint32_t>() + SM_MM;
         CK(cudaMemsetAsync(mm, 0xff, 3 * sizeof(uint32_t), L.st));
         CK(cudaMemsetAsync(mm + 3, 0, 3 * sizeof(uint32_t), L.st));
@@ -505,7 +520,7 @@ int voxelgrid_batch(lvreg_handle* h, VgJob* jobs, int nj) {
             CK(L.segs.reserve(L.seg_host.size() * sizeof(Segment)));
             CK(cudaMemcpyAsync(L.segs.p, L.seg_host.data(), L.seg_host.size() * sizeof(Segment), cudaMemcpyHostToDevice, L.st));
             CK(L.concat.reserve((size_t)J.n * 16));
-            transform_concat_kernel<<<min(nblk(J.n, 256), (uint32_t)h->num_sms * 16), 256, 0, L.st>>>(
+            transform_concat_kernel<<<min(nblk(J.n, 2048), (uint32_t)h->num_sms * 16), 256, 0, L.st>>>(
                 L.segs.as<Segment>(), (uint32_t)L.seg_host.size(), J.n, L.concat.as<float4>(), mm);
             J.pts = L.concat.as<float4>();
         } else {
@@ -521,10 +536,11 @@ int voxelgrid_batch(lvreg_handle* h, VgJob* jobs, int nj) {
         VgJob& J = jobs[order[jo]];
         if (J.n == 0 || J.small) continue;
         Lane& L = h->lane[J.lane];
-        for (int a = 0; a < 3; ++a) {
-            J.mn[a] = ordered_to_float(L.pinned[a]);
-            J.mx[a] = ordered_to_float(L.pinned[3 + a]);
-        }
+        if (!J.cached)
+            for (int a = 0; a < 3; ++a) {
+                J.mn[a] = ordered_to_float(L.pinned[a]);
+                J.mx[a] = ordered_to_float(L.pinned[3 + a]);
+            }
         // PCL voxel_grid.hpp: leaf-size overflow rule and bounds, fp32 exactly as PCL computes them
         const float inv = 1.0f / J.leaf;
         int64_t d[3];
@@ -551,9 +567,14 @@ int voxelgrid_batch(lvreg_handle* h, VgJob* jobs, int nj) {
         vs.key_bits = bits_for((uint64_t)div_b[0] * div_b[1] * div_b[2] - 1);
         CKS(ensure_sort_buffers(h, L, J.n));
         radix_sort_prepare(L.sort_scratch.as<uint32_t>(), J.n, vs.key_bits, L.st);
-        voxel_keys_kernel<<<min(nblk(J.n, 256 * 8), (uint32_t)h->num_sms * 8), 256, 0, L.st>>>(
-            J.pts, J.n, vs, L.keys[0].as<uint32_t>(), L.vals[0].as<uint32_t>(),
-            sort_ghist_ptr(L.sort_scratch.as<uint32_t>(), J.n), sort_num_passes(vs.key_bits));
+        if (J.cached)
+            voxel_keys_seg_kernel<<<min(nblk(J.n, 2048), (uint32_t)h->num_sms * 8), 256, 0, L.st>>>(
+                L.segs.as<Segment>(), (uint32_t)L.seg_host.size(), J.n, vs, L.keys[0].as<uint32_t>(), L.vals[0].as<uint32_t>(),
+                sort_ghist_ptr(L.sort_scratch.as<uint32_t>(), J.n), sort_num_passes(vs.key_bits));
+        else
+            voxel_keys_kernel<<<min(nblk(J.n, 256 * 8), (uint32_t)h->num_sms * 8), 256, 0, L.st>>>(
+                J.pts, J.n, vs, L.keys[0].as<uint32_t>(), L.vals[0].as<uint32_t>(),
+                sort_ghist_ptr(L.sort_scratch.as<uint32_t>(), J.n), sort_num_passes(vs.key_bits));
         launched(h);
         if (J.d_point_keys)
             CK(cudaMemcpyAsync(J.d_point_keys, L.keys[0].p, (size_t)J.n * 4, cudaMemcpyDeviceToDevice, L.st));
@@ -586,9 +607,14 @@ int voxelgrid_batch(lvreg_handle* h, VgJob* jobs, int nj) {
             CK(L.vox_keys.reserve((size_t)(nvox ? nvox : 1) * 4));
             okeys = L.vox_keys.as<uint32_t>();
         }
-        centroid_kernel<<<nblk(nvox, 128), 128, 0, L.st>>>(J.pts, L.keys[J.cur].as<uint32_t>(), L.vals[J.cur].as<uint32_t>(),
-                                                           L.vox_start.as<uint32_t>(), L.small.as<uint32_t>() + SM_NVOX,
-                                                           J.n, J.out->as<float4>(), okeys);
+        if (J.cached)
+            centroid_seg_kernel<<<nblk(nvox, 128), 128, 0, L.st>>>(L.segs.as<Segment>(), L.keys[J.cur].as<uint32_t>(),
+                                                                   L.vals[J.cur].as<uint32_t>(), L.vox_start.as<uint32_t>(),
+                                                                   L.small.as<uint32_t>() + SM_NVOX, J.n, J.out->as<float4>());
+        else
+            centroid_kernel<<<nblk(nvox, 128), 128, 0, L.st>>>(J.pts, L.keys[J.cur].as<uint32_t>(), L.vals[J.cur].as<uint32_t>(),
+                                                               L.vox_start.as<uint32_t>(), L.small.as<uint32_t>() + SM_NVOX,
+                                                               J.n, J.out->as<float4>(), okeys);
         launched(h);
         *J.n_out = nvox;
     }
@@ -785,26 +811,92 @@ void pose_to_affine_host(const float pose[6], float T[12]) {
     T[8] = -D;     T[9] = C * F;           T[10] = C * E;           T[11] = pose[5];
 }
 
+// laserCloudMapContainer (MO:942-954): transforms the not-yet-cached clouds of the listed keyframes under their
+// current poses and measures their bounding boxes -- one batch of launches and ONE host synchronisation for all of
+// them; a keyframe is transformed once per pose, as in the reference.  Runs on the main stream, before the lanes fork.
+int ensure_world_cache(lvreg_handle* h, const int32_t* ids, size_t n_ids) {
+    std::vector<Keyframe*> todo;
+    for (size_t i = 0; i < n_ids; ++i) {
+        Keyframe* kf = h->kfs[ids[i]];
+        if (!kf->world_ok && std::find(todo.begin(), todo.end(), kf) == todo.end()) todo.push_back(kf);
+    }
+    const size_t batch = 1024;                                   // 1024 keyframes x 2 clouds x 6 words = 48 KB of pinned memory
+    uint32_t* host_mm = (uint32_t*)((char*)h->pinned + 8192);
+    for (size_t b0 = 0; b0 < todo.size(); b0 += batch) {
+        const size_t nb = std::min(batch, todo.size() - b0);
+        CK(h->kfmm.reserve(nb * 2 * 6 * 4));
+        bbox_slots_init_kernel<<<nblk((uint32_t)(nb * 12), 256), 256, 0, h->st>>>(h->kfmm.as<uint32_t>(), (uint32_t)(nb * 2));
+        launched(h);
+        for (size_t k = 0; k < nb; ++k) {
+            Keyframe* kf = todo[b0 + k];
+            Affine T;
+            pose_to_affine_host(kf->pose, T.m);                  // pclPointToAffine3f(cloudKeyPoses6D[id])
+            for (int s = 0; s < 2; ++s) {
+                if (kf->n[s] == 0) continue;
+                CK(kf->world[s].reserve((size_t)kf->n[s] * 16));
+                transform_bbox_kernel<<<min(nblk(kf->n[s], 256), (uint32_t)h->num_sms * 4), 256, 0, h->st>>>(
+                    kf->cloud[s].as<float4>(), kf->n[s], T, kf->world[s].as<float4>(), h->kfmm.as<uint32_t>() + (k * 2 + s) * 6);
+                launched(h);
+            }
+        }
+        CK(cudaMemcpyAsync(host_mm, h->kfmm.p, nb * 2 * 6 * 4, cudaMemcpyDeviceToHost, h->st));
+        CK(cudaStreamSynchronize(h->st));
+        for (size_t k = 0; k < nb; ++k) {
+            Keyframe* kf = todo[b0 + k];
+            for (int s = 0; s < 2; ++s)
+                for (int a = 0; a < 3; ++a) {
+                    kf->wmn[s][a] = ordered_to_float(host_mm[(k * 2 + s) * 6 + a]);
+                    kf->wmx[s][a] = ordered_to_float(host_mm[(k * 2 + s) * 6 + 3 + a]);
+                }
+            kf->world_ok = true;
+        }
+    }
+    return LVREG_OK;
+}
+
 // fills the two local-map jobs (lanes 0/1) from the keyframe id list (extractCloud MO:931-957)
 int prepare_map_jobs(lvreg_handle* h, const int32_t* ids, size_t n_ids, VgJob* jobs) {
     if (h->kfs.empty()) return fail(h, LVREG_ERR_NO_KEYFRAMES, "no keyframes");
     for (size_t i = 0; i < n_ids; ++i)
         if (ids[i] < 0 || (size_t)ids[i] >= h->kfs.size()) return fail(h, LVREG_ERR_INVALID, "keyframe id out of range");
+    // which class goes through the cached world-frame clouds: the large ones (the single-launch filter for small maps
+    // transforms in-kernel), when the (segment, offset) payload can address them
+    bool cached[2] = {false, false};
+    bool any_cached = false;
+    for (int s = 0; s < 2; ++s) {
+        uint64_t total = 0, nseg = 0, biggest = 0;
+        for (size_t i = 0; i < n_ids; ++i) {
+            const Keyframe* kf = h->kfs[ids[i]];
+            if (kf->n[s] == 0) continue;
+            total += kf->n[s];
+            ++nseg;
+            if (kf->n[s] > biggest) biggest = kf->n[s];
+        }
+        cached[s] = h->kf_cache_enabled && (total > (uint64_t)kVgMidMax || !h->vg_mid_enabled) &&
+                    nseg <= (1u << (32 - kSegShift)) && biggest <= (uint64_t)kSegOffMask;
+        any_cached = any_cached || cached[s];
+    }
+    if (any_cached) CKS(ensure_world_cache(h, ids, n_ids));
     for (int s = 0; s < 2; ++s) {
         Lane& L = h->lane[s];
         MapSide& ms = h->map[s];
         L.seg_host.clear();
         uint64_t total = 0;
+        float mn[3] = {3.4e38f, 3.4e38f, 3.4e38f}, mx[3] = {-3.4e38f, -3.4e38f, -3.4e38f};
         for (size_t i = 0; i < n_ids; ++i) {
             const Keyframe* kf = h->kfs[ids[i]];
             if (kf->n[s] == 0) continue;          // empty clouds contribute nothing
             Segment sg;
-            sg.src = kf->cloud[s].as<float4>();
+            sg.src = cached[s] ? kf->world[s].as<float4>() : kf->cloud[s].as<float4>();
             sg.begin = (uint32_t)total;
             sg.n = kf->n[s];
             pose_to_affine_host(kf->pose, sg.T.m);        // pclPointToAffine3f(cloudKeyPoses6D[id])
             L.seg_host.push_back(sg);
             total += kf->n[s];
+            for (int a = 0; a < 3; ++a) {
+                mn[a] = fminf(mn[a], kf->wmn[s][a]);
+                mx[a] = fmaxf(mx[a], kf->wmx[s][a]);
+            }
         }
         if (total > 0x7fffffffull) return fail(h, LVREG_ERR_INVALID, "local map too large");
         ms.n_in = total;
@@ -814,6 +906,9 @@ int prepare_map_jobs(lvreg_handle* h, const int32_t* ids, size_t n_ids, VgJob* j
         J.lane = s;
         J.n = (uint32_t)total;
         J.from_segments = true;
+        J.cached = cached[s] && total > 0;
+        if (J.cached)
+            for (int a = 0; a < 3; ++a) { J.mn[a] = mn[a]; J.mx[a] = mx[a]; }
         J.leaf = s == 0 ? h->prm.corner_leaf : h->prm.surf_leaf;
         J.out = &ms.ds;
         J.n_out = &ms.m;
@@ -987,7 +1082,7 @@ int scan2map_impl(lvreg_handle* h, float pose[6], lvreg_result* res) {
     if (h->reg_max_blocks_per_sm == 0) {
         int nb = 0;
         if (variant == 3) {
-            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, register_warm_kernel, kRegThreads, 0));
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, register_warm_kernel_ptr(h->warm_tile), kRegThreads, 0));
         } else if (variant == 2) {
             CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, register_staged_kernel, kRegThreads, register_staged_smem_bytes()));
         } else if (variant == 1) {
@@ -998,7 +1093,7 @@ int scan2map_impl(lvreg_handle* h, float pose[6], lvreg_result* res) {
         if (nb < 1) return fail(h, LVREG_ERR_CUDA, "the registration kernel does not fit on an SM");
         h->reg_max_blocks_per_sm = nb;
     }
-    const int tile_q = variant == 0 ? h->tile : 32;
+    const int tile_q = variant == 0 ? h->tile : (variant == 3 ? h->warm_tile : 32);
     const uint32_t tiles = nblk(h->n_scan[0], tile_q) + nblk(h->n_scan[1], tile_q);
     const int max_grid = h->reg_max_blocks_per_sm * h->num_sms;
     // static tiles: tile t runs on block t % grid, so a small scan spreads over all SMs, one tile per warp
@@ -1025,7 +1120,7 @@ int scan2map_impl(lvreg_handle* h, float pose[6], lvreg_result* res) {
             args.nn_prev[s] = h->nnprev[s].as<int32_t>();
         }
         void* kargs[] = {&args};
-        CK(cudaLaunchCooperativeKernel((void*)register_warm_kernel, dim3(grid), dim3(kRegThreads), kargs, 0, h->st));
+        CK(cudaLaunchCooperativeKernel(register_warm_kernel_ptr(h->warm_tile), dim3(grid), dim3(kRegThreads), kargs, 0, h->st));
     } else if (variant == 2) {
         if (h->debug_tiles) {
             CK(cudaMemsetAsync(h->stagestats.p, 0, 8 * sizeof(uint32_t), h->st));
@@ -1197,6 +1292,8 @@ int lvreg_create(const lvreg_params* p, int device, void* cuda_stream, lvreg_han
         int v = atoi(e);
         if (v == 4 || v == 8 || v == 16 || v == 32) h->lpq = v;
     }
+    e = getenv("LVREG_KF_CACHE");
+    if (e) h->kf_cache_enabled = atoi(e) != 0;
     e = getenv("LVREG_VG_MID");
     if (e) h->vg_mid_enabled = atoi(e) != 0;
     e = getenv("LVREG_DEBUG_TILES");
@@ -1265,7 +1362,7 @@ void lvreg_destroy(lvreg_handle* h) {
     DevBuf* bufs[] = {&h->icp_cur, &h->icp_partials, &h->icp_state, &h->icp_idx, &h->icp_d2, &h->feat_pts, &h->feat_range, &h->feat_col, &h->feat_rings, &h->feat_curv, &h->feat_picked,
                       &h->feat_label, &h->feat_flag, &h->feat_ringof, &h->feat_cidx, &h->feat_ccnt, &h->feat_pos,
                       &h->feat_cand, &h->feat_spec, &h->feat_idx, &h->feat_pidx, &h->feat_corner, &h->feat_surf,
-                      &h->stagestats, &h->nnprev[0], &h->nnprev[1], &h->vgout, &h->partials, &h->regout, &h->lmstate, &h->posebuf, &h->tilectr, &h->tilens, &h->qbuf,
+                      &h->kfmm, &h->stagestats, &h->nnprev[0], &h->nnprev[1], &h->vgout, &h->partials, &h->regout, &h->lmstate, &h->posebuf, &h->tilectr, &h->tilens, &h->qbuf,
                       &h->idxbuf, &h->d2buf, &h->brute_partial, &h->coeffbuf, &h->flagbuf};
     for (DevBuf* b : bufs) b->release();
     h->kf_arena.release_all();
@@ -1325,11 +1422,13 @@ Keyframe* take_keyframe(lvreg_handle* h) {
     if (h->kf_free.empty()) {
         Keyframe* kf = new Keyframe();
         kf->cloud[0].arena = kf->cloud[1].arena = &h->kf_arena;
+        kf->world[0].arena = kf->world[1].arena = &h->kf_arena;
         return kf;
     }
     Keyframe* kf = h->kf_free.back();
     h->kf_free.pop_back();
     kf->n[0] = kf->n[1] = 0;
+    kf->world_ok = false;
     return kf;
 }
 }  // namespace
@@ -1386,7 +1485,10 @@ int lvreg_add_keyframe_from_scan(lvreg_handle* h, const float pose[6], int32_t* 
 int lvreg_update_keyframe_poses(lvreg_handle* h, const float* poses, size_t n) {
     if (!h || (!poses && n)) return LVREG_ERR_INVALID;
     if (n > h->kfs.size()) return fail(h, LVREG_ERR_INVALID, "more poses than keyframes");
-    for (size_t i = 0; i < n; ++i) memcpy(h->kfs[i]->pose, poses + 6 * i, 6 * sizeof(float));
+    for (size_t i = 0; i < n; ++i) {
+        memcpy(h->kfs[i]->pose, poses + 6 * i, 6 * sizeof(float));
+        h->kfs[i]->world_ok = false;                      // laserCloudMapContainer.clear(), MO:1623
+    }
     // the reference drops laserCloudMapContainer here (MO:1623); this library re-transforms on
     // every build, so only the current local map becomes stale
     h->map[0].valid = h->map[1].valid = false;
@@ -1406,14 +1508,12 @@ int lvreg_clear_keyframes(lvreg_handle* h) {
     // no keyframe stays live: hand every cloud back to the arena at once (its slabs are kept and refilled from the
     // start, so replaying session after session on one handle neither allocates nor grows) and recycle the objects
     for (Keyframe* kf : h->kfs) {
-        kf->cloud[0].p = kf->cloud[1].p = nullptr;
-        kf->cloud[0].cap = kf->cloud[1].cap = 0;
         if (h->kf_free.size() < 4096) h->kf_free.push_back(kf);
         else delete kf;
     }
     for (Keyframe* kf : h->kf_free) {
-        kf->cloud[0].p = kf->cloud[1].p = nullptr;
-        kf->cloud[0].cap = kf->cloud[1].cap = 0;
+        for (DevBuf* b : {&kf->cloud[0], &kf->cloud[1], &kf->world[0], &kf->world[1]}) { b->p = nullptr; b->cap = 0; }
+        kf->world_ok = false;
     }
     h->kf_arena.reset();
     h->kfs.clear();
@@ -2361,7 +2461,7 @@ int lvreg_build_global_map(lvreg_handle* h, const int32_t* ids, size_t n_ids, in
             uint32_t* mm = L.small.as<uint32_t>() + SM_MM;
             CK(L.segs.reserve(L.seg_host.size() * sizeof(Segment)));
             CK(cudaMemcpyAsync(L.segs.p, L.seg_host.data(), L.seg_host.size() * sizeof(Segment), cudaMemcpyHostToDevice, h->st));
-            transform_concat_kernel<<<min(nblk(J.n, 256), (uint32_t)h->num_sms * 16), 256, 0, h->st>>>(
+            transform_concat_kernel<<<min(nblk(J.n, 2048), (uint32_t)h->num_sms * 16), 256, 0, h->st>>>(
                 L.segs.as<Segment>(), (uint32_t)L.seg_host.size(), J.n, ms.ds.as<float4>(), mm);
             launched(h);
         }

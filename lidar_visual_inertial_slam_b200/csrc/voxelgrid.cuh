@@ -105,19 +105,32 @@ __global__ void __launch_bounds__(256) transform_concat_kernel(const Segment* __
                                                                float4* __restrict__ out,
                                                                uint32_t* __restrict__ mm) {
     float mnx = 3.4e38f, mny = 3.4e38f, mnz = 3.4e38f, mxx = -3.4e38f, mxy = -3.4e38f, mxz = -3.4e38f;
-    for (uint32_t i = blockIdx.x * 256 + threadIdx.x; i < total; i += gridDim.x * 256) {
-        // last segment with begin <= i (empty segments share a begin and are skipped by the search)
-        uint32_t lo = 0, hi = nseg;
-        while (hi - lo > 1) {
-            uint32_t mid = (lo + hi) >> 1;
-            if (segs[mid].begin <= i) lo = mid; else hi = mid;
+    __shared__ uint32_t seg0_s;
+    // chunks of 2048 consecutive points: one binary search per chunk (last segment with begin <= first point; empty
+    // segments share a begin and are skipped), then the points walk forward from it
+    for (uint32_t c0 = blockIdx.x * 2048u; c0 < total; c0 += gridDim.x * 2048u) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t lo = 0, hi = nseg;
+            while (hi - lo > 1) {
+                uint32_t mid = (lo + hi) >> 1;
+                if (segs[mid].begin <= c0) lo = mid; else hi = mid;
+            }
+            seg0_s = lo;
         }
-        const Segment& s = segs[lo];
-        float4 p = ld_stream(s.src + (i - s.begin));
-        float3 q = apply_affine(s.T, p.x, p.y, p.z);
-        out[i] = make_float4(q.x, q.y, q.z, p.w);
-        mnx = fminf(mnx, q.x); mny = fminf(mny, q.y); mnz = fminf(mnz, q.z);
-        mxx = fmaxf(mxx, q.x); mxy = fmaxf(mxy, q.y); mxz = fmaxf(mxz, q.z);
+        __syncthreads();
+        uint32_t lo = seg0_s;
+        for (int r = 0; r < 8; ++r) {
+            const uint32_t i = c0 + r * 256 + threadIdx.x;
+            if (i >= total) break;
+            while (lo + 1 < nseg && segs[lo + 1].begin <= i) ++lo;
+            const Segment& s = segs[lo];
+            float4 p = ld_stream(s.src + (i - s.begin));
+            float3 q = apply_affine(s.T, p.x, p.y, p.z);
+            out[i] = make_float4(q.x, q.y, q.z, p.w);
+            mnx = fminf(mnx, q.x); mny = fminf(mny, q.y); mnz = fminf(mnz, q.z);
+            mxx = fmaxf(mxx, q.x); mxy = fmaxf(mxy, q.y); mxz = fmaxf(mxz, q.z);
+        }
     }
     block_minmax_commit(mnx, mny, mnz, mxx, mxy, mxz, mm);
 }
@@ -159,6 +172,98 @@ __global__ void __launch_bounds__(256) voxel_keys_kernel(const float4* __restric
         acc.add(key, passes);
     }
     acc.flush(ghist, passes);
+}
+
+// ---- the same two kernels over CACHED world-frame keyframe clouds (laserCloudMapContainer, MO:942-954) ----
+// The reference transforms a keyframe cloud once and keeps the result (MO:945-952); the concatenation is what it
+// redoes per scan.  Here the cached clouds are not even concatenated: the key kernel walks the segment table, and
+// the sort's payload is (segment << kSegShift | offset) instead of a global index, so the centroid kernel gathers
+// straight from the cached clouds.  Input order (segment order, then point order) is what the stable sort keeps,
+// exactly as with a concatenated cloud.
+constexpr int kSegShift = 22;                       // <= 1024 segments of <= 4 Mi points each
+constexpr uint32_t kSegOffMask = (1u << kSegShift) - 1u;
+
+__global__ void __launch_bounds__(256) voxel_keys_seg_kernel(const Segment* __restrict__ segs, uint32_t nseg, uint32_t n,
+                                                             VoxelSpec vs, uint32_t* __restrict__ keys,
+                                                             uint32_t* __restrict__ vals, uint32_t* __restrict__ ghist,
+                                                             int passes) {
+    __shared__ uint32_t hist_s[8][kSortMaxPasses][256];
+    HistAccumulator acc;
+    acc.init(hist_s);
+    __shared__ uint32_t seg0_s;
+    // a block takes chunks of 2048 consecutive points: one binary search per chunk finds its first segment, the
+    // points then walk forward from it (a chunk spans one or two keyframe clouds) -- not a search per point
+    for (uint32_t c0 = blockIdx.x * 2048u; c0 < n; c0 += gridDim.x * 2048u) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t lo = 0, hi = nseg;
+            while (hi - lo > 1) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (segs[mid].begin <= c0) lo = mid; else hi = mid;
+            }
+            seg0_s = lo;
+        }
+        __syncthreads();
+        uint32_t lo = seg0_s;
+#pragma unroll 4
+        for (int r = 0; r < 8; ++r) {
+            const uint32_t i = c0 + r * 256 + threadIdx.x;
+            if (i >= n) break;
+            while (lo + 1 < nseg && segs[lo + 1].begin <= i) ++lo;
+            const Segment& sg = segs[lo];
+            const uint32_t off = i - sg.begin;
+            const float4 p = ld_stream(sg.src + off);
+            const int ix = (int)(floorf(p.x * vs.inv) - (float)vs.min_b[0]);
+            const int iy = (int)(floorf(p.y * vs.inv) - (float)vs.min_b[1]);
+            const int iz = (int)(floorf(p.z * vs.inv) - (float)vs.min_b[2]);
+            const uint32_t key = (uint32_t)(ix * vs.mul[0] + iy * vs.mul[1] + iz * vs.mul[2]);
+            keys[i] = key;
+            vals[i] = (lo << kSegShift) | off;
+            acc.add(key, passes);
+        }
+    }
+    acc.flush(ghist, passes);
+}
+
+__global__ void __launch_bounds__(128) centroid_seg_kernel(const Segment* __restrict__ segs,
+                                                           const uint32_t* __restrict__ sorted_keys,
+                                                           const uint32_t* __restrict__ sorted_vals,
+                                                           const uint32_t* __restrict__ start,
+                                                           const uint32_t* __restrict__ nvox_p, uint32_t n,
+                                                           float4* __restrict__ out) {
+    const uint32_t nvox = *nvox_p;
+    uint32_t v = blockIdx.x * 128 + threadIdx.x;
+    if (v >= nvox) return;
+    const uint32_t b = start[v];
+    const uint32_t e = (v + 1 < nvox) ? start[v + 1] : n;
+    float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
+    for (uint32_t j = b; j < e; ++j) {
+        const uint32_t pv = sorted_vals[j];
+        const float4 p = __ldg(segs[pv >> kSegShift].src + (pv & kSegOffMask));
+        sx += p.x; sy += p.y; sz += p.z; si += p.w;
+    }
+    const float cnt = (float)(e - b);
+    out[v] = make_float4(sx / cnt, sy / cnt, sz / cnt, si / cnt);
+}
+
+// transformPointCloud of one keyframe cloud into the cache + its bounding box (slot = 6 ordered uints, initialised
+// to 0xffffffff x3 / 0 x3 by the caller)
+__global__ void __launch_bounds__(256) transform_bbox_kernel(const float4* __restrict__ in, uint32_t n, Affine T,
+                                                             float4* __restrict__ out, uint32_t* __restrict__ mm) {
+    float mnx = 3.4e38f, mny = 3.4e38f, mnz = 3.4e38f, mxx = -3.4e38f, mxy = -3.4e38f, mxz = -3.4e38f;
+    for (uint32_t i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+        const float4 p = in[i];
+        const float3 q = apply_affine(T, p.x, p.y, p.z);
+        out[i] = make_float4(q.x, q.y, q.z, p.w);
+        mnx = fminf(mnx, q.x); mny = fminf(mny, q.y); mnz = fminf(mnz, q.z);
+        mxx = fmaxf(mxx, q.x); mxy = fmaxf(mxy, q.y); mxz = fmaxf(mxz, q.z);
+    }
+    block_minmax_commit(mnx, mny, mnz, mxx, mxy, mxz, mm);
+}
+
+__global__ void bbox_slots_init_kernel(uint32_t* mm, uint32_t nslots) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nslots * 6) mm[i] = (i % 6) < 3 ? 0xffffffffu : 0u;
 }
 
 // ---- run heads -> voxel starts -----------------------------------------------------------------
