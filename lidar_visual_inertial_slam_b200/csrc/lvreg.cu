@@ -179,6 +179,9 @@ struct lvreg_handle {
     int imu_available = 0;        // cloudInfo.imu_available / imu_roll_init / imu_pitch_init of the current scan (MO:1347-1366)
     float imu_roll = 0.f, imu_pitch = 0.f;
     int warm_tile = 32;
+    int debug_phases = 0;         // LVREG_DEBUG_PHASES=1: per-lane phase time stamps of the VoxelGrid batch on stderr
+    cudaEvent_t dbg_ev[kLanes][6] = {};
+    unsigned dbg_ev_used = 0;
     bool kf_cache_enabled = true; // LVREG_KF_CACHE=0: transform the keyframe clouds on every map build (experiments)
     DevBuf kfmm;                  // bounding-box slots of the keyframe clouds being cached
     bool vg_mid_enabled = true;   // LVREG_VG_MID=0 disables the cooperative single-launch VoxelGrid (experiments)
@@ -405,6 +408,8 @@ struct VgJob {
     uint32_t n = 0;
     bool from_segments = false;        // input = Lane::seg_host, transformed + concatenated into Lane::concat
     bool cached = false;               // segments point at cached WORLD-frame clouds; mn / mx hold their exact bbox
+    DevBuf* morton_out = nullptr;      // optional (single-launch path only): the output once more in Morton order
+    bool morton_done = false;
     float leaf = 0.f;
     DevBuf* out = nullptr;
     uint32_t* n_out = nullptr;
@@ -484,6 +489,13 @@ int voxelgrid_batch(lvreg_handle* h, VgJob* jobs, int nj) {
                 a.out_keys = L.vox_keys.as<uint32_t>();
             }
             a.point_keys = J.d_point_keys;
+            a.morton_out = nullptr;
+            J.morton_done = false;
+            if (J.morton_out) {
+                CK(J.morton_out->reserve((size_t)J.n * 16));
+                a.morton_out = J.morton_out->as<float4>();
+                J.morton_done = true;              // unless PCL's passthrough rule fires (checked after the synchronisation)
+            }
             VgSmallInfo* d_info = reinterpret_cast<VgSmallInfo*>(L.small.as<uint32_t>() + SM_SMALLVG);
             a.info = d_info;
             void* kargs[] = {&a};
@@ -566,6 +578,7 @@ int voxelgrid_batch(lvreg_handle* h, VgJob* jobs, int nj) {
         vs.mul[2] = div_b[0] * div_b[1];
         vs.key_bits = bits_for((uint64_t)div_b[0] * div_b[1] * div_b[2] - 1);
         CKS(ensure_sort_buffers(h, L, J.n));
+        if (h->debug_phases) cudaEventRecord(h->dbg_ev[J.lane][0], L.st);
         radix_sort_prepare(L.sort_scratch.as<uint32_t>(), J.n, vs.key_bits, L.st);
         if (J.cached)
             voxel_keys_seg_kernel<<<min(nblk(J.n, 2048), (uint32_t)h->num_sms * 8), 256, 0, L.st>>>(
@@ -578,14 +591,17 @@ int voxelgrid_batch(lvreg_handle* h, VgJob* jobs, int nj) {
         launched(h);
         if (J.d_point_keys)
             CK(cudaMemcpyAsync(J.d_point_keys, L.keys[0].p, (size_t)J.n * 4, cudaMemcpyDeviceToDevice, L.st));
+        if (h->debug_phases) cudaEventRecord(h->dbg_ev[J.lane][1], L.st);
         J.cur = radix_sort_run(L.keys[0].as<uint32_t>(), L.vals[0].as<uint32_t>(), L.keys[1].as<uint32_t>(),
                                L.vals[1].as<uint32_t>(), J.n, vs.key_bits, L.sort_scratch.as<uint32_t>(), true, L.st,
                                &h->call_launches);
+        if (h->debug_phases) cudaEventRecord(h->dbg_ev[J.lane][2], L.st);
         CK(L.vox_start.reserve((size_t)J.n * 4));
         uint32_t* d_nvox = L.small.as<uint32_t>() + SM_NVOX;
         exclusive_scan(HeadFlagIn{L.keys[J.cur].as<uint32_t>()}, VoxelStartOut{L.vox_start.as<uint32_t>()}, J.n,
                        L.scan_temp.as<uint32_t>(), d_nvox, L.st, &h->call_launches);
         CK(cudaMemcpyAsync(L.pinned + 8, d_nvox, 4, cudaMemcpyDeviceToHost, L.st));
+        if (h->debug_phases) cudaEventRecord(h->dbg_ev[J.lane][3], L.st);
     }
     CK(lanes_sync(h, mask));
     // ---- phase 3: centroids (left running on the lane streams) ----
@@ -595,6 +611,7 @@ int voxelgrid_batch(lvreg_handle* h, VgJob* jobs, int nj) {
             const VgSmallInfo* info = reinterpret_cast<const VgSmallInfo*>(h->lane[J.lane].pinned + 32);
             *J.n_out = info->nvox;
             J.passthrough = info->passthrough;
+            if (J.passthrough) J.morton_done = false;
             for (int a = 0; a < 3; ++a) { J.mn[a] = info->mn[a]; J.mx[a] = info->mx[a]; }
             continue;
         }
@@ -616,6 +633,7 @@ int voxelgrid_batch(lvreg_handle* h, VgJob* jobs, int nj) {
                                                                L.vox_start.as<uint32_t>(), L.small.as<uint32_t>() + SM_NVOX,
                                                                J.n, J.out->as<float4>(), okeys);
         launched(h);
+        if (h->debug_phases) { cudaEventRecord(h->dbg_ev[J.lane][4], L.st); h->dbg_ev_used |= 1u << J.lane; }
         *J.n_out = nvox;
     }
     CK(cudaGetLastError());
@@ -916,6 +934,8 @@ int prepare_map_jobs(lvreg_handle* h, const int32_t* ids, size_t n_ids, VgJob* j
     return LVREG_OK;
 }
 
+int reg_variant(const lvreg_handle* h);
+
 // uploads the raw scan clouds on lanes 2/3 and fills their jobs (downsampleCurrentScan MO:987-999)
 int prepare_scan_jobs(lvreg_handle* h, const lvreg_cloud* corner_raw, const lvreg_cloud* surf_raw, VgJob* jobs) {
     const lvreg_cloud* c[2] = {corner_raw, surf_raw};
@@ -931,6 +951,10 @@ int prepare_scan_jobs(lvreg_handle* h, const lvreg_cloud* corner_raw, const lvre
         J.out = &h->scan_ds[s];
         J.n_out = &h->n_scan[s];
     }
+    // large scans: the registration kernels want the queries in Morton order (want_sorted_scan); the single-launch
+    // filter produces that copy as its last phase, before any host synchronisation
+    if (reg_variant(h) >= 2 && c[0]->n + c[1]->n >= 65536)
+        for (int s = 0; s < 2; ++s) jobs[s].morton_out = &h->scan_sorted[s];
     return LVREG_OK;
 }
 
@@ -1292,6 +1316,12 @@ int lvreg_create(const lvreg_params* p, int device, void* cuda_stream, lvreg_han
         int v = atoi(e);
         if (v == 4 || v == 8 || v == 16 || v == 32) h->lpq = v;
     }
+    e = getenv("LVREG_DEBUG_PHASES");
+    if (e && atoi(e)) {
+        h->debug_phases = 1;
+        for (int l = 0; l < kLanes; ++l)
+            for (int k = 0; k < 6; ++k) cudaEventCreate(&h->dbg_ev[l][k]);
+    }
     e = getenv("LVREG_KF_CACHE");
     if (e) h->kf_cache_enabled = atoi(e) != 0;
     e = getenv("LVREG_VG_MID");
@@ -1599,9 +1629,10 @@ int lvreg_downsample_scan(lvreg_handle* h, const lvreg_cloud* corner_raw, const 
     lanes_fork(h, 0xc);
     CKS(prepare_scan_jobs(h, corner_raw, surf_raw, jobs));
     CKS(voxelgrid_batch(h, jobs, 2));
-    h->scan_sorted_ok[0] = h->scan_sorted_ok[1] = false;
+    for (int s = 0; s < 2; ++s) h->scan_sorted_ok[s] = jobs[s].morton_done;
     if (want_sorted_scan(h, reg_variant(h)))
-        for (int s = 0; s < 2; ++s) CKS(sort_scan_for_search(h, s, h->lane[LANE_SCAN_CORNER + s].st));
+        for (int s = 0; s < 2; ++s)
+            if (!h->scan_sorted_ok[s]) CKS(sort_scan_for_search(h, s, h->lane[LANE_SCAN_CORNER + s].st));
     lanes_join(h, 0xc);
     mark(h, EV_DS);
     CK(cudaStreamSynchronize(h->st));
@@ -1674,10 +1705,11 @@ int lvreg_register_scan(lvreg_handle* h, const lvreg_cloud* corner_raw, const lv
     CKS(prepare_scan_jobs(h, corner_raw, surf_raw, jobs + nj));
     nj += 2;
     CKS(voxelgrid_batch(h, jobs, nj));
-    // staged variant: the scan lanes finish long before the map lanes, order the queries for the search there
-    h->scan_sorted_ok[0] = h->scan_sorted_ok[1] = false;
+    // large scans are Morton-ordered for the search: normally by the single-launch filter itself (morton_done)
+    for (int s = 0; s < 2; ++s) h->scan_sorted_ok[s] = jobs[nj - 2 + s].morton_done;
     if (want_sorted_scan(h, reg_variant(h)))
-        for (int s = 0; s < 2; ++s) CKS(sort_scan_for_search(h, s, h->lane[LANE_SCAN_CORNER + s].st));
+        for (int s = 0; s < 2; ++s)
+            if (!h->scan_sorted_ok[s]) CKS(sort_scan_for_search(h, s, h->lane[LANE_SCAN_CORNER + s].st));
     lanes_join(h, mask);
     mark(h, EV_MAP);
     if (ids) {
@@ -1700,6 +1732,18 @@ int lvreg_register_scan(lvreg_handle* h, const lvreg_cloud* corner_raw, const lv
         h->last.grid_build_ms = span(h, EV_MAP, EV_GRID);
         h->last.register_ms = span(h, EV_GRID, EV_REG);
         finish_timings(h);
+        if (h->debug_phases) {
+            for (int l = 0; l < kLanes; ++l) {
+                if (!(h->dbg_ev_used & (1u << l))) continue;
+                float t[5] = {0, 0, 0, 0, 0};
+                for (int k = 0; k < 5; ++k) cudaEventElapsedTime(&t[k], h->ev[EV_BEGIN], h->dbg_ev[l][k]);
+                fprintf(stderr, "[lvreg] lane %d: keys start %.3f, sort start %.3f, sort done %.3f, heads done %.3f, centroid done %.3f ms "
+                        "(map stage ends %.3f, grids %.3f, registration %.3f)\n", l, t[0], t[1], t[2], t[3], t[4],
+                        h->last.map_build_ms, h->last.map_build_ms + h->last.grid_build_ms,
+                        h->last.map_build_ms + h->last.grid_build_ms + h->last.register_ms);
+            }
+            h->dbg_ev_used = 0;
+        }
     }
     end_call(h);
     return s;

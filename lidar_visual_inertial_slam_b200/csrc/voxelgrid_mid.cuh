@@ -21,6 +21,7 @@
 #include "common.cuh"
 #include "prims.cuh"
 #include "voxelgrid.cuh"
+#include "knn.cuh"
 
 namespace lvreg {
 
@@ -44,6 +45,8 @@ struct VgMidArgs {
     float4* out;                // n: centroids (only nvox are written)
     uint32_t* out_keys;         // optional: idx of every output voxel
     uint32_t* point_keys;       // optional: idx of every input point
+    float4* morton_out;         // optional: the output cloud once more, ordered by the Morton code of its 2 m cell
+                                // (the query order of the registration kernels, knn.cuh); n entries
     VgSmallInfo* info;
 };
 
@@ -169,79 +172,80 @@ __global__ void __launch_bounds__(kVgMidThreads) voxelgrid_mid_kernel(VgMidArgs 
         }
     }
 
-    // ---- stable LSD radix sort, 8 bits per pass ----
-    const int passes = (vs.key_bits + 7) / 8;
+    // ---- stable LSD radix sort, 8 bits per pass, of the (k, v) pairs the tiles hold in registers ----
     uint32_t *kin = a.k0, *vin = a.v0, *kout = a.k1, *vout = a.v1;
-    for (int p = 0; p < passes; ++p) {
-        const int shift = 8 * p;
-        if (p > 0) {
+    auto radix_sort = [&](uint32_t n_items, int passes) {
+        for (int p = 0; p < passes; ++p) {
+            const int shift = 8 * p;
+            if (p > 0) {
+#pragma unroll
+                for (int r = 0; r < kVgMidItems; ++r) {
+                    const uint32_t i = base + r * 32 + lane;
+                    k[r] = i < n_items ? kin[i] : 0xffffffffu;
+                    v[r] = i < n_items ? vin[i] : 0u;
+                }
+            }
+            for (int i = tid; i < (kVgMidThreads / 32) * 256; i += kVgMidThreads) (&wcnt[0][0])[i] = 0;
+            __syncthreads();
+            // rank inside the warp's 256-point chunk: lanes with the same digit from 8 ballots, warp-private counters
+            uint16_t rank[kVgMidItems];
+#pragma unroll
+            for (int r = 0; r < kVgMidItems; ++r) {
+                const uint32_t dg = (k[r] >> shift) & 255u;
+                uint32_t peers = 0xffffffffu;
+#pragma unroll
+                for (int b = 0; b < 8; ++b) {
+                    const bool bit = (dg & (1u << b)) != 0;
+                    const uint32_t bal = __ballot_sync(0xffffffffu, bit);
+                    peers &= bal ^ (bit ? 0u : 0xffffffffu);
+                }
+                const uint32_t lower = peers & lt_mask;
+                const uint32_t old = wcnt[warp][dg];
+                if (lower == 0) wcnt[warp][dg] = old + (uint32_t)__popc(peers);
+                __syncwarp();
+                rank[r] = (uint16_t)(old + __popc(lower));
+            }
+            __syncthreads();
+            // the tile's digit counts (padding sits under digit 255 of every pass, behind every real element in index
+            // order: it is counted, shifts nothing and is never written)
+            uint32_t cnt = 0;
+#pragma unroll
+            for (int w = 0; w < kVgMidThreads / 32; ++w) cnt += wcnt[w][tid];
+            a.tile_hist[tile * 256 + tid] = cnt;
+            __threadfence();
+            grid.sync();
+            // global offset of this tile's run of digit `tid`: all smaller digits + the same digit in earlier tiles
+            uint32_t excl = 0, tot = 0;
+            for (uint32_t t = 0; t < tiles; ++t) {
+                const uint32_t c = a.tile_hist[t * 256 + tid];
+                tot += c;
+                if (t < tile) excl += c;
+            }
+            uint32_t total;
+            uint32_t gofs = block_exclusive_scan(tot, &total) + excl;
+#pragma unroll
+            for (int w = 0; w < kVgMidThreads / 32; ++w) {
+                const uint32_t c = wcnt[w][tid];
+                wcnt[w][tid] = gofs;
+                gofs += c;
+            }
+            __syncthreads();
 #pragma unroll
             for (int r = 0; r < kVgMidItems; ++r) {
                 const uint32_t i = base + r * 32 + lane;
-                k[r] = i < n ? kin[i] : 0xffffffffu;
-                v[r] = i < n ? vin[i] : 0u;
+                if (i < n_items) {
+                    const uint32_t dst = wcnt[warp][(k[r] >> shift) & 255u] + rank[r];
+                    kout[dst] = k[r];
+                    vout[dst] = v[r];
+                }
             }
+            __threadfence();
+            grid.sync();
+            uint32_t* t0 = kin; kin = kout; kout = t0;
+            t0 = vin; vin = vout; vout = t0;
         }
-        for (int i = tid; i < (kVgMidThreads / 32) * 256; i += kVgMidThreads) (&wcnt[0][0])[i] = 0;
-        __syncthreads();
-        // rank inside the warp's 256-point chunk: lanes with the same digit from 8 ballots, warp-private counters
-        uint16_t rank[kVgMidItems];
-#pragma unroll
-        for (int r = 0; r < kVgMidItems; ++r) {
-            const uint32_t dg = (k[r] >> shift) & 255u;
-            uint32_t peers = 0xffffffffu;
-#pragma unroll
-            for (int b = 0; b < 8; ++b) {
-                const bool bit = (dg & (1u << b)) != 0;
-                const uint32_t bal = __ballot_sync(0xffffffffu, bit);
-                peers &= bal ^ (bit ? 0u : 0xffffffffu);
-            }
-            const uint32_t lower = peers & lt_mask;
-            const uint32_t old = wcnt[warp][dg];
-            if (lower == 0) wcnt[warp][dg] = old + (uint32_t)__popc(peers);
-            __syncwarp();
-            rank[r] = (uint16_t)(old + __popc(lower));
-        }
-        __syncthreads();
-        // the tile's digit counts (the padding of the last tile sits under digit 255 of every pass: it is counted,
-        // sorts behind every real element of the tile and is never written)
-        uint32_t cnt = 0;
-#pragma unroll
-        for (int w = 0; w < kVgMidThreads / 32; ++w) cnt += wcnt[w][tid];
-        a.tile_hist[tile * 256 + tid] = cnt;
-        __threadfence();
-        grid.sync();
-        // global offset of this tile's run of digit `tid`: all smaller digits + the same digit in earlier tiles
-        uint32_t excl = 0, tot = 0;
-        for (uint32_t t = 0; t < tiles; ++t) {
-            const uint32_t c = a.tile_hist[t * 256 + tid];
-            tot += c;
-            if (t < tile) excl += c;
-        }
-        // padding: digit 255 of the last tile includes its padding, which must not shift anything (it is last anyway)
-        uint32_t total;
-        uint32_t gofs = block_exclusive_scan(tot, &total) + excl;
-#pragma unroll
-        for (int w = 0; w < kVgMidThreads / 32; ++w) {
-            const uint32_t c = wcnt[w][tid];
-            wcnt[w][tid] = gofs;
-            gofs += c;
-        }
-        __syncthreads();
-#pragma unroll
-        for (int r = 0; r < kVgMidItems; ++r) {
-            const uint32_t i = base + r * 32 + lane;
-            if (i < n) {
-                const uint32_t dst = wcnt[warp][(k[r] >> shift) & 255u] + rank[r];
-                kout[dst] = k[r];
-                vout[dst] = v[r];
-            }
-        }
-        __threadfence();
-        grid.sync();
-        uint32_t* t0 = kin; kin = kout; kout = t0;
-        t0 = vin; vin = vout; vout = t0;
-    }
+    };
+    radix_sort(n, (vs.key_bits + 7) / 8);
     // sorted pairs are in (kin, vin) -- for passes == 0 (cannot happen: key_bits >= 1) they would be in registers only
 
     // ---- run heads -> voxel starts ----
@@ -309,6 +313,28 @@ __global__ void __launch_bounds__(kVgMidThreads) voxelgrid_mid_kernel(VgMidArgs 
     if (tile == 0 && tid == 0) {
         a.info->nvox = nvox; a.info->passthrough = 0;
         for (int q = 0; q < 3; ++q) { a.info->mn[q] = bb_s[q]; a.info->mx[q] = bb_s[3 + q]; }
+    }
+    if (a.morton_out == nullptr) return;
+
+    // ---- the output once more in Morton order of its 2 m cells (same keys as morton_keys_kernel, stable) ----
+    __threadfence();
+    grid.sync();
+#pragma unroll
+    for (int r = 0; r < kVgMidItems; ++r) {
+        const uint32_t i = base + r * 32 + lane;
+        k[r] = 0xffffffffu;
+        v[r] = i;
+        if (i < nvox) {
+            const float4 p = a.out[i];
+            k[r] = morton_cell_key(p.x, p.y, p.z);
+        }
+    }
+    kin = a.k0; vin = a.v0; kout = a.k1; vout = a.v1;
+    radix_sort(nvox, 3);
+#pragma unroll
+    for (int r = 0; r < kVgMidItems; ++r) {
+        const uint32_t i = base + r * 32 + lane;
+        if (i < nvox) a.morton_out[i] = a.out[vin[i]];
     }
 }
 
