@@ -406,7 +406,9 @@ int lvreg_debug_tile_times(lvreg_handle* h, uint32_t* ns_out, size_t cap, size_t
 /* Diagnostics (LVREG_DEBUG_TILES=1): how the shared-memory search of the last registration staged its
  * query tiles in iteration 0: out[0..2] = tiles staged whole / as halves / as quarters, out[3] = queries that
  * took the global-memory search, out[4] = copy-barrier time-outs (must be 0), out[5] = how iteration 0 of the
- * last registration decided degeneracy (1 = Cholesky shortcut, 2 = 6x6 Jacobi; any kernel variant). */
+ * last registration decided degeneracy (1 = Cholesky shortcut, 2 = 6x6 Jacobi; any kernel variant),
+ * out[6] = local-map VoxelGrid jobs that had to be redone by the device-wide sort because a bucket of the
+ * sample-sort path overflowed, out[7] = jobs completed by the sample-sort path (since the handle was created). */
 int lvreg_debug_stage_stats(lvreg_handle* h, uint32_t out[8]);
 /* total kernels launched by this handle since creation */
 int lvreg_get_launch_count(const lvreg_handle* h, uint64_t* n);

@@ -28,6 +28,7 @@
 #include "register_warm.cuh"
 #include "voxelgrid.cuh"
 #include "voxelgrid_mid.cuh"
+#include "voxelgrid_bucket.cuh"
 
 using namespace lvreg;
 
@@ -128,6 +129,8 @@ struct Keyframe {
     // dropped when the poses are corrected (MO:1623), + their bounding boxes (exact: union of them = bbox of any map)
     DevBuf world[2];
     bool world_ok = false;
+    bool wsorted[2] = {false, false};   // world[s] is ordered by the voxel index of leaf wleaf[s] (voxelgrid_bucket.cuh)
+    float wleaf[2] = {0.f, 0.f};
     float wmn[2][3] = {{0, 0, 0}, {0, 0, 0}}, wmx[2][3] = {{0, 0, 0}, {0, 0, 0}};
 };
 
@@ -160,6 +163,7 @@ struct Lane {
     cudaStream_t st = nullptr;
     cudaEvent_t ev = nullptr;
     DevBuf stage, raw, concat, keys[2], vals[2], sort_scratch, scan_temp, scan_in, vox_start, vox_keys, segs, small;
+    DevBuf bsoff, bstatus, bout;            // bucketed VoxelGrid: segment table, chained-scan status, output (swapped with the map)
     uint32_t* pinned = nullptr;             // 64 words of page-locked host memory
     std::vector<Segment> seg_host;
 };
@@ -185,6 +189,9 @@ struct lvreg_handle {
     bool kf_cache_enabled = true; // LVREG_KF_CACHE=0: transform the keyframe clouds on every map build (experiments)
     DevBuf kfmm;                  // bounding-box slots of the keyframe clouds being cached
     bool vg_mid_enabled = true;   // LVREG_VG_MID=0 disables the cooperative single-launch VoxelGrid (experiments)
+    bool vg_bucket_enabled = true;  // LVREG_VG_BUCKET=0: large cached maps through the device-wide sort (experiments)
+    uint32_t vg_bucket_cap = 0;     // LVREG_VG_BUCKET_CAP: smaller bucket capacity, to exercise the overflow fallback
+    uint32_t vg_bucket_fallbacks = 0, vg_bucket_jobs = 0;
     int debug_tiles = 0;          // LVREG_DEBUG_TILES=1: record per-tile durations of iteration 1
     uint32_t debug_ntiles = 0;
     int force_tpq = -1;           // -1 auto, 0 grouped, 1 thread-per-query (LVREG_TPQ)
@@ -408,6 +415,7 @@ struct VgJob {
     uint32_t n = 0;
     bool from_segments = false;        // input = Lane::seg_host, transformed + concatenated into Lane::concat
     bool cached = false;               // segments point at cached WORLD-frame clouds; mn / mx hold their exact bbox
+    bool bucket = false;               // ... every one of them ordered by voxel index: sample-sort path (voxelgrid_bucket.cuh)
     DevBuf* morton_out = nullptr;      // optional (single-launch path only): the output once more in Morton order
     bool morton_done = false;
     float leaf = 0.f;
@@ -577,6 +585,59 @@ int voxelgrid_batch(lvreg_handle* h, VgJob* jobs, int nj) {
         vs.mul[1] = div_b[0];
         vs.mul[2] = div_b[0] * div_b[1];
         vs.key_bits = bits_for((uint64_t)div_b[0] * div_b[1] * div_b[2] - 1);
+        if (J.bucket && !J.want_out_keys && !J.d_point_keys) {
+            // sorted runs -> sample sort with the buckets in shared memory (voxelgrid_bucket.cuh)
+            const uint32_t nseg = (uint32_t)L.seg_host.size();
+            const uint32_t nsamp = (J.n + kVgbSample - 1) / (uint32_t)kVgbSample;     // every q with q * S < n
+            const uint32_t nbuckets = nsamp ? (nsamp + kVgbStride - 1) / kVgbStride : 1;
+            if (h->debug_phases) cudaEventRecord(h->dbg_ev[J.lane][0], L.st);
+            CKS(ensure_sort_buffers(h, L, nsamp ? nsamp : 1));
+            CK(L.bsoff.reserve((size_t)(nbuckets + 1) * nseg * 4));
+            CK(L.bstatus.reserve((size_t)(nbuckets + 8) * 4));
+            CK(L.bout.reserve((size_t)J.n * 16));
+            int cur = 0;
+            const int trunc_shift = 0;      // truncated sample keys (one sort pass less) unbalance the buckets: a block of 16 keys can hold 4 k points
+            const int sample_bits = vs.key_bits - trunc_shift;
+            CK(L.vox_start.reserve((size_t)(nsamp ? nsamp : 1) * 4));
+            if (nsamp) {
+                radix_sort_prepare(L.sort_scratch.as<uint32_t>(), nsamp, sample_bits, L.st);
+                vgb_sample_kernel<<<min(nblk(nsamp, 256), (uint32_t)h->num_sms * 4), 256, 0, L.st>>>(
+                    L.segs.as<Segment>(), nseg, nsamp, vs, trunc_shift, sort_num_passes(sample_bits), L.vox_start.as<uint32_t>(),
+                    L.keys[0].as<uint32_t>(), L.vals[0].as<uint32_t>(), sort_ghist_ptr(L.sort_scratch.as<uint32_t>(), nsamp));
+                launched(h);
+                cur = radix_sort_run(L.keys[0].as<uint32_t>(), L.vals[0].as<uint32_t>(), L.keys[1].as<uint32_t>(),
+                                     L.vals[1].as<uint32_t>(), nsamp, sample_bits, L.sort_scratch.as<uint32_t>(), true, L.st,
+                                     &h->call_launches);
+            }
+            if (h->debug_phases) cudaEventRecord(h->dbg_ev[J.lane][1], L.st);
+            const uint32_t* sorted_samples = L.keys[cur].as<uint32_t>();
+            vgb_split_kernel<<<nblk((nbuckets + 1) * nseg, 256), 256, 0, L.st>>>(L.segs.as<Segment>(), nseg, sorted_samples,
+                                                                                L.vox_start.as<uint32_t>(), nbuckets, trunc_shift,
+                                                                                vs, L.bsoff.as<uint32_t>());
+            launched(h);
+            if (h->debug_phases) cudaEventRecord(h->dbg_ev[J.lane][2], L.st);
+            CK(cudaMemsetAsync(L.bstatus.p, 0, (size_t)(nbuckets + 8) * 4, L.st));
+            VgbArgs a;
+            a.segs = L.segs.as<Segment>();
+            a.nseg = nseg;
+            a.nbuckets = nbuckets;
+            a.cap = h->vg_bucket_cap && h->vg_bucket_cap < (uint32_t)kVgbCap ? h->vg_bucket_cap : (uint32_t)kVgbCap;
+            a.key_end = (uint32_t)((uint64_t)div_b[0] * div_b[1] * div_b[2]);
+            a.trunc_shift = trunc_shift;
+            a.vs = vs;
+            a.sorted_samples = sorted_samples;
+            a.soff = L.bsoff.as<uint32_t>();
+            a.out = L.bout.as<float4>();
+            a.status = L.bstatus.as<uint32_t>();
+            a.ticket = L.bstatus.as<uint32_t>() + nbuckets;
+            a.info = L.bstatus.as<uint32_t>() + nbuckets + 2;
+            vgb_bucket_kernel<<<nbuckets, kVgbThreads, vgb_smem_bytes(nseg), L.st>>>(a);
+            launched(h);
+            CK(cudaMemcpyAsync(L.pinned + 8, a.info, 8, cudaMemcpyDeviceToHost, L.st));
+            if (h->debug_phases) cudaEventRecord(h->dbg_ev[J.lane][3], L.st);
+            continue;
+        }
+        J.bucket = false;
         CKS(ensure_sort_buffers(h, L, J.n));
         if (h->debug_phases) cudaEventRecord(h->dbg_ev[J.lane][0], L.st);
         radix_sort_prepare(L.sort_scratch.as<uint32_t>(), J.n, vs.key_bits, L.st);
@@ -617,6 +678,21 @@ int voxelgrid_batch(lvreg_handle* h, VgJob* jobs, int nj) {
         }
         if (J.n == 0 || J.passthrough) continue;
         Lane& L = h->lane[J.lane];
+        if (J.bucket) {
+            const uint32_t a_cap = h->vg_bucket_cap && h->vg_bucket_cap < (uint32_t)kVgbCap ? h->vg_bucket_cap : (uint32_t)kVgbCap;
+            if (L.pinned[9] > a_cap) {                 // a bucket did not fit: redo this job with the device-wide sort
+                ++h->vg_bucket_fallbacks;
+                J.bucket = false;
+                CKS(voxelgrid_batch(h, &J, 1));
+                continue;
+            }
+            ++h->vg_bucket_jobs;
+            std::swap(*J.out, L.bout);                 // the kernel wrote into the lane's buffer: hand it over, keep the old one
+            *J.n_out = L.pinned[8];
+            if (*J.n_out == 0) CK(J.out->reserve(16));
+            if (h->debug_phases) { cudaEventRecord(h->dbg_ev[J.lane][4], L.st); h->dbg_ev_used |= 1u << J.lane; }
+            continue;
+        }
         const uint32_t nvox = L.pinned[8];
         CK(J.out->reserve((size_t)(nvox ? nvox : 1) * 16));
         uint32_t* okeys = nullptr;
@@ -829,17 +905,50 @@ void pose_to_affine_host(const float pose[6], float T[12]) {
     T[8] = -D;     T[9] = C * F;           T[10] = C * E;           T[11] = pose[5];
 }
 
+// PCL's VoxelGrid bounds of a cloud with the given bounding box; false when PCL would pass the cloud through (index
+// overflow) or the voxel coordinates leave the range in which the fp32 arithmetic of voxel_key is exact
+bool voxel_spec_from_bbox(const float* mn, const float* mx, float leaf, VoxelSpec* vs) {
+    const float inv = 1.0f / leaf;
+    int64_t d[3];
+    for (int a = 0; a < 3; ++a) {
+        if (!(fabsf(mn[a]) * inv < 4194304.f) || !(fabsf(mx[a]) * inv < 4194304.f)) return false;
+        d[a] = (int64_t)((mx[a] - mn[a]) * inv) + 1;
+    }
+    if (d[0] * d[1] * d[2] > (int64_t)INT32_MAX) return false;
+    vs->inv = inv;
+    int div_b[3];
+    for (int a = 0; a < 3; ++a) {
+        vs->min_b[a] = (int)floorf(mn[a] * inv);
+        const int max_b = (int)floorf(mx[a] * inv);
+        div_b[a] = max_b - vs->min_b[a] + 1;
+    }
+    vs->mul[0] = 1;
+    vs->mul[1] = div_b[0];
+    vs->mul[2] = div_b[0] * div_b[1];
+    vs->key_bits = bits_for((uint64_t)div_b[0] * div_b[1] * div_b[2] - 1);
+    return true;
+}
+
 // laserCloudMapContainer (MO:942-954): transforms the not-yet-cached clouds of the listed keyframes under their
 // current poses and measures their bounding boxes -- one batch of launches and ONE host synchronisation for all of
 // them; a keyframe is transformed once per pose, as in the reference.  Runs on the main stream, before the lanes fork.
+// With the bucketed VoxelGrid enabled the cached cloud is additionally ORDERED by its voxel index under the local
+// map's leaf size (stable: points of one voxel keep their scan order, so the sort-based filter still gives the same
+// sums on it); see voxelgrid_bucket.cuh.
 int ensure_world_cache(lvreg_handle* h, const int32_t* ids, size_t n_ids) {
+    const float leaf[2] = {h->prm.corner_leaf, h->prm.surf_leaf};
+    const bool want_sorted = h->vg_bucket_enabled;
     std::vector<Keyframe*> todo;
     for (size_t i = 0; i < n_ids; ++i) {
         Keyframe* kf = h->kfs[ids[i]];
-        if (!kf->world_ok && std::find(todo.begin(), todo.end(), kf) == todo.end()) todo.push_back(kf);
+        bool stale = !kf->world_ok;
+        for (int s = 0; s < 2; ++s)
+            if (kf->n[s] && kf->wsorted[s] && kf->wleaf[s] != leaf[s]) stale = true;     // ordered for another leaf size
+        if (stale && std::find(todo.begin(), todo.end(), kf) == todo.end()) todo.push_back(kf);
     }
     const size_t batch = 1024;                                   // 1024 keyframes x 2 clouds x 6 words = 48 KB of pinned memory
     uint32_t* host_mm = (uint32_t*)((char*)h->pinned + 8192);
+    Lane& L = h->lane[LANE_MAP_SURF];                            // its sort scratch is idle: the lanes have not forked yet
     for (size_t b0 = 0; b0 < todo.size(); b0 += batch) {
         const size_t nb = std::min(batch, todo.size() - b0);
         CK(h->kfmm.reserve(nb * 2 * 6 * 4));
@@ -852,8 +961,13 @@ int ensure_world_cache(lvreg_handle* h, const int32_t* ids, size_t n_ids) {
             for (int s = 0; s < 2; ++s) {
                 if (kf->n[s] == 0) continue;
                 CK(kf->world[s].reserve((size_t)kf->n[s] * 16));
-                transform_bbox_kernel<<<min(nblk(kf->n[s], 256), (uint32_t)h->num_sms * 4), 256, 0, h->st>>>(
-                    kf->cloud[s].as<float4>(), kf->n[s], T, kf->world[s].as<float4>(), h->kfmm.as<uint32_t>() + (k * 2 + s) * 6);
+                const uint32_t blocks = min(nblk(kf->n[s], 256), (uint32_t)h->num_sms * 4);
+                uint32_t* mm = h->kfmm.as<uint32_t>() + (k * 2 + s) * 6;
+                if (want_sorted)
+                    bbox_tf_kernel<<<blocks, 256, 0, h->st>>>(kf->cloud[s].as<float4>(), kf->n[s], T, mm);
+                else
+                    transform_bbox_kernel<<<blocks, 256, 0, h->st>>>(kf->cloud[s].as<float4>(), kf->n[s], T,
+                                                                     kf->world[s].as<float4>(), mm);
                 launched(h);
             }
         }
@@ -861,13 +975,44 @@ int ensure_world_cache(lvreg_handle* h, const int32_t* ids, size_t n_ids) {
         CK(cudaStreamSynchronize(h->st));
         for (size_t k = 0; k < nb; ++k) {
             Keyframe* kf = todo[b0 + k];
-            for (int s = 0; s < 2; ++s)
+            for (int s = 0; s < 2; ++s) {
                 for (int a = 0; a < 3; ++a) {
                     kf->wmn[s][a] = ordered_to_float(host_mm[(k * 2 + s) * 6 + a]);
                     kf->wmx[s][a] = ordered_to_float(host_mm[(k * 2 + s) * 6 + 3 + a]);
                 }
+                kf->wsorted[s] = false;
+                kf->wleaf[s] = 0.f;
+            }
+            if (want_sorted) {
+                Affine T;
+                pose_to_affine_host(kf->pose, T.m);
+                for (int s = 0; s < 2; ++s) {
+                    const uint32_t n = kf->n[s];
+                    if (n == 0) continue;
+                    VoxelSpec vs;
+                    const bool ok = leaf[s] > 0.f && voxel_spec_from_bbox(kf->wmn[s], kf->wmx[s], leaf[s], &vs);
+                    if (!ok) {                                   // cannot be ordered with 32-bit keys: cached as it is
+                        transform_kernel<<<nblk(n, 256), 256, 0, h->st>>>(kf->cloud[s].as<float4>(), n, T, kf->world[s].as<float4>());
+                        launched(h);
+                        continue;
+                    }
+                    CKS(ensure_sort_buffers(h, L, n));
+                    voxel_keys_tf_kernel<<<nblk(n, 256), 256, 0, h->st>>>(kf->cloud[s].as<float4>(), n, T, vs,
+                                                                          L.keys[0].as<uint32_t>(), L.vals[0].as<uint32_t>());
+                    launched(h);
+                    const int cur = radix_sort_pairs(L.keys[0].as<uint32_t>(), L.vals[0].as<uint32_t>(), L.keys[1].as<uint32_t>(),
+                                                     L.vals[1].as<uint32_t>(), n, vs.key_bits, L.sort_scratch.as<uint32_t>(), h->st,
+                                                     &h->call_launches);
+                    gather_tf_kernel<<<nblk(n, 256), 256, 0, h->st>>>(kf->cloud[s].as<float4>(), L.vals[cur].as<uint32_t>(), n, T,
+                                                                      kf->world[s].as<float4>());
+                    launched(h);
+                    kf->wsorted[s] = true;
+                    kf->wleaf[s] = leaf[s];
+                }
+            }
             kf->world_ok = true;
         }
+        CK(cudaGetLastError());
     }
     return LVREG_OK;
 }
@@ -928,6 +1073,11 @@ int prepare_map_jobs(lvreg_handle* h, const int32_t* ids, size_t n_ids, VgJob* j
         if (J.cached)
             for (int a = 0; a < 3; ++a) { J.mn[a] = mn[a]; J.mx[a] = mx[a]; }
         J.leaf = s == 0 ? h->prm.corner_leaf : h->prm.surf_leaf;
+        J.bucket = J.cached && h->vg_bucket_enabled;
+        for (size_t i = 0; i < n_ids && J.bucket; ++i) {
+            const Keyframe* kf = h->kfs[ids[i]];
+            if (kf->n[s] && !(kf->wsorted[s] && kf->wleaf[s] == J.leaf)) J.bucket = false;
+        }
         J.out = &ms.ds;
         J.n_out = &ms.m;
     }
@@ -1307,6 +1457,8 @@ int lvreg_create(const lvreg_params* p, int device, void* cuda_stream, lvreg_han
     cudaFuncSetAttribute(knn5_staged_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     cudaMemsetAsync(h->lmstate.p, 0, sizeof(LmState), h->st);
     // the sort pass keeps 42 KB of staging per block: ask for the large shared-memory carveout
+    cudaFuncSetAttribute(vgb_bucket_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(vgb_bucket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vgb_smem_bytes(kVgbMaxSegs));
     cudaFuncSetAttribute(rs_onesweep_kernel<kSortThreads>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     cudaFuncSetAttribute(rs_onesweep_kernel<kSortThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem_bytes(kSortThreads));
     cudaFuncSetAttribute(rs_onesweep_kernel<kSortThreadsBig>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
@@ -1326,6 +1478,10 @@ int lvreg_create(const lvreg_params* p, int device, void* cuda_stream, lvreg_han
     if (e) h->kf_cache_enabled = atoi(e) != 0;
     e = getenv("LVREG_VG_MID");
     if (e) h->vg_mid_enabled = atoi(e) != 0;
+    e = getenv("LVREG_VG_BUCKET");
+    if (e) h->vg_bucket_enabled = atoi(e) != 0;
+    e = getenv("LVREG_VG_BUCKET_CAP");
+    if (e && atoi(e) > 0) h->vg_bucket_cap = (uint32_t)atoi(e);
     e = getenv("LVREG_DEBUG_TILES");
     if (e) h->debug_tiles = atoi(e);
     e = getenv("LVREG_TPQ");
@@ -1365,7 +1521,7 @@ void lvreg_destroy(lvreg_handle* h) {
         Lane& L = h->lane[l];
         if (L.st) cudaStreamSynchronize(L.st);
         DevBuf* lb[] = {&L.stage, &L.raw, &L.concat, &L.keys[0], &L.keys[1], &L.vals[0], &L.vals[1], &L.sort_scratch,
-                        &L.scan_temp, &L.scan_in, &L.vox_start, &L.vox_keys, &L.segs, &L.small};
+                        &L.scan_temp, &L.scan_in, &L.vox_start, &L.vox_keys, &L.segs, &L.small, &L.bsoff, &L.bstatus, &L.bout};
         for (DevBuf* b : lb) b->release();
         if (L.ev) cudaEventDestroy(L.ev);
         if (L.st) cudaStreamDestroy(L.st);
@@ -3008,6 +3164,8 @@ int lvreg_debug_stage_stats(lvreg_handle* h, uint32_t out[8]) {
     CK(cudaMemcpyAsync(out, h->stagestats.p, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->st));
     CK(cudaStreamSynchronize(h->st));
     out[5] = (uint32_t)((const RegOut*)((const char*)h->pinned + 4096))->pad;   // 1 = Cholesky shortcut, 2 = 6x6 Jacobi
+    out[6] = h->vg_bucket_fallbacks;      // bucketed VoxelGrid jobs redone by the device-wide sort (a bucket overflowed)
+    out[7] = h->vg_bucket_jobs;           // VoxelGrid jobs that went through the bucketed path
     return LVREG_OK;
 }
 
