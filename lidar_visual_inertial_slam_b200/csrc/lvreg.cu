@@ -431,6 +431,7 @@ struct VgJob {
     // internal
     VoxelSpec vs{};
     int cur = 0;
+    uint32_t nbuckets = 0;
 };
 
 // Runs up to kLanes VoxelGrid filters concurrently.  Two host synchronisation points in total
@@ -593,7 +594,7 @@ int voxelgrid_batch(lvreg_handle* h, VgJob* jobs, int nj) {
             if (h->debug_phases) cudaEventRecord(h->dbg_ev[J.lane][0], L.st);
             CKS(ensure_sort_buffers(h, L, nsamp ? nsamp : 1));
             CK(L.bsoff.reserve((size_t)(nbuckets + 1) * nseg * 4));
-            CK(L.bstatus.reserve((size_t)(nbuckets + 8) * 4));
+            CK(L.bstatus.reserve((size_t)(2 * nbuckets + 8) * 4));
             CK(L.bout.reserve((size_t)J.n * 16));
             int cur = 0;
             const int trunc_shift = 0;      // truncated sample keys (one sort pass less) unbalance the buckets: a block of 16 keys can hold 4 k points
@@ -601,7 +602,7 @@ int voxelgrid_batch(lvreg_handle* h, VgJob* jobs, int nj) {
             CK(L.vox_start.reserve((size_t)(nsamp ? nsamp : 1) * 4));
             if (nsamp) {
                 radix_sort_prepare(L.sort_scratch.as<uint32_t>(), nsamp, sample_bits, L.st);
-                vgb_sample_kernel<<<min(nblk(nsamp, 256), (uint32_t)h->num_sms * 4), 256, 0, L.st>>>(
+                vgb_sample_kernel<<<min(nblk(nsamp, 1024), (uint32_t)h->num_sms * 2), 256, 0, L.st>>>(
                     L.segs.as<Segment>(), nseg, nsamp, vs, trunc_shift, sort_num_passes(sample_bits), L.vox_start.as<uint32_t>(),
                     L.keys[0].as<uint32_t>(), L.vals[0].as<uint32_t>(), sort_ghist_ptr(L.sort_scratch.as<uint32_t>(), nsamp));
                 launched(h);
@@ -616,7 +617,10 @@ int voxelgrid_batch(lvreg_handle* h, VgJob* jobs, int nj) {
                                                                                 vs, L.bsoff.as<uint32_t>());
             launched(h);
             if (h->debug_phases) cudaEventRecord(h->dbg_ev[J.lane][2], L.st);
-            CK(cudaMemsetAsync(L.bstatus.p, 0, (size_t)(nbuckets + 8) * 4, L.st));
+            uint32_t* bnvox = L.bstatus.as<uint32_t>();            // [nbuckets + 1]
+            uint32_t* bin = bnvox + nbuckets + 1;                  // [nbuckets]
+            uint32_t* binfo = bin + nbuckets;                      // [2]
+            CK(cudaMemsetAsync(binfo, 0, 8, L.st));
             VgbArgs a;
             a.segs = L.segs.as<Segment>();
             a.nseg = nseg;
@@ -627,13 +631,15 @@ int voxelgrid_batch(lvreg_handle* h, VgJob* jobs, int nj) {
             a.vs = vs;
             a.sorted_samples = sorted_samples;
             a.soff = L.bsoff.as<uint32_t>();
-            a.out = L.bout.as<float4>();
-            a.status = L.bstatus.as<uint32_t>();
-            a.ticket = L.bstatus.as<uint32_t>() + nbuckets;
-            a.info = L.bstatus.as<uint32_t>() + nbuckets + 2;
+            a.tmp = L.bout.as<float4>();
+            a.bucket_nvox = bnvox;
+            a.bucket_in = bin;
+            a.info = binfo;
             vgb_bucket_kernel<<<nbuckets, kVgbThreads, vgb_smem_bytes(nseg), L.st>>>(a);
-            launched(h);
-            CK(cudaMemcpyAsync(L.pinned + 8, a.info, 8, cudaMemcpyDeviceToHost, L.st));
+            vgb_scan_kernel<<<1, 1024, 0, L.st>>>(bnvox, nbuckets, binfo);
+            launched(h, 2);
+            CK(cudaMemcpyAsync(L.pinned + 8, binfo, 8, cudaMemcpyDeviceToHost, L.st));
+            J.nbuckets = nbuckets;
             if (h->debug_phases) cudaEventRecord(h->dbg_ev[J.lane][3], L.st);
             continue;
         }
@@ -687,9 +693,15 @@ int voxelgrid_batch(lvreg_handle* h, VgJob* jobs, int nj) {
                 continue;
             }
             ++h->vg_bucket_jobs;
-            std::swap(*J.out, L.bout);                 // the kernel wrote into the lane's buffer: hand it over, keep the old one
-            *J.n_out = L.pinned[8];
-            if (*J.n_out == 0) CK(J.out->reserve(16));
+            const uint32_t nvox_b = L.pinned[8];
+            *J.n_out = nvox_b;
+            CK(J.out->reserve((size_t)(nvox_b ? nvox_b : 1) * 16));
+            if (nvox_b) {
+                const uint32_t* bnvox = L.bstatus.as<uint32_t>();
+                vgb_compact_kernel<<<J.nbuckets, 128, 0, L.st>>>(L.bout.as<float4>(), bnvox, bnvox + J.nbuckets + 1,
+                                                                J.out->as<float4>());
+                launched(h);
+            }
             if (h->debug_phases) { cudaEventRecord(h->dbg_ev[J.lane][4], L.st); h->dbg_ev_used |= 1u << J.lane; }
             continue;
         }

@@ -14,8 +14,10 @@
 //                       (local key, payload) in shared memory -- stable LSD radix, as many <= 9-bit passes as the key RANGE
 //                       of the bucket needs, usually 2 --, finds the voxel starts, sums the voxels sequentially
 //                       in (keyframe, scan) order = the order the stable device-wide sort gave, and writes the
-//                       centroids at the bucket's offset (chained scan over the buckets' voxel counts, 32
-//                       predecessors per round trip).
+//                       centroids into the bucket's own slice of a scratch cloud.
+//   vgb_scan_kernel     voxel counts of the buckets -> output offsets (+ the total the host waits for)
+//   vgb_compact_kernel  the slices, closed up into the down-sampled map (a chained scan inside the bucket kernel was
+//                       measured first: its polling warp cost 8 % of the instructions and stalled seven others)
 //
 // HBM traffic: the points are read once (16 B, + the second touch from L2 for the sums), the centroids written once;
 // against 4 sort passes x 16 B + keys + histograms + heads + gathers before.  Results are bit-identical to the
@@ -33,7 +35,6 @@ constexpr int kVgbThreads = 256;               // 4 independent blocks per SM: t
 constexpr int kVgbItems = 16;
 constexpr int kVgbCap = kVgbThreads * kVgbItems;     // 4096
 constexpr int kVgbMaxSegs = 1 << (32 - kSegShift);   // 1024
-constexpr uint32_t kVgbFlagAgg = 1u << 30, kVgbFlagIncl = 2u << 30, kVgbFlagMask = 3u << 30;
 
 __device__ __forceinline__ uint32_t voxel_key(const float4 p, const VoxelSpec& vs) {
     const int ix = (int)(floorf(p.x * vs.inv) - (float)vs.min_b[0]);
@@ -157,9 +158,9 @@ struct VgbArgs {
     VoxelSpec vs;
     const uint32_t* sorted_samples;
     const uint32_t* soff;              // [(nbuckets + 1)][nseg]
-    float4* out;
-    volatile uint32_t* status;         // [nbuckets], zeroed
-    uint32_t* ticket;                  // zeroed
+    float4* tmp;                       // [n]: bucket b's centroids start at its input offset (points of the buckets before it)
+    uint32_t* bucket_nvox;             // [nbuckets + 1]: voxels per bucket (the scan kernel turns it into output offsets)
+    uint32_t* bucket_in;               // [nbuckets]: input offset of every bucket
     uint32_t* info;                    // [0] voxels in total, [1] largest bucket population seen (zeroed)
 };
 
@@ -186,25 +187,25 @@ __global__ void __launch_bounds__(kVgbThreads, 4) vgb_bucket_kernel(VgbArgs a) {
     uint32_t* segstart = reinterpret_cast<uint32_t*>(segsrc + a.nseg);                     // [nseg + 1]
     uint32_t* segbase = segstart + a.nseg + 1;                                             // [nseg]
     __shared__ uint32_t scan_ws[WARPS];
-    __shared__ uint32_t bucket_s, nb_s, nv_s, base_s;
+    __shared__ uint32_t nb_s, nv_s, inoff_s;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t lt_mask = (1u << lane) - 1u;
 
-    if (tid == 0) bucket_s = atomicAdd(a.ticket, 1u);
     // run starts: "no run starts here" everywhere first
     for (int i = tid; i < kVgbCap / 2; i += kVgbThreads) reinterpret_cast<uint32_t*>(seghead)[i] = 0xffffffffu;
     __syncthreads();
-    const uint32_t b = bucket_s;
+    const uint32_t b = blockIdx.x;
     const uint32_t nseg = a.nseg;
 
     // ---- the bucket's segment table: (run, first position, length) -> exclusive prefix of the lengths ----
-    uint32_t carry = 0;
-    for (uint32_t r0 = 0; r0 < nseg; r0 += kVgbThreads) {          // nseg <= 1024: at most two rounds
+    uint32_t carry = 0, before = 0;                                // before: points of this thread's runs in earlier buckets
+    for (uint32_t r0 = 0; r0 < nseg; r0 += kVgbThreads) {          // nseg <= 1024: at most four rounds
         const uint32_t r = r0 + tid;
         uint32_t len = 0;
         if (r < nseg) {
             const uint32_t s0 = a.soff[(size_t)b * nseg + r], s1 = a.soff[(size_t)(b + 1) * nseg + r];
             len = s1 - s0;
+            before += s0;
             segbase[r] = s0;
             segsrc[r] = a.segs[r].src;
         }
@@ -225,8 +226,11 @@ __global__ void __launch_bounds__(kVgbThreads, 4) vgb_bucket_kernel(VgbArgs a) {
         carry += tot;
         __syncthreads();
     }
-    if (tid == 0) { segstart[nseg] = carry; nb_s = carry; }
+    if (tid == 0) { segstart[nseg] = carry; nb_s = carry; inoff_s = 0; }
     __syncthreads();
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) before += __shfl_xor_sync(0xffffffffu, before, o);
+    if (lane == 0 && before) atomicAdd(&inoff_s, before);
     uint32_t nb = nb_s;
     if (nb > a.cap) {                                              // does not fit: flag it, contribute nothing
         if (tid == 0) atomicMax(a.info + 1, nb);
@@ -391,8 +395,8 @@ __global__ void __launch_bounds__(kVgbThreads, 4) vgb_bucket_kernel(VgbArgs a) {
         }
         if (tid == 0) {
             nv_s = tot;
-            // publish the voxel count NOW: by the time the successors (and this bucket) need offsets, it is long there
-            a.status[b] = (b == 0 ? kVgbFlagIncl : kVgbFlagAgg) | tot;
+            a.bucket_nvox[b] = tot;
+            a.bucket_in[b] = inoff_s;
         }
     }
 #pragma unroll
@@ -416,35 +420,6 @@ __global__ void __launch_bounds__(kVgbThreads, 4) vgb_bucket_kernel(VgbArgs a) {
     __syncthreads();
     const uint32_t nv = nv_s;
 
-    // ---- the bucket's offset in the output: chained scan over the buckets' voxel counts (warp 0) ----
-    if (warp == 0) {
-        uint32_t excl = 0;
-        if (b > 0) {
-            int pred = (int)b - 1;
-            for (;;) {
-                const int idx = pred - lane;
-                uint32_t s = kVgbFlagIncl;                          // before bucket 0: inclusive prefix 0
-                if (idx >= 0) {
-                    s = a.status[idx];
-                    while ((s & kVgbFlagMask) == 0) s = a.status[idx];
-                }
-                const uint32_t incl = __ballot_sync(0xffffffffu, (s & kVgbFlagIncl) != 0);
-                const int first = incl ? __ffs(incl) - 1 : 32;      // nearest predecessor with an inclusive prefix
-                uint32_t v = lane <= first ? (s & ~kVgbFlagMask) : 0u;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                excl += v;
-                if (first < 32) break;
-                pred -= 32;
-            }
-            if (lane == 0) a.status[b] = kVgbFlagIncl | (excl + nv);
-        }
-        if (lane == 0) {
-            base_s = excl;
-            if (b + 1 == a.nbuckets) a.info[0] = excl + nv;
-        }
-    }
-
     // ---- centroids: sequential sums in sorted order (= keyframe order, then scan order), half a bucket at a time;
     // the one voxel that straddles the halves carries its partial sum in registers ----
     float cx = 0.f, cy = 0.f, cz = 0.f, ci = 0.f;                  // carry of this thread's straddling voxel
@@ -461,11 +436,10 @@ __global__ void __launch_bounds__(kVgbThreads, 4) vgb_bucket_kernel(VgbArgs a) {
             }
             if (s1 > hi && !final_half) { cx = sx; cy = sy; cz = sz; ci = si; continue; }
             const float cnt = (float)(s1 - s0);
-            a.out[base + v] = make_float4(sx / cnt, sy / cnt, sz / cnt, si / cnt);
+            a.tmp[base + v] = make_float4(sx / cnt, sy / cnt, sz / cnt, si / cnt);
         }
     };
-    __syncthreads();                                               // base_s is published
-    const uint32_t base = base_s;
+    const uint32_t base = inoff_s;                                 // nv <= nb: the bucket's own input range is free
     sum_half(0, HALF, base, nb <= (uint32_t)HALF);
     if (nb > (uint32_t)HALF) {
         __syncthreads();
@@ -480,6 +454,43 @@ __global__ void __launch_bounds__(kVgbThreads, 4) vgb_bucket_kernel(VgbArgs a) {
         __syncthreads();
         sum_half(HALF, 2 * HALF, base, true);
     }
+}
+
+// exclusive scan of the buckets' voxel counts in place (one block; a few thousand values) + the grand total
+__global__ void __launch_bounds__(1024) vgb_scan_kernel(uint32_t* __restrict__ bucket_nvox, uint32_t nbuckets,
+                                                        uint32_t* __restrict__ info) {
+    __shared__ uint32_t ws[32];
+    __shared__ uint32_t carry_s;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) carry_s = 0;
+    __syncthreads();
+    for (uint32_t i0 = 0; i0 < nbuckets; i0 += 1024) {
+        const uint32_t i = i0 + tid;
+        const uint32_t v = i < nbuckets ? bucket_nvox[i] : 0u;
+        const uint32_t inc = warp_inclusive_scan(v, lane);
+        if (lane == 31) ws[warp] = inc;
+        __syncthreads();
+        uint32_t wpre = 0, tot = 0;
+        for (int w = 0; w < 32; ++w) {
+            const uint32_t s = ws[w];
+            if (w < warp) wpre += s;
+            tot += s;
+        }
+        const uint32_t carry = carry_s;
+        if (i < nbuckets) bucket_nvox[i] = carry + wpre + inc - v;
+        __syncthreads();
+        if (tid == 0) carry_s = carry + tot;
+        __syncthreads();
+    }
+    if (tid == 0) { bucket_nvox[nbuckets] = carry_s; info[0] = carry_s; }
+}
+
+// out[offset of bucket b + v] = tmp[input offset of bucket b + v]
+__global__ void __launch_bounds__(128) vgb_compact_kernel(const float4* __restrict__ tmp, const uint32_t* __restrict__ bucket_out,
+                                                          const uint32_t* __restrict__ bucket_in, float4* __restrict__ out) {
+    const uint32_t b = blockIdx.x;
+    const uint32_t o0 = bucket_out[b], nv = bucket_out[b + 1] - o0, i0 = bucket_in[b];
+    for (uint32_t v = threadIdx.x; v < nv; v += 128) out[o0 + v] = tmp[i0 + v];
 }
 
 }  // namespace lvreg
