@@ -313,7 +313,7 @@ def registration_ours(args, log):
             if st != lv.OK:
                 raise SystemExit("register_scan failed with status %d" % st)
             if keep_results:
-                out.append((pose, res, h.timings()))
+                out.append((pose, res, h.timings(), h.bucket_kernel_ms()))
         return out
 
     def timed(n, first, on_device, keep_results=True):
@@ -332,6 +332,7 @@ def registration_ours(args, log):
         wall_ms, _ = multi.reduce_timing(wall * 1e3, n, device="cuda")
         return ms, wall_ms / 1e3, out, h.launch_count() - l0
 
+    h.enable_kernel_timing(True)              # event pairs around the local-map bucket kernels (roofline_map_build_kernel)
     sampler = ClockSampler(local_rank)        # sampled under load: warm-up + the timed regions
     sampler.start()
     run_steps(args.warmup, 0, True)
@@ -349,9 +350,9 @@ def registration_ours(args, log):
     clocks = sampler.stop()
 
     # per-stage device time (CUDA events recorded by the library on the launching stream)
-    stage = {k: float(np.mean([getattr(t, k) for _, _, t in out_dev]))
+    stage = {k: float(np.mean([getattr(t, k) for _, _, t, _ in out_dev]))
              for k in ("upload_ms", "map_build_ms", "grid_build_ms", "downsample_ms", "register_ms", "total_ms")}
-    iters = [r.iterations for _, r, _ in out_dev]
+    iters = [r.iterations for _, r, _, _ in out_dev]
     res0 = out_dev[0][1]
     nq = res0.n_corner_ds + res0.n_surf_ds
     mm = res0.n_corner_map + res0.n_surf_map
@@ -379,6 +380,23 @@ def registration_ours(args, log):
     reg_s = stage["register_ms"] * 1e-3
     achieved = reg_bytes / reg_s / 1e9 if reg_s > 0 else 0.0
 
+    # the local-map VoxelGrid's bucket kernel (voxelgrid_bucket.cuh), surf map = its largest launch: event pair on its own
+    # stream inside the timed steps (the corner map's launch and the scan filters run next to it).  Algorithmic bytes per
+    # launch: 16 B per input point + 16 B per output voxel.
+    bk = [b for _, _, _, b in out_dev if b[0][1] > 0]
+    bucket = None
+    if bk:
+        b_ms = float(np.mean([b[0][1] for b in bk]))
+        b_in, b_out = int(bk[0][1][1]), int(bk[0][2][1])
+        b_bytes = 16.0 * (b_in + b_out)
+        b_gbs = b_bytes / (b_ms * 1e-3) / 1e9
+        bucket = dict(kernel="vgb_bucket_kernel (surf map: %d points in, %d voxels out)" % (b_in, b_out), bound="hbm",
+                      achieved=b_gbs, peak=hbm_peak, unit="GB/s", frac=b_gbs / hbm_peak,
+                      traffic=ncu_traffic("r02_bucket_kernel_traffic.json", b_in), algorithmic_bytes_per_launch=b_bytes,
+                      launch_ms=b_ms, corner_map_launch_ms=float(np.mean([b[0][0] for b in bk])),
+                      how="CUDA event pair around the launch on its own stream inside the timed steps",
+                      note="instruction-bound (ranking in shared memory), see profiles/r02_ncu_bucket_summary.txt")
+
     n_total_steps = args.steps * world
     value = n_total_steps / (ms_dev * 1e-3)
     e2e = n_total_steps / (ms_e2e * 1e-3)
@@ -394,20 +412,26 @@ def registration_ours(args, log):
                 gpu_launches=int(launches),
                 knn_queries_per_s=float(np.sum([it * nq for it in iters]) * world / (ms_dev * 1e-3)),
                 stages_ms=stage,
-                roofline=dict(kernel="rs_onesweep_kernel (one 8-bit radix-sort pass over %d pairs)" % n_sort, bound="hbm",
-                              achieved=sort_gbs, peak=hbm_peak, unit="GB/s", frac=sort_gbs / hbm_peak,
-                              traffic=ncu_traffic("r02_sort_kernel_traffic.json", n_sort), peak_source=peak_src,
-                              algorithmic_bytes_per_launch=sort_bytes, launch_ms=pass_ms, passes_per_sort=sort_passes,
-                              how="timed alone with CUDA events on the launching stream (the lanes overlap inside a step)"),
-                roofline_map_build_stage=dict(what="transform + concatenate + VoxelGrid of the local map (all launches of the "
-                                                   "stage, scan lanes included)", bound="hbm", achieved=stage_gbs, peak=hbm_peak,
+                # the dominant kernel of the step by duration (profiles/r02_launches_bench_c3_summary.txt): the registration
+                # kernel, ONE cooperative launch per registration; then the bucket kernel of the local-map VoxelGrid
+                roofline=dict(kernel="register_warm_kernel (one cooperative launch = the whole LM loop)", bound="hbm",
+                              achieved=achieved, peak=hbm_peak, unit="GB/s", frac=achieved / hbm_peak,
+                              traffic=ncu_traffic("r02_register_kernel_traffic.json", nq), peak_source=peak_src,
+                              algorithmic_bytes_per_launch=reg_bytes, launch_ms=stage["register_ms"],
+                              share_of_step=stage["register_ms"] / (ms_dev / args.steps),
+                              how="the library's CUDA event pair around the launch inside the timed steps",
+                              note="issue/latency-bound, the map stays L2-resident: a few % of HBM peak by construction"),
+                roofline_map_build_kernel=bucket,
+                roofline_map_build_stage=dict(what="VoxelGrid of the local map from the resident keyframes + down-sampling of the "
+                                                   "scan (all launches of the stage)", bound="hbm", achieved=stage_gbs, peak=hbm_peak,
                                               unit="GB/s", frac=stage_gbs / hbm_peak, algorithmic_bytes=stage_bytes,
                                               stage_ms=stage["map_build_ms"]),
-                roofline_register=dict(kernel="register_warm_kernel (one cooperative launch = the whole LM loop)", bound="hbm",
-                                       achieved=achieved, peak=hbm_peak, unit="GB/s", frac=achieved / hbm_peak,
-                                       traffic=ncu_traffic("r02_register_kernel_traffic.json", nq),
-                                       algorithmic_bytes_per_launch=reg_bytes, launch_ms=stage["register_ms"],
-                                       note="issue/latency-bound, the map stays L2-resident: a few % of HBM peak by construction"),
+                roofline_sort_pass=dict(kernel="rs_onesweep_kernel (one 8-bit radix-sort pass over %d pairs; since the bucketed "
+                                               "VoxelGrid it only sorts the samples, scans and submaps)" % n_sort, bound="hbm",
+                                        achieved=sort_gbs, peak=hbm_peak, unit="GB/s", frac=sort_gbs / hbm_peak,
+                                        traffic=ncu_traffic("r02_sort_kernel_traffic.json", n_sort),
+                                        algorithmic_bytes_per_launch=sort_bytes, launch_ms=pass_ms, passes_per_sort=sort_passes,
+                                        how="timed alone with CUDA events on the launching stream"),
                 clocks=clocks, wall_s=dict(resident=wall_dev, e2e=wall_e2e))
     if sustained:
         line["sustained"] = sustained
@@ -430,7 +454,7 @@ def registration_ours(args, log):
         same_iters = True
         for k, (cp, cr) in enumerate(zip(cposes, cres)):
             j = (k + 1) % N_RING_SCANS                 # the CPU arm ran one warm-up step first
-            for (gp, gr, _), i in zip(out_dev, range(args.warmup, args.warmup + args.steps)):
+            for (gp, gr, _, _), i in zip(out_dev, range(args.warmup, args.warmup + args.steps)):
                 if i % N_RING_SCANS == j:
                     rerr = max(rerr, float(np.abs(gp[:3] - cp[:3]).max()))
                     perr = max(perr, float(np.abs(gp[3:] - cp[3:]).max()))

@@ -410,6 +410,12 @@ int lvreg_debug_tile_times(lvreg_handle* h, uint32_t* ns_out, size_t cap, size_t
  * out[6] = local-map VoxelGrid jobs that had to be redone by the device-wide sort because a bucket of the
  * sample-sort path overflowed, out[7] = jobs completed by the sample-sort path (since the handle was created). */
 int lvreg_debug_stage_stats(lvreg_handle* h, uint32_t out[8]);
+/* Measurement support (bench.py `roofline`): with timing enabled every call brackets the bucket kernel of each local-map
+ * VoxelGrid (extractCloud, MO:959-965; voxelgrid_bucket.cuh) with a CUDA event pair on the stream it is launched on.
+ * lvreg_get_bucket_kernel_ms returns, for the last call, [0] corner map / [1] surf map: the kernel's duration in ms
+ * (0 if the map did not go through that kernel), its input points and its output voxels. */
+int lvreg_enable_kernel_timing(lvreg_handle* h, int on);
+int lvreg_get_bucket_kernel_ms(lvreg_handle* h, float ms[2], uint32_t n_in[2], uint32_t n_out[2]);
 /* total kernels launched by this handle since creation */
 int lvreg_get_launch_count(const lvreg_handle* h, uint64_t* n);
 /* kNN micro-benchmark on device-resident data: runs `repeats` launches of the chosen variant on

@@ -651,6 +651,18 @@ class Lvreg:
         self._ck(self.L.lvreg_debug_stage_stats(self.h, out.ctypes.data_as(C.c_void_p)))
         return out
 
+    def enable_kernel_timing(self, on=True):
+        self._ck(self.L.lvreg_enable_kernel_timing(self.h, C.c_int(1 if on else 0)))
+
+    def bucket_kernel_ms(self):
+        """(ms[2], points_in[2], voxels_out[2]) of the local-map bucket kernels of the last call (corner, surf)"""
+        ms = np.zeros(2, np.float32)
+        nin = np.zeros(2, np.uint32)
+        nout = np.zeros(2, np.uint32)
+        self._ck(self.L.lvreg_get_bucket_kernel_ms(self.h, ms.ctypes.data_as(C.c_void_p), nin.ctypes.data_as(C.c_void_p),
+                                                   nout.ctypes.data_as(C.c_void_p)))
+        return ms, nin, nout
+
     def launch_count(self):
         n = C.c_uint64(0)
         self._ck(self.L.lvreg_get_launch_count(self.h, C.byref(n)))

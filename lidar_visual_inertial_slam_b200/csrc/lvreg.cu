@@ -131,6 +131,8 @@ struct Keyframe {
     bool world_ok = false;
     bool wsorted[2] = {false, false};   // world[s] is ordered by the voxel index of leaf wleaf[s] (voxelgrid_bucket.cuh)
     float wleaf[2] = {0.f, 0.f};
+    DevBuf wkey[2];                     // ... and the points' voxel coordinates relative to wminb, packed in 4 bytes
+    int wminb[2][3] = {{0, 0, 0}, {0, 0, 0}};
     float wmn[2][3] = {{0, 0, 0}, {0, 0, 0}}, wmx[2][3] = {{0, 0, 0}, {0, 0, 0}};
 };
 
@@ -166,6 +168,8 @@ struct Lane {
     DevBuf bsoff, bstatus, bout;            // bucketed VoxelGrid: segment table, chained-scan status, output (swapped with the map)
     uint32_t* pinned = nullptr;             // 64 words of page-locked host memory
     std::vector<Segment> seg_host;
+    Segment* seg_pin = nullptr;             // page-locked staging of seg_host (a pageable source makes the copy synchronous)
+    size_t seg_pin_cap = 0;
 };
 
 }  // namespace
@@ -186,12 +190,21 @@ struct lvreg_handle {
     int debug_phases = 0;         // LVREG_DEBUG_PHASES=1: per-lane phase time stamps of the VoxelGrid batch on stderr
     cudaEvent_t dbg_ev[kLanes][6] = {};
     unsigned dbg_ev_used = 0;
+    double dbg_host_us[8] = {};   // LVREG_DEBUG_PHASES: host clock at call begin / first chain / all enqueued / after sync / ...
     bool kf_cache_enabled = true; // LVREG_KF_CACHE=0: transform the keyframe clouds on every map build (experiments)
     DevBuf kfmm;                  // bounding-box slots of the keyframe clouds being cached
     bool vg_mid_enabled = true;   // LVREG_VG_MID=0 disables the cooperative single-launch VoxelGrid (experiments)
     bool vg_bucket_enabled = true;  // LVREG_VG_BUCKET=0: large cached maps through the device-wide sort (experiments)
+    bool vg_cached_first = false;   // LVREG_VG_CACHED_FIRST=1: enqueue the whole chain of the cached (map) jobs before the scan lanes
+                                    // (measured slower at C3: the scan filters then compete with the bucket kernel instead of
+                                    // overlapping the latency-bound sample sort)
+    bool dbg_no_precompact = false, dbg_nowkey = false, dbg_reverse = false, dbg_dealt = false, dbg_alloc = false;   // LVREG_DEBUG_* experiments
     uint32_t vg_bucket_cap = 0;     // LVREG_VG_BUCKET_CAP: smaller bucket capacity, to exercise the overflow fallback
     uint32_t vg_bucket_fallbacks = 0, vg_bucket_jobs = 0;
+    bool kernel_timing = false;        // lvreg_enable_kernel_timing: event pairs around the bucket kernels of a call
+    cudaEvent_t kt_ev[2][2] = {};
+    bool kt_set[2] = {false, false};
+    uint32_t kt_n_in[2] = {0, 0};
     int debug_tiles = 0;          // LVREG_DEBUG_TILES=1: record per-tile durations of iteration 1
     uint32_t debug_ntiles = 0;
     int force_tpq = -1;           // -1 auto, 0 grouped, 1 thread-per-query (LVREG_TPQ)
@@ -268,10 +281,12 @@ inline uint32_t nblk(uint32_t n, uint32_t per) { return (n + per - 1) / per; }
 enum { SM_MM = 0 /*6 u32*/, SM_NVOX = 8, SM_TOTAL = 9, SM_CONV = 10, SM_SMALLVG = 32 /*VgSmallInfo, 8 words*/, SM_WORDS = 64 };
 
 inline void launched(lvreg_handle* h, int k = 1) { h->call_launches += k; }
+inline double host_now_us() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 inline void begin_call(lvreg_handle* h) {
     h->call_launches = 0;
     for (int i = 0; i < EV_COUNT; ++i) h->ev_set[i] = false;
+    h->kt_set[0] = h->kt_set[1] = false;
     memset(&h->last, 0, sizeof(h->last));
 }
 inline void mark(lvreg_handle* h, int which) {
@@ -431,8 +446,28 @@ struct VgJob {
     // internal
     VoxelSpec vs{};
     int cur = 0;
-    uint32_t nbuckets = 0;
+    uint32_t nbuckets = 0, compact_cap = 0;
+    bool bucket_enqueued = false;
+    bool mark_map_stage = false;       // record EV_MAP on the main stream when the filters are done (before the grids)
 };
+
+// segment table of a lane -> device, through page-locked staging so that the copy really is asynchronous.  Every
+// VoxelGrid batch ends with a synchronisation of its lanes, so the staging buffer is free again by the next upload.
+int upload_segs(lvreg_handle* h, Lane& L, cudaStream_t st) {
+    const size_t n = L.seg_host.size();
+    CK(L.segs.reserve(n * sizeof(Segment)));
+    if (n > L.seg_pin_cap) {
+        if (L.seg_pin) cudaFreeHost(L.seg_pin);
+        L.seg_pin = nullptr;
+        L.seg_pin_cap = 0;
+        const size_t cap = n < 256 ? 256 : 2 * n;
+        CK(cudaMallocHost((void**)&L.seg_pin, cap * sizeof(Segment)));
+        L.seg_pin_cap = cap;
+    }
+    memcpy(L.seg_pin, L.seg_host.data(), n * sizeof(Segment));
+    CK(cudaMemcpyAsync(L.segs.p, L.seg_pin, n * sizeof(Segment), cudaMemcpyHostToDevice, st));
+    return LVREG_OK;
+}
 
 // Runs up to kLanes VoxelGrid filters concurrently.  Two host synchronisation points in total
 // (bounding boxes, voxel counts).  On return the centroid kernels are enqueued on the lane
@@ -445,14 +480,21 @@ int voxelgrid_batch(lvreg_handle* h, VgJob* jobs, int nj) {
     for (int a2 = 0; a2 < nj; ++a2)
         for (int b2 = a2 + 1; b2 < nj; ++b2)
             if (jobs[order[b2]].n > jobs[order[a2]].n) { int t2 = order[a2]; order[a2] = order[b2]; order[b2] = t2; }
+    if (h->dbg_reverse) { for (int a2 = 0; a2 < nj / 2; ++a2) { int t2 = order[a2]; order[a2] = order[nj - 1 - a2]; order[nj - 1 - a2] = t2; } }
+    // Two rounds: the jobs over cached world-frame clouds first -- they depend on nothing, and the largest of them is the
+    // critical path of the call, so their whole chain is enqueued before the host spends time on the other lanes --
+    // then the rest, which share the bounding-box synchronisation.
+    for (int round = 0; round < 2; ++round) {
     // ---- phase 1: (transform + concatenate +) bounding box ----
     unsigned sync1_mask = 0;
     for (int jo = 0; jo < nj; ++jo) {
         VgJob& J = jobs[order[jo]];
+        if ((J.cached && J.n > 0 && h->vg_cached_first) != (round == 0)) continue;
         Lane& L = h->lane[J.lane];
         *J.n_out = 0;
         J.passthrough = 0;
         J.small = false;
+        J.bucket_enqueued = false;
         if (J.n == 0) {
             CK(J.out->reserve(16));
             continue;
@@ -471,8 +513,7 @@ int voxelgrid_batch(lvreg_handle* h, VgJob* jobs, int nj) {
             a.nseg = 0;
             a.world = nullptr;
             if (J.from_segments) {
-                CK(L.segs.reserve(L.seg_host.size() * sizeof(Segment)));
-                CK(cudaMemcpyAsync(L.segs.p, L.seg_host.data(), L.seg_host.size() * sizeof(Segment), cudaMemcpyHostToDevice, L.st));
+                CKS(upload_segs(h, L, L.st));
                 CK(L.concat.reserve((size_t)J.n * 16));
                 a.segs = L.segs.as<Segment>();
                 a.nseg = (uint32_t)L.seg_host.size();
@@ -530,16 +571,14 @@ int voxelgrid_batch(lvreg_handle* h, VgJob* jobs, int nj) {
             continue;
         }
         if (J.cached) {                                // world-frame clouds and their exact bbox are already known
-            CK(L.segs.reserve(L.seg_host.size() * sizeof(Segment)));
-            CK(cudaMemcpyAsync(L.segs.p, L.seg_host.data(), L.seg_host.size() * sizeof(Segment), cudaMemcpyHostToDevice, L.st));
+            CKS(upload_segs(h, L, L.st));
             continue;
         }
         uint32_t* mm = L.small.as<uint32_t>() + SM_MM;
         CK(cudaMemsetAsync(mm, 0xff, 3 * sizeof(uint32_t), L.st));
         CK(cudaMemsetAsync(mm + 3, 0, 3 * sizeof(uint32_t), L.st));
         if (J.from_segments) {
-            CK(L.segs.reserve(L.seg_host.size() * sizeof(Segment)));
-            CK(cudaMemcpyAsync(L.segs.p, L.seg_host.data(), L.seg_host.size() * sizeof(Segment), cudaMemcpyHostToDevice, L.st));
+            CKS(upload_segs(h, L, L.st));
             CK(L.concat.reserve((size_t)J.n * 16));
             transform_concat_kernel<<<min(nblk(J.n, 2048), (uint32_t)h->num_sms * 16), 256, 0, L.st>>>(
                 L.segs.as<Segment>(), (uint32_t)L.seg_host.size(), J.n, L.concat.as<float4>(), mm);
@@ -555,6 +594,7 @@ int voxelgrid_batch(lvreg_handle* h, VgJob* jobs, int nj) {
     // ---- phase 2: keys, stable sort, run heads ----
     for (int jo = 0; jo < nj; ++jo) {
         VgJob& J = jobs[order[jo]];
+        if ((J.cached && J.n > 0 && h->vg_cached_first) != (round == 0)) continue;
         if (J.n == 0 || J.small) continue;
         Lane& L = h->lane[J.lane];
         if (!J.cached)
@@ -635,12 +675,20 @@ int voxelgrid_batch(lvreg_handle* h, VgJob* jobs, int nj) {
             a.bucket_nvox = bnvox;
             a.bucket_in = bin;
             a.info = binfo;
+            const bool timed = h->kernel_timing && J.lane < 2;
+            if (timed) cudaEventRecord(h->kt_ev[J.lane][0], L.st);
             vgb_bucket_kernel<<<nbuckets, kVgbThreads, vgb_smem_bytes(nseg), L.st>>>(a);
+            if (timed) { cudaEventRecord(h->kt_ev[J.lane][1], L.st); h->kt_set[J.lane] = true; h->kt_n_in[J.lane] = J.n; }
             vgb_scan_kernel<<<1, 1024, 0, L.st>>>(bnvox, nbuckets, binfo);
             launched(h, 2);
             CK(cudaMemcpyAsync(L.pinned + 8, binfo, 8, cudaMemcpyDeviceToHost, L.st));
-            J.nbuckets = nbuckets;
             if (h->debug_phases) cudaEventRecord(h->dbg_ev[J.lane][3], L.st);
+            J.nbuckets = nbuckets;
+            // the slices are closed up right away (below, after every chain is enqueued) if the output buffer of the
+            // previous build is, as usual, large enough
+            J.compact_cap = (uint32_t)std::min<size_t>(J.out->cap / 16, 0xffffffffu);
+            if (h->dbg_no_precompact) J.compact_cap = 0;
+            J.bucket_enqueued = true;
             continue;
         }
         J.bucket = false;
@@ -670,7 +718,31 @@ int voxelgrid_batch(lvreg_handle* h, VgJob* jobs, int nj) {
         CK(cudaMemcpyAsync(L.pinned + 8, d_nvox, 4, cudaMemcpyDeviceToHost, L.st));
         if (h->debug_phases) cudaEventRecord(h->dbg_ev[J.lane][3], L.st);
     }
+    }   // rounds
+    // compaction of the sample-sort jobs (after every chain is enqueued: the largest job's chain goes out first)
+    for (int jo = 0; jo < nj; ++jo) {
+        VgJob& J = jobs[order[jo]];
+        if (!J.bucket_enqueued || !J.compact_cap) continue;
+        Lane& L = h->lane[J.lane];
+        const uint32_t* bnvox = L.bstatus.as<uint32_t>();
+        vgb_compact_kernel<<<J.nbuckets, 128, 0, L.st>>>(L.bout.as<float4>(), bnvox, bnvox + J.nbuckets + 1, J.nbuckets,
+                                                        J.compact_cap, J.out->as<float4>());
+        launched(h);
+        if (h->debug_phases) { cudaEventRecord(h->dbg_ev[J.lane][4], L.st); h->dbg_ev_used |= 1u << J.lane; }
+    }
+    // local-map jobs: the filters end here for the stage timings (the host's synchronisation below and what it enqueues
+    // afterwards belong to the grid stage)
+    {
+        bool any = false;
+        for (int j = 0; j < nj; ++j) any = any || jobs[j].mark_map_stage;
+        if (any && !h->ev_set[EV_MAP]) {
+            lanes_join(h, mask);
+            mark(h, EV_MAP);
+        }
+    }
+    if (h->debug_phases) h->dbg_host_us[2] = host_now_us();
     CK(lanes_sync(h, mask));
+    if (h->debug_phases) h->dbg_host_us[3] = host_now_us();
     // ---- phase 3: centroids (left running on the lane streams) ----
     for (int jo = 0; jo < nj; ++jo) {
         VgJob& J = jobs[order[jo]];
@@ -695,14 +767,15 @@ int voxelgrid_batch(lvreg_handle* h, VgJob* jobs, int nj) {
             ++h->vg_bucket_jobs;
             const uint32_t nvox_b = L.pinned[8];
             *J.n_out = nvox_b;
-            CK(J.out->reserve((size_t)(nvox_b ? nvox_b : 1) * 16));
-            if (nvox_b) {
+            if (nvox_b > J.compact_cap) {              // first build, or the map grew past the buffer: grow it, then compact
+                if (h->debug_phases) fprintf(stderr, "[lvreg] lane %d: compaction repeated after the synchronisation (%u voxels, buffer for %u)\n", J.lane, nvox_b, J.compact_cap);
+                CK(J.out->reserve((size_t)nvox_b * 16 + (size_t)nvox_b * 2));
                 const uint32_t* bnvox = L.bstatus.as<uint32_t>();
-                vgb_compact_kernel<<<J.nbuckets, 128, 0, L.st>>>(L.bout.as<float4>(), bnvox, bnvox + J.nbuckets + 1,
-                                                                J.out->as<float4>());
+                vgb_compact_kernel<<<J.nbuckets, 128, 0, L.st>>>(L.bout.as<float4>(), bnvox, bnvox + J.nbuckets + 1, J.nbuckets,
+                                                                nvox_b, J.out->as<float4>());
                 launched(h);
             }
-            if (h->debug_phases) { cudaEventRecord(h->dbg_ev[J.lane][4], L.st); h->dbg_ev_used |= 1u << J.lane; }
+            if (nvox_b == 0) CK(J.out->reserve(16));
             continue;
         }
         const uint32_t nvox = L.pinned[8];
@@ -1002,7 +1075,12 @@ int ensure_world_cache(lvreg_handle* h, const int32_t* ids, size_t n_ids) {
                     const uint32_t n = kf->n[s];
                     if (n == 0) continue;
                     VoxelSpec vs;
-                    const bool ok = leaf[s] > 0.f && voxel_spec_from_bbox(kf->wmn[s], kf->wmx[s], leaf[s], &vs);
+                    bool ok = leaf[s] > 0.f && voxel_spec_from_bbox(kf->wmn[s], kf->wmx[s], leaf[s], &vs);
+                    if (ok) {                                    // the packed voxel coordinates have 11 | 11 | 10 bits
+                        const int dxk = vs.mul[1], dyk = vs.mul[1] ? vs.mul[2] / vs.mul[1] : 0;
+                        const int dzk = (int)floorf(kf->wmx[s][2] * vs.inv) - vs.min_b[2] + 1;
+                        ok = dxk <= (1 << kVgbPackX) && dyk <= (1 << kVgbPackY) && dzk <= (1 << kVgbPackZ);
+                    }
                     if (!ok) {                                   // cannot be ordered with 32-bit keys: cached as it is
                         transform_kernel<<<nblk(n, 256), 256, 0, h->st>>>(kf->cloud[s].as<float4>(), n, T, kf->world[s].as<float4>());
                         launched(h);
@@ -1015,9 +1093,11 @@ int ensure_world_cache(lvreg_handle* h, const int32_t* ids, size_t n_ids) {
                     const int cur = radix_sort_pairs(L.keys[0].as<uint32_t>(), L.vals[0].as<uint32_t>(), L.keys[1].as<uint32_t>(),
                                                      L.vals[1].as<uint32_t>(), n, vs.key_bits, L.sort_scratch.as<uint32_t>(), h->st,
                                                      &h->call_launches);
-                    gather_tf_kernel<<<nblk(n, 256), 256, 0, h->st>>>(kf->cloud[s].as<float4>(), L.vals[cur].as<uint32_t>(), n, T,
-                                                                      kf->world[s].as<float4>());
+                    CK(kf->wkey[s].reserve((size_t)n * 4));
+                    gather_tf_kernel<<<nblk(n, 256), 256, 0, h->st>>>(kf->cloud[s].as<float4>(), L.vals[cur].as<uint32_t>(), n, T, vs,
+                                                                      kf->world[s].as<float4>(), kf->wkey[s].as<uint32_t>());
                     launched(h);
+                    for (int a = 0; a < 3; ++a) kf->wminb[s][a] = vs.min_b[a];
                     kf->wsorted[s] = true;
                     kf->wleaf[s] = leaf[s];
                 }
@@ -1065,7 +1145,10 @@ int prepare_map_jobs(lvreg_handle* h, const int32_t* ids, size_t n_ids, VgJob* j
             sg.src = cached[s] ? kf->world[s].as<float4>() : kf->cloud[s].as<float4>();
             sg.begin = (uint32_t)total;
             sg.n = kf->n[s];
-            pose_to_affine_host(kf->pose, sg.T.m);        // pclPointToAffine3f(cloudKeyPoses6D[id])
+            sg.wkey = cached[s] && kf->wsorted[s] && !h->dbg_nowkey ? kf->wkey[s].as<uint32_t>() : nullptr;
+            for (int a = 0; a < 3; ++a) sg.kminb[a] = kf->wminb[s][a];
+            if (cached[s]) memset(&sg.T, 0, sizeof(sg.T));   // world-frame cloud: no transform
+            else pose_to_affine_host(kf->pose, sg.T.m);      // pclPointToAffine3f(cloudKeyPoses6D[id])
             L.seg_host.push_back(sg);
             total += kf->n[s];
             for (int a = 0; a < 3; ++a) {
@@ -1092,6 +1175,7 @@ int prepare_map_jobs(lvreg_handle* h, const int32_t* ids, size_t n_ids, VgJob* j
         }
         J.out = &ms.ds;
         J.n_out = &ms.m;
+        J.mark_map_stage = true;
     }
     return LVREG_OK;
 }
@@ -1124,9 +1208,10 @@ int prepare_scan_jobs(lvreg_handle* h, const lvreg_cloud* corner_raw, const lvre
 int build_map_grids(lvreg_handle* h, VgJob* map_jobs) {
     for (int s = 0; s < 2; ++s) {
         const bool have_bb = map_jobs && map_jobs[s].n > 0;
-        CKS(build_grid(h, h->lane[s], h->map[s], have_bb ? map_jobs[s].mn : nullptr, have_bb ? map_jobs[s].mx : nullptr,
+        MapSide& ms = h->map[s];
+        CKS(build_grid(h, h->lane[s], ms, have_bb ? map_jobs[s].mn : nullptr, have_bb ? map_jobs[s].mx : nullptr,
                        0.f, nullptr, true));
-        h->map[s].valid = true;
+        ms.valid = true;
     }
     return LVREG_OK;
 }
@@ -1251,7 +1336,7 @@ int scan2map_impl(lvreg_handle* h, float pose[6], lvreg_result* res) {
         args.scan[s] = h->scan_ds[s].as<float4>();
         args.n[s] = h->n_scan[s];
     }
-    args.dealt = getenv("LVREG_DEALT") ? 1 : 0;
+    args.dealt = h->dbg_dealt ? 1 : 0;
     if (want_sorted_scan(h, reg_variant(h)) && !args.dealt)     // spatially compact tiles: similar paths, shared cache lines
         for (int s = 0; s < 2; ++s) {
             if (!h->scan_sorted_ok[s]) CKS(sort_scan_for_search(h, s, h->st));
@@ -1443,9 +1528,15 @@ int lvreg_create(const lvreg_params* p, int device, void* cuda_stream, lvreg_han
     }
     if (cudaMallocHost(&h->pinned, 65536) != cudaSuccess) return bail(LVREG_ERR_CUDA);
     if (cudaEventCreateWithFlags(&h->ev_main, cudaEventDisableTiming) != cudaSuccess) return bail(LVREG_ERR_CUDA);
+    if (const char* se = getenv("LVREG_DEBUG_STREAM_SHIFT"))       // experiments: dummy streams created ahead of the lanes
+        for (int i = 0; i < atoi(se); ++i) { cudaStream_t d; cudaStreamCreateWithFlags(&d, cudaStreamNonBlocking); }
     for (int l = 0; l < kLanes; ++l) {
         Lane& L = h->lane[l];
-        if (cudaStreamCreateWithFlags(&L.st, cudaStreamNonBlocking) != cudaSuccess ||
+        int prio_lo = 0, prio_hi = 0;
+        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+        const char* pe = getenv("LVREG_LANE_PRIO");                  // experiments: bit l set = lane l gets the high priority
+        const int prio = pe && ((atoi(pe) >> l) & 1) ? prio_hi : prio_lo;
+        if (cudaStreamCreateWithPriority(&L.st, cudaStreamNonBlocking, prio) != cudaSuccess ||
             cudaEventCreateWithFlags(&L.ev, cudaEventDisableTiming) != cudaSuccess ||
             L.small.reserve(SM_WORDS * 4) != cudaSuccess)
             return bail(LVREG_ERR_CUDA);
@@ -1492,6 +1583,13 @@ int lvreg_create(const lvreg_params* p, int device, void* cuda_stream, lvreg_han
     if (e) h->vg_mid_enabled = atoi(e) != 0;
     e = getenv("LVREG_VG_BUCKET");
     if (e) h->vg_bucket_enabled = atoi(e) != 0;
+    h->dbg_no_precompact = getenv("LVREG_DEBUG_NO_PRECOMPACT") != nullptr;
+    h->dbg_nowkey = getenv("LVREG_DEBUG_NOWKEY") != nullptr;
+    h->dbg_reverse = getenv("LVREG_DEBUG_REVERSE") != nullptr;
+    h->dbg_dealt = getenv("LVREG_DEALT") != nullptr;
+    h->dbg_alloc = getenv("LVREG_DEBUG_ALLOC") != nullptr;
+    e = getenv("LVREG_VG_CACHED_FIRST");
+    if (e) h->vg_cached_first = atoi(e) != 0;
     e = getenv("LVREG_VG_BUCKET_CAP");
     if (e && atoi(e) > 0) h->vg_bucket_cap = (uint32_t)atoi(e);
     e = getenv("LVREG_DEBUG_TILES");
@@ -1535,6 +1633,7 @@ void lvreg_destroy(lvreg_handle* h) {
         DevBuf* lb[] = {&L.stage, &L.raw, &L.concat, &L.keys[0], &L.keys[1], &L.vals[0], &L.vals[1], &L.sort_scratch,
                         &L.scan_temp, &L.scan_in, &L.vox_start, &L.vox_keys, &L.segs, &L.small, &L.bsoff, &L.bstatus, &L.bout};
         for (DevBuf* b : lb) b->release();
+        if (L.seg_pin) cudaFreeHost(L.seg_pin);
         if (L.ev) cudaEventDestroy(L.ev);
         if (L.st) cudaStreamDestroy(L.st);
     }
@@ -1564,6 +1663,9 @@ void lvreg_destroy(lvreg_handle* h) {
                       &h->idxbuf, &h->d2buf, &h->brute_partial, &h->coeffbuf, &h->flagbuf};
     for (DevBuf* b : bufs) b->release();
     h->kf_arena.release_all();
+    for (int l = 0; l < 2; ++l)
+        for (int k = 0; k < 2; ++k)
+            if (h->kt_ev[l][k]) cudaEventDestroy(h->kt_ev[l][k]);
     if (h->ev_main) cudaEventDestroy(h->ev_main);
     if (h->pinned) cudaFreeHost(h->pinned);
     for (int i = 0; i < EV_COUNT; ++i)
@@ -1621,6 +1723,7 @@ Keyframe* take_keyframe(lvreg_handle* h) {
         Keyframe* kf = new Keyframe();
         kf->cloud[0].arena = kf->cloud[1].arena = &h->kf_arena;
         kf->world[0].arena = kf->world[1].arena = &h->kf_arena;
+        kf->wkey[0].arena = kf->wkey[1].arena = &h->kf_arena;
         return kf;
     }
     Keyframe* kf = h->kf_free.back();
@@ -1710,7 +1813,7 @@ int lvreg_clear_keyframes(lvreg_handle* h) {
         else delete kf;
     }
     for (Keyframe* kf : h->kf_free) {
-        for (DevBuf* b : {&kf->cloud[0], &kf->cloud[1], &kf->world[0], &kf->world[1]}) { b->p = nullptr; b->cap = 0; }
+        for (DevBuf* b : {&kf->cloud[0], &kf->cloud[1], &kf->world[0], &kf->world[1], &kf->wkey[0], &kf->wkey[1]}) { b->p = nullptr; b->cap = 0; }
         kf->world_ok = false;
     }
     h->kf_arena.reset();
@@ -1731,7 +1834,7 @@ int lvreg_build_local_map(lvreg_handle* h, const int32_t* ids, size_t n, lvreg_m
     lanes_fork(h, 0x3);
     CKS(voxelgrid_batch(h, jobs, 2));
     lanes_join(h, 0x3);
-    mark(h, EV_MAP);
+    if (!h->ev_set[EV_MAP]) mark(h, EV_MAP);
     CKS(build_map_grids(h, jobs));
     lanes_join(h, 0x3);
     mark(h, EV_GRID);
@@ -1762,7 +1865,7 @@ int lvreg_set_local_map(lvreg_handle* h, const lvreg_cloud* corner_ds, const lvr
         h->map[s].n_in = c[s]->n;
     }
     lanes_join(h, 0x3);
-    mark(h, EV_MAP);
+    if (!h->ev_set[EV_MAP]) mark(h, EV_MAP);
     CKS(build_map_grids(h, nullptr));
     lanes_join(h, 0x3);
     mark(h, EV_GRID);
@@ -1858,6 +1961,7 @@ int lvreg_register_scan(lvreg_handle* h, const lvreg_cloud* corner_raw, const lv
     CK(cudaSetDevice(h->device));
     begin_call(h);
     mark(h, EV_BEGIN);
+    if (h->debug_phases) h->dbg_host_us[0] = host_now_us();
     // extractSurroundingKeyFrames (MO:318) and downsampleCurrentScan (MO:320) are independent: all
     // four VoxelGrid filters run concurrently on the lanes and share two host synchronisations
     VgJob jobs[4];
@@ -1872,26 +1976,32 @@ int lvreg_register_scan(lvreg_handle* h, const lvreg_cloud* corner_raw, const lv
     lanes_fork(h, mask);
     CKS(prepare_scan_jobs(h, corner_raw, surf_raw, jobs + nj));
     nj += 2;
+    if (h->debug_phases) h->dbg_host_us[1] = host_now_us();
     CKS(voxelgrid_batch(h, jobs, nj));
+    if (h->debug_phases) h->dbg_host_us[4] = host_now_us();
     // large scans are Morton-ordered for the search: normally by the single-launch filter itself (morton_done)
     for (int s = 0; s < 2; ++s) h->scan_sorted_ok[s] = jobs[nj - 2 + s].morton_done;
     if (want_sorted_scan(h, reg_variant(h)))
         for (int s = 0; s < 2; ++s)
             if (!h->scan_sorted_ok[s]) CKS(sort_scan_for_search(h, s, h->lane[LANE_SCAN_CORNER + s].st));
+    if (h->debug_phases)
+        for (int l = 0; l < kLanes; ++l) cudaEventRecord(h->dbg_ev[l][5], h->lane[l].st);
     lanes_join(h, mask);
-    mark(h, EV_MAP);
+    if (!h->ev_set[EV_MAP]) mark(h, EV_MAP);
     if (ids) {
         CKS(build_map_grids(h, jobs));
         lanes_join(h, 0x3);
     }
     mark(h, EV_GRID);
-    if (getenv("LVREG_DEBUG_ALLOC") && g_alloc_calls) {
+    if (h->dbg_alloc && g_alloc_calls) {
         fprintf(stderr, "[lvreg] allocations in this call: %d calls, %.1f MB requested, %.2f ms\n", g_alloc_calls,
                 g_alloc_bytes / 1048576.0, g_alloc_ms);
         g_alloc_ms = 0.0; g_alloc_bytes = 0; g_alloc_calls = 0;
     }
     guard.commit();                                            // scan and map are consistent from here on
+    if (h->debug_phases) h->dbg_host_us[5] = host_now_us();
     int s = scan2map_impl(h, pose, res);                      // scan2MapOptimization MO:322
+    if (h->debug_phases) h->dbg_host_us[6] = host_now_us();
     if (s == LVREG_OK || s == LVREG_ERR_NOT_ENOUGH_FEATURES) {
         CK(cudaStreamSynchronize(h->st));
         // the four filters overlap, so they are reported together: map_build_ms covers H2D + pack +
@@ -1911,6 +2021,13 @@ int lvreg_register_scan(lvreg_handle* h, const lvreg_cloud* corner_raw, const lv
                         h->last.map_build_ms + h->last.grid_build_ms + h->last.register_ms);
             }
             h->dbg_ev_used = 0;
+            float e[kLanes];
+            for (int l = 0; l < kLanes; ++l) cudaEventElapsedTime(&e[l], h->ev[EV_BEGIN], h->dbg_ev[l][5]);
+            const double* t = h->dbg_host_us;
+            fprintf(stderr, "[lvreg] host clock (ms after the call began): VoxelGrid batch entered %.3f, all chains enqueued %.3f, "
+                    "synchronised %.3f, batch left %.3f, grids enqueued %.3f, registration enqueued %.3f\n", (t[1] - t[0]) * 1e-3,
+                    (t[2] - t[0]) * 1e-3, (t[3] - t[0]) * 1e-3, (t[4] - t[0]) * 1e-3, (t[5] - t[0]) * 1e-3, (t[6] - t[0]) * 1e-3);
+            fprintf(stderr, "[lvreg] lanes idle at: map corner %.3f, map surf %.3f, scan corner %.3f, scan surf %.3f ms\n", e[0], e[1], e[2], e[3]);
         }
     }
     end_call(h);
@@ -2507,6 +2624,8 @@ int prepare_submap_job(lvreg_handle* h, const int32_t* ids, size_t n_ids, int wh
             sg.src = kf->cloud[s].as<float4>();
             sg.begin = (uint32_t)total;
             sg.n = kf->n[s];
+            sg.wkey = nullptr;
+            sg.kminb[0] = sg.kminb[1] = sg.kminb[2] = 0;
             pose_to_affine_host(kf->pose, sg.T.m);
             L.seg_host.push_back(sg);
             total += kf->n[s];
@@ -2638,7 +2757,7 @@ int lvreg_loop_find_near_keyframes(lvreg_handle* h, int key, int search_num, int
     lanes_fork(h, 1u << slot);
     CKS(voxelgrid_batch(h, &J, 1));
     lanes_join(h, 1u << slot);
-    mark(h, EV_MAP);
+    if (!h->ev_set[EV_MAP]) mark(h, EV_MAP);
     if (slot == 1) {
         CKS(build_icp_grids(h, J.n ? J.mn : nullptr, J.n ? J.mx : nullptr));
         lanes_join(h, 1u << slot);
@@ -2671,8 +2790,7 @@ int lvreg_build_global_map(lvreg_handle* h, const int32_t* ids, size_t n_ids, in
         CK(ms.ds.reserve((size_t)(J.n ? J.n : 1) * 16));
         if (J.n) {
             uint32_t* mm = L.small.as<uint32_t>() + SM_MM;
-            CK(L.segs.reserve(L.seg_host.size() * sizeof(Segment)));
-            CK(cudaMemcpyAsync(L.segs.p, L.seg_host.data(), L.seg_host.size() * sizeof(Segment), cudaMemcpyHostToDevice, h->st));
+            CKS(upload_segs(h, L, h->st));
             transform_concat_kernel<<<min(nblk(J.n, 2048), (uint32_t)h->num_sms * 16), 256, 0, h->st>>>(
                 L.segs.as<Segment>(), (uint32_t)L.seg_host.size(), J.n, ms.ds.as<float4>(), mm);
             launched(h);
@@ -2687,7 +2805,7 @@ int lvreg_build_global_map(lvreg_handle* h, const int32_t* ids, size_t n_ids, in
     lanes_fork(h, 0x1);
     CKS(voxelgrid_batch(h, &J, 1));
     lanes_join(h, 0x1);
-    mark(h, EV_MAP);
+    if (!h->ev_set[EV_MAP]) mark(h, EV_MAP);
     CK(cudaStreamSynchronize(h->st));
     h->icp_cloud[0].valid = true;                 // read back with lvreg_icp_get_cloud(h, 0, ...)
     h->last.map_build_ms = span(h, EV_BEGIN, EV_MAP);
@@ -2792,7 +2910,7 @@ int lvreg_perform_loop_closure(lvreg_handle* h, int key_cur, int key_pre, int se
     lanes_fork(h, 0x3);
     CKS(voxelgrid_batch(h, jobs, 2));
     lanes_join(h, 0x3);
-    mark(h, EV_MAP);
+    if (!h->ev_set[EV_MAP]) mark(h, EV_MAP);
     CKS(build_icp_grids(h, jobs[1].n ? jobs[1].mn : nullptr, jobs[1].n ? jobs[1].mx : nullptr));
     lanes_join(h, 0x2);
     mark(h, EV_GRID);
@@ -3167,6 +3285,29 @@ int lvreg_debug_tile_times(lvreg_handle* h, uint32_t* ns_out, size_t cap, size_t
     size_t n = *n_tiles < cap ? *n_tiles : cap;
     CK(cudaMemcpyAsync(ns_out, h->tilens.p, n * 4, cudaMemcpyDeviceToHost, h->st));
     CK(cudaStreamSynchronize(h->st));
+    return LVREG_OK;
+}
+
+int lvreg_enable_kernel_timing(lvreg_handle* h, int on) {
+    if (!h) return LVREG_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    if (on && !h->kt_ev[0][0])
+        for (int l = 0; l < 2; ++l)
+            for (int k = 0; k < 2; ++k) CK(cudaEventCreate(&h->kt_ev[l][k]));
+    h->kernel_timing = on != 0;
+    return LVREG_OK;
+}
+
+int lvreg_get_bucket_kernel_ms(lvreg_handle* h, float ms[2], uint32_t n_in[2], uint32_t n_out[2]) {
+    if (!h || !ms || !n_in || !n_out) return LVREG_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->st));
+    for (int l = 0; l < 2; ++l) {
+        ms[l] = 0.f;
+        n_in[l] = h->kt_set[l] ? h->kt_n_in[l] : 0u;
+        n_out[l] = h->kt_set[l] ? h->map[l].m : 0u;
+        if (h->kt_set[l]) CK(cudaEventElapsedTime(&ms[l], h->kt_ev[l][0], h->kt_ev[l][1]));
+    }
     return LVREG_OK;
 }
 

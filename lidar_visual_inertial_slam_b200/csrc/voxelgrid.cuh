@@ -98,6 +98,10 @@ struct Segment {                 // one selected keyframe cloud
     uint32_t begin;              // first index in the concatenated cloud
     uint32_t n;
     Affine T;                    // pclPointToAffine3f(cloudKeyPoses6D[id]), computed on the host
+    // voxel-ordered world-frame cache only (voxelgrid_bucket.cuh): per point its voxel coordinates relative to
+    // kminb, packed 11 | 11 | 10 bits (x | y | z)
+    const uint32_t* wkey;
+    int kminb[3];
 };
 
 __global__ void __launch_bounds__(256) transform_concat_kernel(const Segment* __restrict__ segs,

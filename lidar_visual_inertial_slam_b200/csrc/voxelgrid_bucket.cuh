@@ -43,6 +43,22 @@ __device__ __forceinline__ uint32_t voxel_key(const float4 p, const VoxelSpec& v
     return (uint32_t)(ix * vs.mul[0] + iy * vs.mul[1] + iz * vs.mul[2]);
 }
 
+// The cached clouds carry their voxel coordinates (relative to the keyframe's own bounds) in 4 bytes per point, so the
+// passes that only need keys -- samples, splitter search, the gather of a bucket -- read a quarter of the bytes and do
+// integer arithmetic only.  key under the map's bounds = lin(packed) + a constant of the run.
+constexpr int kVgbPackX = 11, kVgbPackY = 11, kVgbPackZ = 10;
+__device__ __forceinline__ uint32_t pack_ijk(int i, int j, int k) {
+    return (uint32_t)i | ((uint32_t)j << kVgbPackX) | ((uint32_t)k << (kVgbPackX + kVgbPackY));
+}
+__device__ __forceinline__ uint32_t packed_lin(uint32_t w, const VoxelSpec& vs) {
+    return (w & ((1u << kVgbPackX) - 1u)) * (uint32_t)vs.mul[0] + ((w >> kVgbPackX) & ((1u << kVgbPackY) - 1u)) * (uint32_t)vs.mul[1] +
+           (w >> (kVgbPackX + kVgbPackY)) * (uint32_t)vs.mul[2];
+}
+__device__ __forceinline__ uint32_t run_key_offset(const Segment& sg, const VoxelSpec& vs) {
+    return (uint32_t)((sg.kminb[0] - vs.min_b[0]) * vs.mul[0] + (sg.kminb[1] - vs.min_b[1]) * vs.mul[1] +
+                      (sg.kminb[2] - vs.min_b[2]) * vs.mul[2]);
+}
+
 // ---- cache fill: a keyframe cloud under its pose, ordered by voxel index ------------------------------------
 __global__ void __launch_bounds__(256) bbox_tf_kernel(const float4* __restrict__ in, uint32_t n, Affine T,
                                                       uint32_t* __restrict__ mm) {
@@ -68,12 +84,15 @@ __global__ void __launch_bounds__(256) voxel_keys_tf_kernel(const float4* __rest
 }
 
 __global__ void __launch_bounds__(256) gather_tf_kernel(const float4* __restrict__ in, const uint32_t* __restrict__ order,
-                                                        uint32_t n, Affine T, float4* __restrict__ out) {
+                                                        uint32_t n, Affine T, VoxelSpec vs, float4* __restrict__ out,
+                                                        uint32_t* __restrict__ wkey) {
     const uint32_t i = blockIdx.x * 256 + threadIdx.x;
     if (i >= n) return;
     const float4 p = in[order[i]];
     const float3 q = apply_affine(T, p.x, p.y, p.z);
     out[i] = make_float4(q.x, q.y, q.z, p.w);
+    wkey[i] = pack_ijk((int)(floorf(q.x * vs.inv) - (float)vs.min_b[0]), (int)(floorf(q.y * vs.inv) - (float)vs.min_b[1]),
+                       (int)(floorf(q.z * vs.inv) - (float)vs.min_b[2]));
 }
 
 // ---- splitters ---------------------------------------------------------------------------------------------
@@ -95,8 +114,8 @@ __global__ void __launch_bounds__(256) vgb_sample_kernel(const Segment* __restri
             const uint32_t mid = (lo + hi) >> 1;
             if (segs[mid].begin <= g) lo = mid; else hi = mid;
         }
-        const float4 p = __ldg(segs[lo].src + (g - segs[lo].begin));
-        const uint32_t key = voxel_key(p, vs);
+        const uint32_t key = segs[lo].wkey ? packed_lin(__ldg(segs[lo].wkey + (g - segs[lo].begin)), vs) + run_key_offset(segs[lo], vs)
+                                           : voxel_key(__ldg(segs[lo].src + (g - segs[lo].begin)), vs);
         raw[q] = key;
         keys[q] = key >> trunc_shift;
         vals[q] = q;
@@ -137,10 +156,12 @@ __global__ void __launch_bounds__(256) vgb_split_kernel(const Segment* __restric
         // the answer lies in (position of sample a-1, position of sample a]
         uint32_t lo = a > q0 ? (a - 1) * kVgbSample - begin + 1 : 0;
         uint32_t hi = a < q1 ? a * kVgbSample - begin : len;
-        const float4* src = segs[r].src;
+        const uint32_t* wk = segs[r].wkey;
+        const uint32_t koff = run_key_offset(segs[r], vs);
         while (lo < hi) {
             const uint32_t mid = (lo + hi) >> 1;
-            if (voxel_key(__ldg(src + mid), vs) < sp) lo = mid + 1; else hi = mid;
+            const uint32_t km = wk ? packed_lin(__ldg(wk + mid), vs) + koff : voxel_key(__ldg(segs[r].src + mid), vs);
+            if (km < sp) lo = mid + 1; else hi = mid;
         }
         res = lo;
     }
@@ -169,8 +190,8 @@ struct VgbArgs {
 constexpr int kVgbDigitBits = 9;                // 512 digits = one packed counter word per thread
 constexpr int kVgbDigits = 1 << kVgbDigitBits;
 constexpr size_t vgb_smem_bytes(uint32_t nseg) {
-    return (size_t)kVgbCap * 8 + (size_t)(kVgbThreads / 32) * kVgbDigits * 2 + (size_t)(nseg + 1) * 4 + (size_t)nseg * 4 +
-           (size_t)nseg * 8 + 64;
+    return (size_t)kVgbCap * 8 + (size_t)(kVgbThreads / 32) * kVgbDigits * 2 + (size_t)(nseg + 1) * 4 + (size_t)nseg * 8 +
+           (size_t)nseg * 16 + 64;
 }
 
 __global__ void __launch_bounds__(kVgbThreads, 4) vgb_bucket_kernel(VgbArgs a) {
@@ -184,8 +205,10 @@ __global__ void __launch_bounds__(kVgbThreads, 4) vgb_bucket_kernel(VgbArgs a) {
     uint16_t* seghead = &wcnt[0][0];                                                       // before the sort: [cap]
     uint16_t* vstart = &wcnt[0][0];                                                        // after the sort: [cap]
     const float4** segsrc = reinterpret_cast<const float4**>(&wcnt[WARPS][0]);            // [nseg]
-    uint32_t* segstart = reinterpret_cast<uint32_t*>(segsrc + a.nseg);                     // [nseg + 1]
+    const uint32_t** segkey = reinterpret_cast<const uint32_t**>(segsrc + a.nseg);         // [nseg] packed voxel coordinates
+    uint32_t* segstart = reinterpret_cast<uint32_t*>(segkey + a.nseg);                     // [nseg + 1]
     uint32_t* segbase = segstart + a.nseg + 1;                                             // [nseg]
+    uint32_t* segkoff = segbase + a.nseg;                                                  // [nseg] key offset of the run
     __shared__ uint32_t scan_ws[WARPS];
     __shared__ uint32_t nb_s, nv_s, inoff_s;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -208,6 +231,8 @@ __global__ void __launch_bounds__(kVgbThreads, 4) vgb_bucket_kernel(VgbArgs a) {
             before += s0;
             segbase[r] = s0;
             segsrc[r] = a.segs[r].src;
+            segkey[r] = a.segs[r].wkey;
+            segkoff[r] = run_key_offset(a.segs[r], a.vs);
         }
         const uint32_t inc = warp_inclusive_scan(len, lane);
         if (lane == 31) scan_ws[warp] = inc;
@@ -253,7 +278,8 @@ __global__ void __launch_bounds__(kVgbThreads, 4) vgb_bucket_kernel(VgbArgs a) {
     const int rounds = (int)((nb + kVgbThreads - 1) / kVgbThreads);          // <= kVgbItems
     const uint32_t wbase = (uint32_t)warp * (uint32_t)rounds * 32u;
 
-    // ---- gather: element e of the bucket = position (e - segstart[r]) of run r's slice; 8 loads in flight ----
+    // ---- gather: element e of the bucket = position (e - segstart[r]) of run r's slice; its key from the packed voxel
+    // coordinates (4 B per point; the points themselves are only read once, in sorted order, for the sums) ----
     if (wbase < nb) {
         uint32_t cur;                                              // run of the element before this warp's next round
         {
@@ -268,7 +294,7 @@ __global__ void __launch_bounds__(kVgbThreads, 4) vgb_bucket_kernel(VgbArgs a) {
         for (int g = 0; g < rounds; g += 8) {
             if (wbase + g * 32 >= nb) break;
             uint32_t pay[8];
-            float4 p[8];
+            uint32_t p[8], pk[8];
 #pragma unroll
             for (int r = 0; r < 8; ++r) {
                 const uint32_t e = wbase + (g + r) * 32 + lane;
@@ -284,7 +310,13 @@ __global__ void __launch_bounds__(kVgbThreads, 4) vgb_bucket_kernel(VgbArgs a) {
                     if (e < nb) {
                         const uint32_t off = segbase[run] + (e - segstart[run]);
                         pay[r] = (run << kSegShift) | off;
-                        p[r] = __ldg(segsrc[run] + off);
+                        if (segkey[run]) {
+                            p[r] = __ldg(segkey[run] + off);
+                            pk[r] = segkoff[run];
+                        } else {                                   // a run without packed coordinates: key from the point
+                            p[r] = 0u;
+                            pk[r] = voxel_key(__ldg(segsrc[run] + off), a.vs);
+                        }
                     }
                 }
             }
@@ -293,7 +325,7 @@ __global__ void __launch_bounds__(kVgbThreads, 4) vgb_bucket_kernel(VgbArgs a) {
                 const uint32_t e = wbase + (g + r) * 32 + lane;
                 if (g + r < rounds && wbase + (g + r) * 32 < nb) {
                     uint2 kv = make_uint2(0xffffffffu, 0u);            // padding sorts last
-                    if (e < nb) kv = make_uint2(voxel_key(p[r], a.vs) - key_lo, pay[r]);
+                    if (e < nb) kv = make_uint2(packed_lin(p[r], a.vs) + pk[r] - key_lo, pay[r]);
                     skv[e] = kv;
                 }
             }
@@ -313,6 +345,7 @@ __global__ void __launch_bounds__(kVgbThreads, 4) vgb_bucket_kernel(VgbArgs a) {
             if (r < rounds && wbase + r * 32 < nb) {                 // warp-uniform
                 kv[r] = skv[wbase + r * 32 + lane];
                 const uint32_t dg = (kv[r].x >> shift) & dmask;
+#ifdef LVREG_VGB_BALLOT
                 uint32_t peers = 0xffffffffu;
 #pragma unroll
                 for (int bb = 0; bb < kVgbDigitBits; ++bb) {
@@ -322,6 +355,9 @@ __global__ void __launch_bounds__(kVgbThreads, 4) vgb_bucket_kernel(VgbArgs a) {
                         peers &= bal ^ (bit ? 0u : 0xffffffffu);
                     }
                 }
+#else
+                const uint32_t peers = __match_any_sync(0xffffffffu, dg);
+#endif
                 const uint32_t lower = peers & lt_mask;
                 const uint32_t old = wcnt[warp][dg];
                 if (lower == 0) wcnt[warp][dg] = (uint16_t)(old + (uint32_t)__popc(peers));
@@ -460,34 +496,38 @@ __global__ void __launch_bounds__(kVgbThreads, 4) vgb_bucket_kernel(VgbArgs a) {
 __global__ void __launch_bounds__(1024) vgb_scan_kernel(uint32_t* __restrict__ bucket_nvox, uint32_t nbuckets,
                                                         uint32_t* __restrict__ info) {
     __shared__ uint32_t ws[32];
-    __shared__ uint32_t carry_s;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) carry_s = 0;
+    const uint32_t per = (nbuckets + 1023) / 1024;                 // consecutive values per thread
+    const uint32_t i0 = (uint32_t)tid * per;
+    uint32_t sum = 0;
+    for (uint32_t k = 0; k < per; ++k)
+        if (i0 + k < nbuckets) sum += bucket_nvox[i0 + k];
+    const uint32_t inc = warp_inclusive_scan(sum, lane);
+    if (lane == 31) ws[warp] = inc;
     __syncthreads();
-    for (uint32_t i0 = 0; i0 < nbuckets; i0 += 1024) {
-        const uint32_t i = i0 + tid;
-        const uint32_t v = i < nbuckets ? bucket_nvox[i] : 0u;
-        const uint32_t inc = warp_inclusive_scan(v, lane);
-        if (lane == 31) ws[warp] = inc;
-        __syncthreads();
-        uint32_t wpre = 0, tot = 0;
-        for (int w = 0; w < 32; ++w) {
-            const uint32_t s = ws[w];
-            if (w < warp) wpre += s;
-            tot += s;
-        }
-        const uint32_t carry = carry_s;
-        if (i < nbuckets) bucket_nvox[i] = carry + wpre + inc - v;
-        __syncthreads();
-        if (tid == 0) carry_s = carry + tot;
-        __syncthreads();
+    uint32_t wpre = 0, tot = 0;
+    for (int w = 0; w < 32; ++w) {
+        const uint32_t s = ws[w];
+        if (w < warp) wpre += s;
+        tot += s;
     }
-    if (tid == 0) { bucket_nvox[nbuckets] = carry_s; info[0] = carry_s; }
+    uint32_t run = wpre + inc - sum;
+    for (uint32_t k = 0; k < per; ++k)
+        if (i0 + k < nbuckets) {
+            const uint32_t v = bucket_nvox[i0 + k];
+            bucket_nvox[i0 + k] = run;
+            run += v;
+        }
+    if (tid == 0) { bucket_nvox[nbuckets] = tot; info[0] = tot; }
 }
 
 // out[offset of bucket b + v] = tmp[input offset of bucket b + v]
+// (launched BEFORE the host knows the total, into whatever the output buffer holds: does nothing if that is too small,
+// the host then repeats it after growing the buffer)
 __global__ void __launch_bounds__(128) vgb_compact_kernel(const float4* __restrict__ tmp, const uint32_t* __restrict__ bucket_out,
-                                                          const uint32_t* __restrict__ bucket_in, float4* __restrict__ out) {
+                                                          const uint32_t* __restrict__ bucket_in, uint32_t nbuckets,
+                                                          uint32_t out_capacity, float4* __restrict__ out) {
+    if (bucket_out[nbuckets] > out_capacity) return;
     const uint32_t b = blockIdx.x;
     const uint32_t o0 = bucket_out[b], nv = bucket_out[b + 1] - o0, i0 = bucket_in[b];
     for (uint32_t v = threadIdx.x; v < nv; v += 128) out[o0 + v] = tmp[i0 + v];
