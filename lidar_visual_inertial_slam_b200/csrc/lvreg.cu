@@ -131,7 +131,9 @@ struct Keyframe {
     bool world_ok = false;
     bool wsorted[2] = {false, false};   // world[s] is ordered by the voxel index of leaf wleaf[s] (voxelgrid_bucket.cuh)
     float wleaf[2] = {0.f, 0.f};
-    DevBuf wkey[2];                     // ... and the points' voxel coordinates relative to wminb, packed in 4 bytes
+    DevBuf wkey[2];                     // ... and (wpacked: when they fit 11 | 11 | 10 bits) the points' voxel coordinates relative
+                                        // to wminb, packed in 4 bytes
+    bool wpacked[2] = {false, false};
     int wminb[2][3] = {{0, 0, 0}, {0, 0, 0}};
     float wmn[2][3] = {{0, 0, 0}, {0, 0, 0}}, wmx[2][3] = {{0, 0, 0}, {0, 0, 0}};
 };
@@ -1075,12 +1077,14 @@ int ensure_world_cache(lvreg_handle* h, const int32_t* ids, size_t n_ids) {
                     const uint32_t n = kf->n[s];
                     if (n == 0) continue;
                     VoxelSpec vs;
-                    bool ok = leaf[s] > 0.f && voxel_spec_from_bbox(kf->wmn[s], kf->wmx[s], leaf[s], &vs);
-                    if (ok) {                                    // the packed voxel coordinates have 11 | 11 | 10 bits
+                    const bool ok = leaf[s] > 0.f && voxel_spec_from_bbox(kf->wmn[s], kf->wmx[s], leaf[s], &vs);
+                    bool packs = false;                          // the packed voxel coordinates have 11 | 11 | 10 bits
+                    if (ok) {
                         const int dxk = vs.mul[1], dyk = vs.mul[1] ? vs.mul[2] / vs.mul[1] : 0;
                         const int dzk = (int)floorf(kf->wmx[s][2] * vs.inv) - vs.min_b[2] + 1;
-                        ok = dxk <= (1 << kVgbPackX) && dyk <= (1 << kVgbPackY) && dzk <= (1 << kVgbPackZ);
+                        packs = dxk <= (1 << kVgbPackX) && dyk <= (1 << kVgbPackY) && dzk <= (1 << kVgbPackZ);
                     }
+                    kf->wpacked[s] = false;
                     if (!ok) {                                   // cannot be ordered with 32-bit keys: cached as it is
                         transform_kernel<<<nblk(n, 256), 256, 0, h->st>>>(kf->cloud[s].as<float4>(), n, T, kf->world[s].as<float4>());
                         launched(h);
@@ -1093,9 +1097,11 @@ int ensure_world_cache(lvreg_handle* h, const int32_t* ids, size_t n_ids) {
                     const int cur = radix_sort_pairs(L.keys[0].as<uint32_t>(), L.vals[0].as<uint32_t>(), L.keys[1].as<uint32_t>(),
                                                      L.vals[1].as<uint32_t>(), n, vs.key_bits, L.sort_scratch.as<uint32_t>(), h->st,
                                                      &h->call_launches);
-                    CK(kf->wkey[s].reserve((size_t)n * 4));
+                    if (packs) CK(kf->wkey[s].reserve((size_t)n * 4));
                     gather_tf_kernel<<<nblk(n, 256), 256, 0, h->st>>>(kf->cloud[s].as<float4>(), L.vals[cur].as<uint32_t>(), n, T, vs,
-                                                                      kf->world[s].as<float4>(), kf->wkey[s].as<uint32_t>());
+                                                                      kf->world[s].as<float4>(),
+                                                                      packs ? kf->wkey[s].as<uint32_t>() : nullptr);
+                    kf->wpacked[s] = packs;
                     launched(h);
                     for (int a = 0; a < 3; ++a) kf->wminb[s][a] = vs.min_b[a];
                     kf->wsorted[s] = true;
@@ -1145,7 +1151,7 @@ int prepare_map_jobs(lvreg_handle* h, const int32_t* ids, size_t n_ids, VgJob* j
             sg.src = cached[s] ? kf->world[s].as<float4>() : kf->cloud[s].as<float4>();
             sg.begin = (uint32_t)total;
             sg.n = kf->n[s];
-            sg.wkey = cached[s] && kf->wsorted[s] && !h->dbg_nowkey ? kf->wkey[s].as<uint32_t>() : nullptr;
+            sg.wkey = cached[s] && kf->wsorted[s] && kf->wpacked[s] && !h->dbg_nowkey ? kf->wkey[s].as<uint32_t>() : nullptr;
             for (int a = 0; a < 3; ++a) sg.kminb[a] = kf->wminb[s][a];
             if (cached[s]) memset(&sg.T, 0, sizeof(sg.T));   // world-frame cloud: no transform
             else pose_to_affine_host(kf->pose, sg.T.m);      // pclPointToAffine3f(cloudKeyPoses6D[id])

@@ -44,8 +44,8 @@ __device__ __forceinline__ uint32_t voxel_key(const float4 p, const VoxelSpec& v
 }
 
 // The cached clouds carry their voxel coordinates (relative to the keyframe's own bounds) in 4 bytes per point, so the
-// passes that only need keys -- samples, splitter search, the gather of a bucket -- read a quarter of the bytes and do
-// integer arithmetic only.  key under the map's bounds = lin(packed) + a constant of the run.
+// passes that only need keys -- the samples and the splitter search, which probes every 10th point of the input --
+// read a quarter of the bytes and do integer arithmetic only (split kernel: 45 -> 15 us at C3).  key under the map's bounds = lin(packed) + a constant of the run.
 constexpr int kVgbPackX = 11, kVgbPackY = 11, kVgbPackZ = 10;
 __device__ __forceinline__ uint32_t pack_ijk(int i, int j, int k) {
     return (uint32_t)i | ((uint32_t)j << kVgbPackX) | ((uint32_t)k << (kVgbPackX + kVgbPackY));
@@ -91,7 +91,8 @@ __global__ void __launch_bounds__(256) gather_tf_kernel(const float4* __restrict
     const float4 p = in[order[i]];
     const float3 q = apply_affine(T, p.x, p.y, p.z);
     out[i] = make_float4(q.x, q.y, q.z, p.w);
-    wkey[i] = pack_ijk((int)(floorf(q.x * vs.inv) - (float)vs.min_b[0]), (int)(floorf(q.y * vs.inv) - (float)vs.min_b[1]),
+    if (wkey)
+        wkey[i] = pack_ijk((int)(floorf(q.x * vs.inv) - (float)vs.min_b[0]), (int)(floorf(q.y * vs.inv) - (float)vs.min_b[1]),
                        (int)(floorf(q.z * vs.inv) - (float)vs.min_b[2]));
 }
 
@@ -190,8 +191,8 @@ struct VgbArgs {
 constexpr int kVgbDigitBits = 9;                // 512 digits = one packed counter word per thread
 constexpr int kVgbDigits = 1 << kVgbDigitBits;
 constexpr size_t vgb_smem_bytes(uint32_t nseg) {
-    return (size_t)kVgbCap * 8 + (size_t)(kVgbThreads / 32) * kVgbDigits * 2 + (size_t)(nseg + 1) * 4 + (size_t)nseg * 8 +
-           (size_t)nseg * 16 + 64;
+    return (size_t)kVgbCap * 8 + (size_t)(kVgbThreads / 32) * kVgbDigits * 2 + (size_t)(nseg + 1) * 4 + (size_t)nseg * 4 +
+           (size_t)nseg * 8 + 64;
 }
 
 __global__ void __launch_bounds__(kVgbThreads, 4) vgb_bucket_kernel(VgbArgs a) {
@@ -205,10 +206,8 @@ __global__ void __launch_bounds__(kVgbThreads, 4) vgb_bucket_kernel(VgbArgs a) {
     uint16_t* seghead = &wcnt[0][0];                                                       // before the sort: [cap]
     uint16_t* vstart = &wcnt[0][0];                                                        // after the sort: [cap]
     const float4** segsrc = reinterpret_cast<const float4**>(&wcnt[WARPS][0]);            // [nseg]
-    const uint32_t** segkey = reinterpret_cast<const uint32_t**>(segsrc + a.nseg);         // [nseg] packed voxel coordinates
-    uint32_t* segstart = reinterpret_cast<uint32_t*>(segkey + a.nseg);                     // [nseg + 1]
+    uint32_t* segstart = reinterpret_cast<uint32_t*>(segsrc + a.nseg);                     // [nseg + 1]
     uint32_t* segbase = segstart + a.nseg + 1;                                             // [nseg]
-    uint32_t* segkoff = segbase + a.nseg;                                                  // [nseg] key offset of the run
     __shared__ uint32_t scan_ws[WARPS];
     __shared__ uint32_t nb_s, nv_s, inoff_s;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -231,8 +230,6 @@ __global__ void __launch_bounds__(kVgbThreads, 4) vgb_bucket_kernel(VgbArgs a) {
             before += s0;
             segbase[r] = s0;
             segsrc[r] = a.segs[r].src;
-            segkey[r] = a.segs[r].wkey;
-            segkoff[r] = run_key_offset(a.segs[r], a.vs);
         }
         const uint32_t inc = warp_inclusive_scan(len, lane);
         if (lane == 31) scan_ws[warp] = inc;
@@ -278,8 +275,9 @@ __global__ void __launch_bounds__(kVgbThreads, 4) vgb_bucket_kernel(VgbArgs a) {
     const int rounds = (int)((nb + kVgbThreads - 1) / kVgbThreads);          // <= kVgbItems
     const uint32_t wbase = (uint32_t)warp * (uint32_t)rounds * 32u;
 
-    // ---- gather: element e of the bucket = position (e - segstart[r]) of run r's slice; its key from the packed voxel
-    // coordinates (4 B per point; the points themselves are only read once, in sorted order, for the sums) ----
+    // ---- gather: element e of the bucket = position (e - segstart[r]) of run r's slice; its key from the point itself
+    // (reading the 4-byte packed coordinates here instead was measured 5 % slower for the kernel: the second read of the
+    // points, in sorted order, then misses L2) ----
     if (wbase < nb) {
         uint32_t cur;                                              // run of the element before this warp's next round
         {
@@ -294,7 +292,7 @@ __global__ void __launch_bounds__(kVgbThreads, 4) vgb_bucket_kernel(VgbArgs a) {
         for (int g = 0; g < rounds; g += 8) {
             if (wbase + g * 32 >= nb) break;
             uint32_t pay[8];
-            uint32_t p[8], pk[8];
+            float4 p[8];
 #pragma unroll
             for (int r = 0; r < 8; ++r) {
                 const uint32_t e = wbase + (g + r) * 32 + lane;
@@ -310,13 +308,7 @@ __global__ void __launch_bounds__(kVgbThreads, 4) vgb_bucket_kernel(VgbArgs a) {
                     if (e < nb) {
                         const uint32_t off = segbase[run] + (e - segstart[run]);
                         pay[r] = (run << kSegShift) | off;
-                        if (segkey[run]) {
-                            p[r] = __ldg(segkey[run] + off);
-                            pk[r] = segkoff[run];
-                        } else {                                   // a run without packed coordinates: key from the point
-                            p[r] = 0u;
-                            pk[r] = voxel_key(__ldg(segsrc[run] + off), a.vs);
-                        }
+                        p[r] = __ldg(segsrc[run] + off);
                     }
                 }
             }
@@ -325,7 +317,7 @@ __global__ void __launch_bounds__(kVgbThreads, 4) vgb_bucket_kernel(VgbArgs a) {
                 const uint32_t e = wbase + (g + r) * 32 + lane;
                 if (g + r < rounds && wbase + (g + r) * 32 < nb) {
                     uint2 kv = make_uint2(0xffffffffu, 0u);            // padding sorts last
-                    if (e < nb) kv = make_uint2(packed_lin(p[r], a.vs) + pk[r] - key_lo, pay[r]);
+                    if (e < nb) kv = make_uint2(voxel_key(p[r], a.vs) - key_lo, pay[r]);
                     skv[e] = kv;
                 }
             }
@@ -339,11 +331,14 @@ __global__ void __launch_bounds__(kVgbThreads, 4) vgb_bucket_kernel(VgbArgs a) {
         uint2 kv[kVgbItems];
         uint16_t rank[kVgbItems];
         for (int j = lane; j <= (int)(dmask >> 1); j += 32) wcnt2[warp][j] = 0;
-        __syncwarp();
+        // the loads, then the matches, then the counter chain: the 16 loads and the 16 matches of a thread are
+        // independent and overlap; only the chain through the warp's counters is sequential
+#pragma unroll
+        for (int r = 0; r < kVgbItems; ++r)
+            if (r < rounds && wbase + r * 32 < nb) kv[r] = skv[wbase + r * 32 + lane];
 #pragma unroll
         for (int r = 0; r < kVgbItems; ++r) {
             if (r < rounds && wbase + r * 32 < nb) {                 // warp-uniform
-                kv[r] = skv[wbase + r * 32 + lane];
                 const uint32_t dg = (kv[r].x >> shift) & dmask;
 #ifdef LVREG_VGB_BALLOT
                 uint32_t peers = 0xffffffffu;
@@ -358,11 +353,20 @@ __global__ void __launch_bounds__(kVgbThreads, 4) vgb_bucket_kernel(VgbArgs a) {
 #else
                 const uint32_t peers = __match_any_sync(0xffffffffu, dg);
 #endif
-                const uint32_t lower = peers & lt_mask;
+                // lanes before this one with the same digit (5 bits) | size of the group (6 bits)
+                rank[r] = (uint16_t)((uint32_t)__popc(peers & lt_mask) | ((uint32_t)__popc(peers) << 8));
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < kVgbItems; ++r) {
+            if (r < rounds && wbase + r * 32 < nb) {
+                const uint32_t dg = (kv[r].x >> shift) & dmask;
+                const uint32_t lower = rank[r] & 0xffu;
                 const uint32_t old = wcnt[warp][dg];
-                if (lower == 0) wcnt[warp][dg] = (uint16_t)(old + (uint32_t)__popc(peers));
+                if (lower == 0) wcnt[warp][dg] = (uint16_t)(old + (rank[r] >> 8));
                 __syncwarp();
-                rank[r] = (uint16_t)(old + __popc(lower));
+                rank[r] = (uint16_t)(old + lower);
             }
         }
         __syncthreads();

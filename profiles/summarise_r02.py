@@ -36,7 +36,12 @@ if os.path.exists(csvp):
     body = [l for l in lines[hdr_i + 1:] if l.strip()]
     last_fill = max([i for i, l in enumerate(body) if "gather_tf_kernel" in l or "bbox_tf_kernel" in l] + [-1])
     steady = os.path.join(P, "r02_launches_bench_c3.csv")
-    open(steady, "w").write("\n".join(lines[:hdr_i + 1] + body[last_fill + 1:]) + "\n")
+    # ... and drop the radix-sort micro-benchmark bench.py runs after the timed steps (roofline_sort_pass: 8192-pair tiles,
+    # which no step of this workload launches any more)
+    keep = [l for l in body[last_fill + 1:] if "rs_onesweep_kernel<512>" not in l and "bench_fill_kernel" not in l and
+            "rs_global_hist_kernel" not in l]
+    open(steady, "w").write("\n".join(lines[:hdr_i + 1] + keep) + "\n")
+    body = body[:last_fill + 1] + keep
     out = subprocess.run([sys.executable, os.path.join(P, "launch_summary.py"), steady], capture_output=True, text=True).stdout
     head = ("launch list summary of `bench.py --steps 2 --warmup 1 --no-cpu-baseline --sustain-seconds 0` (ncu --metrics "
             "gpu__time_duration.sum --clock-control none; the %d launches after the one-time keyframe-cache fill of %d launches; "
