@@ -735,8 +735,8 @@ int voxelgrid_batch(lvreg_handle* h, VgJob* jobs, int nj) {
     // local-map jobs: the filters end here for the stage timings (the host's synchronisation below and what it enqueues
     // afterwards belong to the grid stage)
     {
-        bool any = false;
-        for (int j = 0; j < nj; ++j) any = any || jobs[j].mark_map_stage;
+        bool any = false;            // only where the filter is a long chain: small maps do not pay for the extra join
+        for (int j = 0; j < nj; ++j) any = any || (jobs[j].mark_map_stage && jobs[j].bucket_enqueued);
         if (any && !h->ev_set[EV_MAP]) {
             lanes_join(h, mask);
             mark(h, EV_MAP);

@@ -84,3 +84,16 @@ for rep, txt, traffic, pairs_key in (("r02_ncu_register.ncu-rep", "r02_ncu_regis
                    duration_us=vals.get("gpu__time_duration.sum"), source="ncu --set full --clock-control none, one launch (" + rep + ")"),
               open(os.path.join(P, traffic), "w"), indent=1)
     print(txt, "dram R %.1f MB W %.1f MB" % (rd / 1e6, wr / 1e6))
+
+# the bench line was printed before these captures existed on the box: fill its `traffic` fields from them
+b3p = os.path.join(P, "r02_bench_c3.json")
+if os.path.exists(b3p):
+    b3 = json.load(open(b3p))
+    for key, tf, nkey in (("roofline", "r02_register_kernel_traffic.json", "queries"), ("roofline_map_build_kernel", "r02_bucket_kernel_traffic.json", "points"),
+                          ("roofline_sort_pass", "r02_sort_kernel_traffic.json", "pairs")):
+        tp = os.path.join(P, tf)
+        if key in b3 and b3[key] and os.path.exists(tp):
+            t = json.load(open(tp))
+            b3[key]["traffic"] = t.get("dram_bytes_per_launch")
+            b3[key]["traffic_source"] = "profiles/" + tf
+    json.dump(b3, open(b3p, "w"), indent=1)
