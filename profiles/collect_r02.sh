@@ -23,7 +23,7 @@ timeout 300 python profiles/ncu_reg.py c3 3 > $O/r02_plain_reg.log 2>&1 && \
     python profiles/ncu_reg.py c3 3 > $O/r02_ncu_register.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:vgb_bucket_kernel -s 2 -c 1 -o $O/r02_ncu_bucket -f \
     python profiles/ncu_reg.py c3 3 > $O/r02_ncu_bucket.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:.*rs_onesweep_kernel<512>.*" -s 8 -c 1 -o $O/r02_ncu_sort_new -f \
+timeout 600 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:.*rs_onesweep_kernel<.int.512>.*" -s 8 -c 1 -o $O/r02_ncu_sort_new -f \
     python bench.py --steps 1 --warmup 1 --no-cpu-baseline --sustain-seconds 0 > $O/r02_ncu_sort.log 2>&1
 [ -s $O/r02_ncu_sort_new.ncu-rep ] && mv $O/r02_ncu_sort_new.ncu-rep $O/r02_ncu_sort.ncu-rep
 ls -la $O | grep r02_ | head -40
