@@ -7,7 +7,9 @@ memory) against the CPU restatement: bit-exact maps, in PCL's output order, for
   * a forced bucket overflow (LVREG_VG_BUCKET_CAP) -> the job is redone by the device-wide sort,
   * the device-wide sort on the same (voxel-ordered) cache (LVREG_VG_BUCKET=0),
   * corrected keyframe poses (correctPoses, MO:1607-1640: the cache is dropped and rebuilt),
-  * a growing map (keyframes added between builds).
+  * a growing map (keyframes added between builds),
+  * more keyframes than threads of a bucket block (segment table built in several rounds), some of them without
+    corner points, one of them a single point.
 """
 import numpy as np
 import pytest
@@ -153,4 +155,24 @@ def test_corrected_poses_and_growing_map(lv):
     _, gc, gs = _device_maps(lv, h, 16)
     assert np.array_equal(gc, oc) and np.array_equal(gs, os_)
     assert h.debug_stage_stats()[6] == 0
+    h.close()
+
+
+def test_many_small_keyframes(lv):
+    rng = np.random.default_rng(6)
+    kfs = []
+    for i in range(700):
+        pose = np.array([rng.uniform(-0.03, 0.03), rng.uniform(-0.03, 0.03), rng.uniform(-3.1, 3.1),
+                         rng.uniform(-8, 8), rng.uniform(-8, 8), rng.uniform(-0.2, 0.2)], np.float32)
+        nc = 0 if i % 7 == 3 else 420 + int(rng.integers(0, 60))
+        ns = 1 if i == 11 else 800 + int(rng.integers(0, 200))
+        c = _room_cloud(rng, nc) if nc else np.zeros((0, 4), np.float32)
+        kfs.append((c, _room_cloud(rng, ns), pose))
+    oc, os_ = _oracle_maps(kfs)
+    h = _fill(lv, kfs)
+    info, gc, gs = _device_maps(lv, h, len(kfs))
+    assert info.n_corner_in > 262144 and info.n_surf_in > 262144
+    assert np.array_equal(gc, oc) and np.array_equal(gs, os_)
+    st = h.debug_stage_stats()
+    assert st[7] == 2 and st[6] == 0, st
     h.close()
