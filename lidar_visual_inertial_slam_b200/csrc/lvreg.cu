@@ -200,7 +200,7 @@ struct lvreg_handle {
     bool vg_cached_first = false;   // LVREG_VG_CACHED_FIRST=1: enqueue the whole chain of the cached (map) jobs before the scan lanes
                                     // (measured slower at C3: the scan filters then compete with the bucket kernel instead of
                                     // overlapping the latency-bound sample sort)
-    bool dbg_no_precompact = false, dbg_nowkey = false, dbg_reverse = false, dbg_dealt = false, dbg_alloc = false;   // LVREG_DEBUG_* experiments
+    bool dbg_nowkey = false, dbg_dealt = false, dbg_alloc = false;   // LVREG_DEBUG_NOWKEY / LVREG_DEALT / LVREG_DEBUG_ALLOC
     uint32_t vg_bucket_cap = 0;     // LVREG_VG_BUCKET_CAP: smaller bucket capacity, to exercise the overflow fallback
     uint32_t vg_bucket_fallbacks = 0, vg_bucket_jobs = 0;
     bool kernel_timing = false;        // lvreg_enable_kernel_timing: event pairs around the bucket kernels of a call
@@ -485,7 +485,6 @@ int voxelgrid_batch(lvreg_handle* h, VgJob* jobs, int nj) {
     for (int a2 = 0; a2 < nj; ++a2)
         for (int b2 = a2 + 1; b2 < nj; ++b2)
             if (jobs[order[b2]].n > jobs[order[a2]].n) { int t2 = order[a2]; order[a2] = order[b2]; order[b2] = t2; }
-    if (h->dbg_reverse) { for (int a2 = 0; a2 < nj / 2; ++a2) { int t2 = order[a2]; order[a2] = order[nj - 1 - a2]; order[nj - 1 - a2] = t2; } }
     // Two rounds: the jobs over cached world-frame clouds first -- they depend on nothing, and the largest of them is the
     // critical path of the call, so their whole chain is enqueued before the host spends time on the other lanes --
     // then the rest, which share the bounding-box synchronisation.
@@ -692,7 +691,6 @@ int voxelgrid_batch(lvreg_handle* h, VgJob* jobs, int nj) {
             // the slices are closed up right away (below, after every chain is enqueued) if the output buffer of the
             // previous build is, as usual, large enough
             J.compact_cap = (uint32_t)std::min<size_t>(J.out->cap / 16, 0xffffffffu);
-            if (h->dbg_no_precompact) J.compact_cap = 0;
             J.bucket_enqueued = true;
             continue;
         }
@@ -1537,15 +1535,9 @@ int lvreg_create(const lvreg_params* p, int device, void* cuda_stream, lvreg_han
     }
     if (cudaMallocHost(&h->pinned, 65536) != cudaSuccess) return bail(LVREG_ERR_CUDA);
     if (cudaEventCreateWithFlags(&h->ev_main, cudaEventDisableTiming) != cudaSuccess) return bail(LVREG_ERR_CUDA);
-    if (const char* se = getenv("LVREG_DEBUG_STREAM_SHIFT"))       // experiments: dummy streams created ahead of the lanes
-        for (int i = 0; i < atoi(se); ++i) { cudaStream_t d; cudaStreamCreateWithFlags(&d, cudaStreamNonBlocking); }
     for (int l = 0; l < kLanes; ++l) {
         Lane& L = h->lane[l];
-        int prio_lo = 0, prio_hi = 0;
-        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
-        const char* pe = getenv("LVREG_LANE_PRIO");                  // experiments: bit l set = lane l gets the high priority
-        const int prio = pe && ((atoi(pe) >> l) & 1) ? prio_hi : prio_lo;
-        if (cudaStreamCreateWithPriority(&L.st, cudaStreamNonBlocking, prio) != cudaSuccess ||
+        if (cudaStreamCreateWithFlags(&L.st, cudaStreamNonBlocking) != cudaSuccess ||
             cudaEventCreateWithFlags(&L.ev, cudaEventDisableTiming) != cudaSuccess ||
             L.small.reserve(SM_WORDS * 4) != cudaSuccess)
             return bail(LVREG_ERR_CUDA);
@@ -1592,9 +1584,7 @@ int lvreg_create(const lvreg_params* p, int device, void* cuda_stream, lvreg_han
     if (e) h->vg_mid_enabled = atoi(e) != 0;
     e = getenv("LVREG_VG_BUCKET");
     if (e) h->vg_bucket_enabled = atoi(e) != 0;
-    h->dbg_no_precompact = getenv("LVREG_DEBUG_NO_PRECOMPACT") != nullptr;
     h->dbg_nowkey = getenv("LVREG_DEBUG_NOWKEY") != nullptr;
-    h->dbg_reverse = getenv("LVREG_DEBUG_REVERSE") != nullptr;
     h->dbg_dealt = getenv("LVREG_DEALT") != nullptr;
     h->dbg_alloc = getenv("LVREG_DEBUG_ALLOC") != nullptr;
     e = getenv("LVREG_VG_CACHED_FIRST");
