@@ -97,10 +97,11 @@ __global__ void __launch_bounds__(256) gather_tf_kernel(const float4* __restrict
 }
 
 // ---- splitters ---------------------------------------------------------------------------------------------
-// Sample q = the point at position q * kVgbSample of the concatenation.  Its full key goes to `raw` (the split
-// kernel searches the samples of a run before it touches the run); the copy that is sorted is truncated to its top 24
-// bits (three 8-bit passes instead of four: splitters only have to balance the buckets, any monotone sequence of keys
-// is a valid partition).  The digit histograms of the sort are accumulated here.
+// Sample q = the point at position q * kVgbSample of the concatenation.  Its key goes to `raw` in input order (the
+// split kernel searches the samples of a run before it touches the run) and to the array that is sorted; the digit
+// histograms of the sort are accumulated here.  `trunc_shift` drops low key bits from the sorted copy (one sort pass
+// less for keys of more than 24 bits): the host passes 0 -- with truncated keys a block of 16 consecutive voxel indices
+// cannot be split, and at C3 such a block holds up to 4 k points, which overflowed the buckets.
 __global__ void __launch_bounds__(256) vgb_sample_kernel(const Segment* __restrict__ segs, uint32_t nseg, uint32_t nsamp,
                                                          VoxelSpec vs, int trunc_shift, int passes,
                                                          uint32_t* __restrict__ raw, uint32_t* __restrict__ keys,
